@@ -1,0 +1,357 @@
+// HBM-bound kernels around the two tensor-core GEMMs: lattice phase transforms (k2R / R2k), batched transposes,
+// symmetrise + pack + transpose of the 3-index tensor, s4 -> s1 / s8 re-layouts, triangle mirror, J/K contraction,
+// k-point reduction and the synthetic GDF generator.  All are coalesced, grid-sized streaming kernels; the
+// reference routines each one replaces are cited per kernel (paths relative to /root/reference).
+#pragma once
+#include "common.cuh"
+
+namespace ldm {
+
+// ----------------------------------------------------------------------------------------------------------
+// Lattice Fourier transform as a dense phase-matrix product (Nk <= a few hundred):
+//     out[b][k][x] = scale * sum_R W[k][R] * in[b][R][x]
+// Replaces scipy fftn/ifftn in libdmet/system/fourier.py:160-177 (FFTtoK / FFTtoT) and the einsum of
+// eri_transform.py:125 (get_basis_k).  in may be real (in_real) and out may keep only the real part (out_real,
+// k2R returns .real, fourier.py:157); max|imag| of the discarded part is accumulated into *imag_max
+// (the reference warns when it exceeds IMAG_DISCARD_TOL, fourier.py:174-175).
+// Each thread owns one x and KT output k's; the phase matrix sits in shared memory.
+// ----------------------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(128)
+phase_transform_kernel(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ W,
+                       int nin, int nout, long long X, double scale, int in_real, int out_real,
+                       unsigned long long* imag_max) {
+    extern __shared__ double2 sW[];   // [KT][nin]
+    const int k0 = blockIdx.y * KT;
+    for (int idx = threadIdx.x; idx < KT * nin; idx += blockDim.x) {
+        const int kk = idx / nin, r = idx - kk * nin;
+        sW[idx] = (k0 + kk < nout) ? W[(size_t)(k0 + kk) * nin + r] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t bin = (size_t)blockIdx.z * nin * X;
+    const size_t bout = (size_t)blockIdx.z * nout * X;
+    double accr[KT], acci[KT];
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) accr[kk] = acci[kk] = 0.0;
+    if (x < X) {
+        for (int r = 0; r < nin; ++r) {
+            double vr, vi;
+            if (in_real) {
+                vr = in[bin + (size_t)r * X + x];
+                vi = 0.0;
+            } else {
+                const double2 v = reinterpret_cast<const double2*>(in)[bin + (size_t)r * X + x];
+                vr = v.x;
+                vi = v.y;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KT; ++kk) {
+                const double2 w = sW[kk * nin + r];
+                accr[kk] = fma(w.x, vr, accr[kk]);
+                accr[kk] = fma(-w.y, vi, accr[kk]);
+                acci[kk] = fma(w.x, vi, acci[kk]);
+                acci[kk] = fma(w.y, vr, acci[kk]);
+            }
+        }
+    }
+    double im_max = 0.0;
+    if (x < X) {
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+            if (k0 + kk >= nout) break;
+            const double re = accr[kk] * scale, im = acci[kk] * scale;
+            if (out_real) {
+                out[bout + (size_t)(k0 + kk) * X + x] = re;
+                im_max = fmax(im_max, fabs(im));
+            } else {
+                reinterpret_cast<double2*>(out)[bout + (size_t)(k0 + kk) * X + x] = make_double2(re, im);
+            }
+        }
+    }
+    if (out_real && imag_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) im_max = fmax(im_max, __shfl_xor_sync(0xffffffffu, im_max, o));
+        if ((threadIdx.x & 31) == 0 && im_max > 0.0) atomicMax(imag_max, (unsigned long long)__double_as_longlong(im_max));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Batched complex transpose with optional conjugation and real scale:  out[b][c][r] = scale * op(in[b][r][c]).
+// Used to lay coefficient matrices out with the contraction index contiguous for the TN GEMM.
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ztranspose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int rows, int cols, int conj,
+                  double scale) {
+    __shared__ double2 tile[32][33];
+    const size_t boff = (size_t)blockIdx.z * rows * cols;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += 8) {
+        const int r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[dy][threadIdx.x] = in[boff + (size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += 8) {
+        const int c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            double2 v = tile[threadIdx.x][dy];
+            v.x *= scale;
+            v.y *= conj ? -scale : scale;
+            out[boff + (size_t)c * rows + r] = v;
+        }
+    }
+}
+
+// real -> complex widening copy (basis in R-space is real; the GEMM operands are complex)
+__global__ void d2z_kernel(const double* __restrict__ in, double2* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_double2(in[i], 0.0);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Symmetrise + pack + transpose of the accumulated embedding-orbital 3-index tensor of one transfer momentum.
+//   S_sym [L][x][y]  : sum over the blocks the reference symmetrises (hermi_sum SYMMETRIC, eri_transform.py:371-373)
+//   S_pln [L][n][m]  : sum over the blocks it does not, stored transposed, S_pln[L][n][m] = T[L][m][n]
+//   Lambda[L, tri(m,n)] = S_sym[L][m][n] + S_sym[L][n][m] + S_pln[L][n][m]     (m >= n; pack_tril, l.375)
+// Output goes K-contiguous for the stage-3 GEMM:  XT[P][col_re + L] = Re Lambda, XT[P][col_im + L] = Im Lambda.
+// One CTA handles a 16x16 (m, n) tile for 16 consecutive L: reads are 256-byte rows, writes are 128-byte rows.
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_sym_kernel(const double2* __restrict__ S_sym, const double2* __restrict__ S_pln, double* __restrict__ XT,
+                int naux, int neo, long long ldx, long long col_re, long long col_im) {
+    extern __shared__ double2 v_raw[];
+    double2 (*v)[16][17] = reinterpret_cast<double2 (*)[16][17]>(v_raw);   // [L][m][n]
+    const int tm = blockIdx.x, tn = blockIdx.y;
+    if (tn > tm) return;
+    const int L0 = blockIdx.z * 16;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const size_t n2 = (size_t)neo * neo;
+    for (int l = 0; l < 16; ++l) {
+        const int L = L0 + l;
+        double2 acc = make_double2(0.0, 0.0);
+        const int m = tm * 16 + ty, n = tn * 16 + tx;      // contiguous reads along n:  S[L][m][n]
+        const int m2 = tm * 16 + tx, n2i = tn * 16 + ty;    // contiguous reads along m:  S[L][n][m]
+        double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+        if (L < naux) {
+            if (S_sym && m < neo && n < neo) a = S_sym[(size_t)L * n2 + (size_t)m * neo + n];
+            if (m2 < neo && n2i < neo) {
+                if (S_sym) { const double2 q = S_sym[(size_t)L * n2 + (size_t)n2i * neo + m2]; b.x += q.x; b.y += q.y; }
+                if (S_pln) { const double2 q = S_pln[(size_t)L * n2 + (size_t)n2i * neo + m2]; b.x += q.x; b.y += q.y; }
+            }
+        }
+        v[l][ty][tx] = a;                 // (m = ty, n = tx)
+        __syncthreads();
+        // add the transposed-read contribution: element (m = tx, n = ty) was read by this thread as b
+        acc = v[l][tx][ty];
+        __syncthreads();
+        acc.x += b.x;
+        acc.y += b.y;
+        v[l][tx][ty] = acc;
+    }
+    __syncthreads();
+    // write: 16 pairs per pass, 16 L each (128-byte rows of XT)
+    const int l = threadIdx.x & 15;
+    for (int pp = threadIdx.x >> 4; pp < 256; pp += 16) {
+        const int mi = pp >> 4, ni = pp & 15;
+        const int m = tm * 16 + mi, n = tn * 16 + ni;
+        if (m >= neo || n > m || L0 + l >= naux) continue;
+        const long long P = (long long)m * (m + 1) / 2 + n;
+        const double2 val = v[l][mi][ni];
+        XT[P * ldx + col_re + L0 + l] = val.x;
+        if (col_im >= 0) XT[P * ldx + col_im + L0 + l] = val.y;
+    }
+}
+
+// zero-fill columns [c0, c1) of the rows of XT (K-padding so stale data never enters a Gram product)
+__global__ void fill_cols_kernel(double* __restrict__ XT, long long rows, long long ldx, long long c0, long long c1) {
+    const long long w = c1 - c0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * w;
+         i += (long long)gridDim.x * blockDim.x)
+        XT[(i / w) * ldx + c0 + (i % w)] = 0.0;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// eri[P][Q] = eri[Q][P] for Q > P : fills the upper triangle from the lower one (the reference's lib.dot
+// produces both, eri_transform.py:455-459).
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mirror_lower_kernel(double* __restrict__ E, int n, long long ld) {
+    __shared__ double tile[32][33];
+    const int tp = blockIdx.y, tq = blockIdx.x;   // source tile (rows tp, cols tq), tq <= tp
+    if (tq > tp) return;
+    for (int dy = threadIdx.y; dy < 32; dy += 8) {
+        const int r = tp * 32 + dy, c = tq * 32 + threadIdx.x;
+        if (r < n && c < n) tile[dy][threadIdx.x] = E[(long long)r * ld + c];
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += 8) {
+        const int r = tq * 32 + dy, c = tp * 32 + threadIdx.x;   // destination (rows tq, cols tp)
+        if (r < n && c < n && c > r) E[(long long)r * ld + c] = tile[threadIdx.x][dy];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// s4 -> s1 : out[i][j][k][l] = eri4[tri(i,j)][tri(k,l)]   (pyscf ao2mo.restore(1, ...), eri_transform.py:529,543)
+// s4 -> s8 : out[tri(P,Q)]   = eri4[P][Q], P >= Q          (ao2mo.restore(8, ...))
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tri_idx(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+__global__ void __launch_bounds__(256)
+restore_s1_kernel(const double* __restrict__ eri4, double* __restrict__ out, int n, long long npair) {
+    const int ij = blockIdx.x;
+    const int i = ij / n, j = ij - i * n;
+    const double* row = eri4 + (long long)tri_idx(i, j) * npair;
+    double* dst = out + (long long)ij * n * n;
+    for (int kl = threadIdx.x; kl < n * n; kl += blockDim.x) {
+        const int k = kl / n, l = kl - k * n;
+        dst[kl] = row[tri_idx(k, l)];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+restore_s8_kernel(const double* __restrict__ eri4, double* __restrict__ out, long long npair) {
+    const long long P = blockIdx.x;
+    const double* row = eri4 + P * npair;
+    double* dst = out + P * (P + 1) / 2;
+    for (long long Q = threadIdx.x; Q <= P; Q += blockDim.x) dst[Q] = row[Q];
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// J/K contraction of an s4 ERI with density matrices (PySCF hf.dot_eri_dm; call site libdmet/solver/scf.py:300-326;
+// convention J_ij = sum_kl (ij|kl) D_kl, K_jk = sum_il (ij|kl) D_il, scf.py:269-271).
+// One CTA per packed row P = (i >= j): the row is staged in shared memory once and used for
+//    vj[P]      = sum_Q row[Q] * dd[Q]                       dd[Q=(k>=l)] = D_kl + D_lk (k != l), D_kk
+//    y1[k]      = sum_l M[k][l] D[i][l]   -> contributes to K[j][k]
+//    y2[k]      = sum_l M[k][l] D[j][l]   -> contributes to K[i][k]   (i != j)
+// partial rows are written out and reduced in fixed order by jk_reduce_kernel (deterministic, no atomics).
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, double* __restrict__ vj_packed,
+               double* __restrict__ kpart, int n, long long npair, int with_k) {
+    extern __shared__ double srow[];     // [npair] + [2n] D rows + [8] reduction
+    double* dI = srow + npair;
+    double* dJ = dI + n;
+    double* red = dJ + n;
+    const long long P = blockIdx.x;
+    int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= P) ++i;
+    while ((long long)i * (i + 1) / 2 > P) --i;
+    const int j = (int)(P - (long long)i * (i + 1) / 2);
+    const double* row = eri4 + P * npair;
+    for (long long q = threadIdx.x; q < npair; q += blockDim.x) srow[q] = row[q];
+    for (int l = threadIdx.x; l < n; l += blockDim.x) {
+        dI[l] = D[(size_t)i * n + l];
+        dJ[l] = D[(size_t)j * n + l];
+    }
+    __syncthreads();
+    // ---- J ----
+    double part = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double* mrow = srow + (size_t)k * (k + 1) / 2;
+        double s = 0.0;
+        for (int l = 0; l < k; ++l) s += mrow[l] * (D[(size_t)k * n + l] + D[(size_t)l * n + k]);
+        s += mrow[k] * D[(size_t)k * n + k];
+        part += s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        vj_packed[P] = s;
+    }
+    if (!with_k) return;
+    // ---- K partials ----
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double y1 = 0.0, y2 = 0.0;
+        for (int l = 0; l < n; ++l) {
+            const double m = srow[tri_idx(k, l)];
+            y1 = fma(m, dI[l], y1);
+            y2 = fma(m, dJ[l], y2);
+        }
+        kpart[(P * 2 + 0) * n + k] = y1;
+        kpart[(P * 2 + 1) * n + k] = y2;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+jk_reduce_kernel(const double* __restrict__ kpart, double* __restrict__ vk, int n) {
+    const int a = blockIdx.x;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double s = 0.0;
+        for (int i = a; i < n; ++i) s += kpart[(((long long)i * (i + 1) / 2 + a) * 2 + 0) * n + k];
+        for (int j = 0; j < a; ++j) s += kpart[(((long long)a * (a + 1) / 2 + j) * 2 + 1) * n + k];
+        vk[(size_t)a * n + k] = s;
+    }
+}
+
+// unpack a packed symmetric vector to a full (n, n) matrix
+__global__ void unpack_sym_kernel(const double* __restrict__ packed, double* __restrict__ full, int n) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+        const int r = idx / n, c = idx - r * n;
+        full[idx] = packed[tri_idx(r, c)];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// res[x] = scale * Re sum_k in[k][x]  (+ max|Im|)  -- the sum over k-points of transform_trans_inv_k
+// (libdmet/routine/slater_helper.py:37-50): one thread per x, fixed summation order.
+// ----------------------------------------------------------------------------------------------------------
+__global__ void ksum_real_kernel(const double2* __restrict__ in, double* __restrict__ out, int nk, long long X,
+                                 double scale, unsigned long long* imag_max) {
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double im_max = 0.0;
+    if (x < X) {
+        double re = 0.0, im = 0.0;
+        for (int k = 0; k < nk; ++k) {
+            const double2 v = in[(size_t)k * X + x];
+            re += v.x;
+            im += v.y;
+        }
+        out[x] = re * scale;
+        im_max = fabs(im);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) im_max = fmax(im_max, __shfl_xor_sync(0xffffffffu, im_max, o));
+    if (imag_max && (threadIdx.x & 31) == 0 && im_max > 0.0)
+        atomicMax(imag_max, (unsigned long long)__double_as_longlong(im_max));
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Synthetic GDF generator (benchmarks and parity tests; the host twin is libdmet_preview_b200/synthetic.py).
+//   L(ki,kj)[L,p,q] = scale/4 * ( u_ij[L,p,q] + conj(u_ji[L,q,p]) + conj(u_-i-j[L,p,q]) + u_-j-i[L,q,p] )
+// which satisfies L(kj,ki) = L(ki,kj)^H and L(-ki,-kj) = conj L(ki,kj) by construction; u is a counter-based
+// 32-bit hash mapped to [-1, 1) so host and device produce identical bits.
+// ----------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ double synth_u(uint32_t key, uint32_t idx) {
+    return (double)(int32_t)lowbias32(idx ^ key) * 4.656612873077393e-10;   // 2^-31
+}
+__global__ void __launch_bounds__(256)
+synth_block_kernel(double2* __restrict__ out, int naux, int nao, uint32_t key_ij, uint32_t key_ji, uint32_t key_mij,
+                   uint32_t key_mji, double scale) {
+    const size_t total = (size_t)naux * nao * nao;
+    const double s = 0.25 * scale;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t q = (uint32_t)(e % nao);
+        const uint32_t lp = (uint32_t)(e / nao);
+        const uint32_t p = lp % nao, L = lp / nao;
+        const uint32_t d = 2u * (uint32_t)e;                              // (L, p, q)
+        const uint32_t tt = 2u * ((L * nao + q) * nao + p);               // (L, q, p)
+        const double re = synth_u(key_ij, d) + synth_u(key_ji, tt) + synth_u(key_mij, d) + synth_u(key_mji, tt);
+        const double im = synth_u(key_ij, d + 1) - synth_u(key_ji, tt + 1) - synth_u(key_mij, d + 1) +
+                          synth_u(key_mji, tt + 1);
+        out[e] = make_double2(s * re, s * im);
+    }
+}
+
+}  // namespace ldm

@@ -1,0 +1,844 @@
+// libldm_b200.so -- host runtime and C ABI (include/ldm_b200.h) around the sm_100a kernels.
+// Native code on purpose: the block scheduler, the staging ring, the tensor-map set-up and the kernel launches of
+// the embedding-ERI pipeline all live here; Python only replays the k-point schedule and hands over pointers.
+#include "../../include/ldm_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "dgemm_tn.cuh"
+#include "zgemm_tn.cuh"
+
+namespace ldm {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+
+// ----------------------------------------------------------------------------------------------------------
+// tensor maps
+// ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int encode_tmap_f64_3d(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
+                       bool swizzle128) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return -3;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15)) {
+        set_error("tensor map: base and strides must be 16-byte aligned");
+        return -2;
+    }
+    cuuint64_t dims[3] = {dim0, dim1, dim2 ? dim2 : 1};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes ? stride2_bytes : stride1_bytes * dim1};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " dims=(" +
+                  std::to_string(dim0) + "," + std::to_string(dim1) + "," + std::to_string(dim2) + ") strides=(" +
+                  std::to_string(stride1_bytes) + "," + std::to_string(stride2_bytes) + ") box=(" +
+                  std::to_string(box0) + "," + std::to_string(box1) + ")");
+        return -3;
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// zgemm tile configurations
+// ----------------------------------------------------------------------------------------------------------
+struct ZConfig {
+    int BM, BN, threads, smem;
+    void (*kernel)(const CUtensorMap, const CUtensorMap, const ZGemmArgs);
+};
+
+template <int WM, int WN, int FA, int FB>
+static ZConfig make_zconfig() {
+    using T = ZTile<WM, WN, FA, FB>;
+    return ZConfig{T::BM, T::BN, T::THREADS, T::SMEM, zgemm_tn_kernel<WM, WN, FA, FB>};
+}
+
+static const std::vector<ZConfig>& zconfigs() {
+    static std::vector<ZConfig> v = {
+        make_zconfig<2, 4, 4, 5>(), make_zconfig<4, 2, 4, 5>(), make_zconfig<8, 1, 4, 5>(),
+        make_zconfig<2, 4, 4, 4>(), make_zconfig<4, 2, 4, 4>(), make_zconfig<8, 1, 4, 4>(),
+        make_zconfig<2, 4, 4, 3>(), make_zconfig<4, 2, 4, 3>(), make_zconfig<8, 1, 4, 3>(),
+    };
+    return v;
+}
+
+static const ZConfig& pick_zconfig(int N) {
+    const auto& v = zconfigs();
+    int best = 0;
+    long best_pad = -1;
+    for (size_t i = 0; i < v.size(); ++i) {
+        long pad = (long)((N + v[i].BN - 1) / v[i].BN) * v[i].BN;
+        if (best_pad < 0 || pad < best_pad || (pad == best_pad && v[i].BN > v[best].BN)) {
+            best = (int)i;
+            best_pad = pad;
+        }
+    }
+    return v[best];
+}
+
+}  // namespace ldm
+
+using namespace ldm;
+
+// ----------------------------------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------------------------------
+struct EriPlan;
+
+struct ldm_context {
+    int device = 0;
+    int num_sms = 148;
+    int64_t launches = 0;
+    // small reusable device scratch for segment tables / offsets
+    void* scratch_d = nullptr;
+    void* scratch_h = nullptr;   // pinned twin of scratch_d: tables are written here, then copied asynchronously
+    size_t scratch_bytes = 0;
+    size_t scratch_used = 0;
+    cudaEvent_t scratch_ev = nullptr;
+    unsigned long long* imag_d = nullptr;
+    void* jk_part_d = nullptr;
+    size_t jk_part_bytes = 0;
+    EriPlan* plan = nullptr;
+    bool attrs_set = false;
+};
+
+static int ensure_attrs(ldm_handle h) {
+    if (h->attrs_set) return 0;
+    for (const auto& c : zconfigs())
+        LDM_CUDA_OK(cudaFuncSetAttribute((const void*)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)dgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     DTile::SMEM));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)pack_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     16 * 16 * 17 * 16));
+    h->attrs_set = true;
+    return 0;
+}
+
+// Segment tables / offset tables are tiny.  Each launch writes its table into a fresh region of a pinned host
+// buffer and copies it asynchronously to the same offset of the device twin (a pageable source would make
+// cudaMemcpyAsync synchronise the stream); the regions wrap after a device sync.
+static int scratch_put(ldm_handle h, cudaStream_t st, const void* src, size_t bytes, void** out) {
+    const size_t padded = (bytes + 255) & ~size_t(255);
+    if (!h->scratch_d) {
+        h->scratch_bytes = 8 << 20;
+        LDM_CUDA_OK(cudaMalloc(&h->scratch_d, h->scratch_bytes));
+        LDM_CUDA_OK(cudaHostAlloc(&h->scratch_h, h->scratch_bytes, cudaHostAllocDefault));
+    }
+    LDM_REQUIRE(padded <= h->scratch_bytes, "segment table too large");
+    if (h->scratch_used + padded > h->scratch_bytes) {
+        LDM_CUDA_OK(cudaDeviceSynchronize());   // rare: everything that used older tables has finished
+        h->scratch_used = 0;
+    }
+    *out = static_cast<char*>(h->scratch_d) + h->scratch_used;
+    void* stage = static_cast<char*>(h->scratch_h) + h->scratch_used;
+    h->scratch_used += padded;
+    std::memcpy(stage, src, bytes);
+    LDM_CUDA_OK(cudaMemcpyAsync(*out, stage, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+extern "C" {
+
+int ldm_version(void) { return 100; }
+const char* ldm_last_error(void) { return ldm::last_error(); }
+
+int ldm_create(int device, ldm_handle* out) {
+    LDM_REQUIRE(out != nullptr, "out");
+    int count = 0;
+    LDM_CUDA_OK(cudaGetDeviceCount(&count));
+    LDM_REQUIRE(device >= 0 && device < count, "device index out of range");
+    LDM_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LDM_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("libldm_b200 is built for sm_100a only; device is ") + prop.name + " (sm_" +
+                  std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+        return -4;
+    }
+    ldm_context* h = new ldm_context();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    LDM_CUDA_OK(cudaMalloc(&h->imag_d, sizeof(unsigned long long)));
+    *out = h;
+    return ensure_attrs(h);
+}
+
+int ldm_eri_end(ldm_handle h);
+
+int ldm_destroy(ldm_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->plan) ldm_eri_end(h);
+    if (h->scratch_d) cudaFree(h->scratch_d);
+    if (h->scratch_h) cudaFreeHost(h->scratch_h);
+    if (h->imag_d) cudaFree(h->imag_d);
+    if (h->jk_part_d) cudaFree(h->jk_part_d);
+    delete h;
+    return 0;
+}
+
+int ldm_host_alloc(size_t bytes, void** out_h) {
+    LDM_CUDA_OK(cudaHostAlloc(out_h, bytes, cudaHostAllocDefault));
+    return 0;
+}
+int ldm_host_free(void* p_h) {
+    LDM_CUDA_OK(cudaFreeHost(p_h));
+    return 0;
+}
+int ldm_dev_alloc(ldm_handle h, size_t bytes, void** out_d) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    LDM_CUDA_OK(cudaMalloc(out_d, bytes));
+    return 0;
+}
+int ldm_dev_free(ldm_handle h, void* p_d) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    LDM_CUDA_OK(cudaFree(p_d));
+    return 0;
+}
+int ldm_memcpy_h2d(ldm_handle h, void* dst_d, const void* src_h, size_t bytes, void* stream) {
+    LDM_CUDA_OK(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int ldm_memcpy_d2h(ldm_handle h, void* dst_h, const void* src_d, size_t bytes, void* stream) {
+    LDM_CUDA_OK(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+int ldm_memset(ldm_handle h, void* dst_d, int value, size_t bytes, void* stream) {
+    LDM_CUDA_OK(cudaMemsetAsync(dst_d, value, bytes, (cudaStream_t)stream));
+    return 0;
+}
+int ldm_stream_sync(ldm_handle h, void* stream) {
+    LDM_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int64_t ldm_launch_count(ldm_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------------
+// GEMM launchers (internal; tensor maps supplied by the caller so the ERI pipeline can cache them)
+// ----------------------------------------------------------------------------------------------------------
+static int launch_zgemm(ldm_handle h, cudaStream_t st, const ZConfig& cfg, const CUtensorMap& tmA,
+                        const CUtensorMap& tmB, int M, int N, int K, int nseg, int nbatch, const ZSeg* segs_h,
+                        double2* C, const long long* c_off_h, int rdiv, long long s_outer, long long s_inner,
+                        long long s_col, double alpha, int accumulate) {
+    if (M <= 0 || N <= 0 || nbatch <= 0) return 0;
+    void* segs_d = nullptr;
+    void* off_d = nullptr;
+    int rc = scratch_put(h, st, segs_h, sizeof(ZSeg) * (size_t)nseg * nbatch, &segs_d);
+    if (rc) return rc;
+    if (c_off_h) {
+        rc = scratch_put(h, st, c_off_h, sizeof(long long) * (size_t)nbatch, &off_d);
+        if (rc) return rc;
+    }
+    ZGemmArgs a;
+    a.M = M; a.N = N; a.K = K; a.nseg = nseg; a.nbatch = nbatch;
+    a.segs = static_cast<const ZSeg*>(segs_d);
+    a.C = C;
+    a.c_off = static_cast<const long long*>(off_d);
+    a.rdiv = rdiv > 0 ? rdiv : 1;
+    a.s_outer = s_outer; a.s_inner = s_inner; a.s_col = s_col;
+    a.alpha = alpha; a.accumulate = accumulate;
+    a.tiles_m = (M + cfg.BM - 1) / cfg.BM;
+    a.tiles_n = (N + cfg.BN - 1) / cfg.BN;
+    long long ntiles = (long long)a.tiles_m * a.tiles_n * nbatch;
+    LDM_REQUIRE(ntiles < (1ll << 31), "too many tiles");
+    int grid = (int)std::min<long long>(ntiles, h->num_sms);
+    cfg.kernel<<<grid, cfg.threads, cfg.smem, st>>>(tmA, tmB, a);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+static int launch_dgemm(ldm_handle h, cudaStream_t st, const double* A, long long lda, const double* B, long long ldb,
+                        int M, int N, int K, double* C, long long ldc, double alpha, int accumulate, int lower_only) {
+    if (M <= 0 || N <= 0) return 0;
+    LDM_REQUIRE(!lower_only || M == N, "lower_only needs a square product");
+    CUtensorMap tmA, tmB;
+    int rc = encode_tmap_f64_3d(&tmA, A, (uint64_t)K, (uint64_t)M, 1, (uint64_t)lda * 8, 0, 16, DTile::BM, true);
+    if (rc) return rc;
+    rc = encode_tmap_f64_3d(&tmB, B, (uint64_t)K, (uint64_t)N, 1, (uint64_t)ldb * 8, 0, 16, DTile::BN, true);
+    if (rc) return rc;
+    DGemmArgs a;
+    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.alpha = alpha; a.accumulate = accumulate;
+    a.lower_only = lower_only;
+    a.tiles_m = (M + DTile::BM - 1) / DTile::BM;
+    a.tiles_n = (N + DTile::BN - 1) / DTile::BN;
+    long long ntiles = lower_only ? (long long)a.tiles_m * (a.tiles_m + 1) / 2 : (long long)a.tiles_m * a.tiles_n;
+    int grid = (int)std::min<long long>(ntiles, h->num_sms);
+    dgemm_tn_kernel<<<grid, DTile::THREADS, DTile::SMEM, st>>>(tmA, tmB, a);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" {
+
+int ldm_zgemm_tn(ldm_handle h, void* stream, const void* A_d, int za_count, const void* B_d, int zb_count, int M,
+                 int N, int K, int nseg, int nbatch, const int32_t* segs_h, void* C_d, const int64_t* c_off_h,
+                 int rdiv, int64_t s_outer, int64_t s_inner, int64_t s_col, double alpha, int accumulate) {
+    LDM_REQUIRE(h && A_d && B_d && C_d && segs_h, "null pointer");
+    LDM_REQUIRE(M > 0 && N > 0 && K > 0 && nseg > 0 && nbatch > 0, "shape");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    const ZConfig& cfg = pick_zconfig(N);
+    CUtensorMap tmA, tmB;
+    int rc = encode_tmap_f64_3d(&tmA, A_d, 2ull * K, (uint64_t)M, (uint64_t)za_count, 16ull * K, 16ull * K * M, 16,
+                                cfg.BM, true);
+    if (rc) return rc;
+    rc = encode_tmap_f64_3d(&tmB, B_d, 2ull * K, (uint64_t)N, (uint64_t)zb_count, 16ull * K, 16ull * K * N, 8, cfg.BN,
+                            false);
+    if (rc) return rc;
+    std::vector<ZSeg> segs((size_t)nseg * nbatch);
+    for (size_t i = 0; i < segs.size(); ++i) {
+        segs[i].az = segs_h[4 * i + 0];
+        segs[i].bz = segs_h[4 * i + 1];
+        segs[i].conjA = segs_h[4 * i + 2] ? 0x80000000u : 0u;
+        segs[i].conjB = segs_h[4 * i + 3] ? 0x80000000u : 0u;
+        LDM_REQUIRE(segs[i].az >= 0 && segs[i].az < za_count && segs[i].bz >= 0 && segs[i].bz < zb_count,
+                    "segment slice out of range");
+    }
+    std::vector<long long> offs;
+    if (c_off_h) offs.assign(c_off_h, c_off_h + nbatch);
+    rc = launch_zgemm(h, (cudaStream_t)stream, cfg, tmA, tmB, M, N, K, nseg, nbatch, segs.data(),
+                      static_cast<double2*>(C_d), c_off_h ? offs.data() : nullptr, rdiv, s_outer, s_inner, s_col,
+                      alpha, accumulate);
+    if (rc) return rc;
+    return 0;
+}
+
+int ldm_dgemm_tn(ldm_handle h, void* stream, const double* A_d, int64_t lda, const double* B_d, int64_t ldb, int M,
+                 int N, int K, double* C_d, int64_t ldc, double alpha, int accumulate, int lower_only) {
+    LDM_REQUIRE(h && A_d && B_d && C_d, "null pointer");
+    LDM_REQUIRE((lda % 2) == 0 && (ldb % 2) == 0, "leading dimensions must be even (16-byte rows for TMA)");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    return launch_dgemm(h, (cudaStream_t)stream, A_d, lda, B_d, ldb, M, N, K, C_d, ldc, alpha, accumulate,
+                        lower_only);
+}
+
+int ldm_mirror_lower(ldm_handle h, void* stream, double* C_d, int n, int64_t ldc) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    int t = (n + 31) / 32;
+    mirror_lower_kernel<<<dim3(t, t), dim3(32, 8), 0, (cudaStream_t)stream>>>(C_d, n, ldc);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int ldm_phase_transform(ldm_handle h, void* stream, const void* in_d, void* out_d, const void* W_d, int nin,
+                        int nout, int64_t X, int batch, double scale, int in_real, int out_real,
+                        double* imag_max_h) {
+    LDM_REQUIRE(h && in_d && out_d && W_d, "null pointer");
+    LDM_REQUIRE(nin > 0 && nout > 0 && X > 0 && batch > 0, "shape");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int KT = 8;
+    LDM_REQUIRE((size_t)KT * nin * 16 <= 48 * 1024, "too many cells for the phase-matrix kernel");
+    if (out_real) LDM_CUDA_OK(cudaMemsetAsync(h->imag_d, 0, sizeof(unsigned long long), st));
+    dim3 grid((unsigned)((X + 127) / 128), (unsigned)((nout + KT - 1) / KT), (unsigned)batch);
+    phase_transform_kernel<KT><<<grid, 128, (size_t)KT * nin * 16, st>>>(
+        static_cast<const double*>(in_d), static_cast<double*>(out_d), static_cast<const double2*>(W_d), nin, nout,
+        (long long)X, scale, in_real, out_real, out_real ? h->imag_d : nullptr);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    if (out_real && imag_max_h) {
+        unsigned long long bits = 0;
+        LDM_CUDA_OK(cudaMemcpyAsync(&bits, h->imag_d, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        LDM_CUDA_OK(cudaStreamSynchronize(st));
+        double v;
+        std::memcpy(&v, &bits, sizeof(v));
+        *imag_max_h = v;
+    }
+    return 0;
+}
+
+int ldm_ztranspose(ldm_handle h, void* stream, const void* in_d, void* out_d, int batch, int rows, int cols,
+                   int conj, double scale) {
+    LDM_REQUIRE(h && in_d && out_d && batch > 0 && rows > 0 && cols > 0, "arguments");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+    ztranspose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_cast<const double2*>(in_d),
+                                                                       static_cast<double2*>(out_d), rows, cols, conj,
+                                                                       scale);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int ldm_d2z(ldm_handle h, void* stream, const double* in_d, void* out_d, int64_t n) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    d2z_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in_d, static_cast<double2*>(out_d), (size_t)n);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int ldm_ksum_real(ldm_handle h, void* stream, const void* in_d, double* out_d, int nk, int64_t X, double scale,
+                  double* imag_max_h) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    LDM_CUDA_OK(cudaMemsetAsync(h->imag_d, 0, sizeof(unsigned long long), st));
+    ksum_real_kernel<<<(unsigned)((X + 255) / 256), 256, 0, st>>>(static_cast<const double2*>(in_d), out_d, nk,
+                                                                  (long long)X, scale, h->imag_d);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    if (imag_max_h) {
+        unsigned long long bits = 0;
+        LDM_CUDA_OK(cudaMemcpyAsync(&bits, h->imag_d, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        LDM_CUDA_OK(cudaStreamSynchronize(st));
+        double v;
+        std::memcpy(&v, &bits, sizeof(v));
+        *imag_max_h = v;
+    }
+    return 0;
+}
+
+int ldm_restore_s1(ldm_handle h, void* stream, const double* eri4_d, double* out_d, int n) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    long long npair = (long long)n * (n + 1) / 2;
+    restore_s1_kernel<<<n * n, 256, 0, (cudaStream_t)stream>>>(eri4_d, out_d, n, npair);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int ldm_restore_s8(ldm_handle h, void* stream, const double* eri4_d, double* out_d, int n) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    long long npair = (long long)n * (n + 1) / 2;
+    restore_s8_kernel<<<(unsigned)npair, 256, 0, (cudaStream_t)stream>>>(eri4_d, out_d, npair);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm_d, double* vj_d, double* vk_d,
+              int n) {
+    LDM_REQUIRE(h && eri4_d && dm_d && vj_d, "null pointer");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    long long npair = (long long)n * (n + 1) / 2;
+    size_t smem = (size_t)(npair + 2 * n + 8) * 8;
+    LDM_REQUIRE(smem <= 200 * 1024, "neo too large for the shared-memory J/K kernel");
+    size_t need = (size_t)npair * 8 + (size_t)npair * 2 * n * 8;
+    if (h->jk_part_bytes < need) {
+        if (h->jk_part_d) LDM_CUDA_OK(cudaFree(h->jk_part_d));
+        LDM_CUDA_OK(cudaMalloc(&h->jk_part_d, need));
+        h->jk_part_bytes = need;
+    }
+    double* vj_packed = static_cast<double*>(h->jk_part_d);
+    double* kpart = vj_packed + npair;
+    jk_rows_kernel<<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, vj_packed, kpart, n, npair, vk_d != nullptr);
+    LDM_CUDA_OK(cudaGetLastError());
+    unpack_sym_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(vj_packed, vj_d, n);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches += 2;
+    if (vk_d) {
+        jk_reduce_kernel<<<n, 256, 0, st>>>(kpart, vk_d, n);
+        LDM_CUDA_OK(cudaGetLastError());
+        h->launches++;
+    }
+    return 0;
+}
+
+int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, uint32_t key_ij, uint32_t key_ji,
+                    uint32_t key_mij, uint32_t key_mji, double scale) {
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    LDM_REQUIRE(2.0 * naux * nao * (double)nao < 4294967296.0, "block too large for the 32-bit counter");
+    synth_block_kernel<<<h->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(static_cast<double2*>(out_d), naux, nao,
+                                                                          key_ij, key_ji, key_mij, key_mji, scale);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------------
+// embedding-ERI pipeline
+// ----------------------------------------------------------------------------------------------------------
+struct PendingBlock {
+    int ki, kj, sym;
+    int slot;      // slice index in the tensor map of its source
+    int source;    // 0 = ring, 1 = store
+};
+
+struct EriPlan {
+    cudaStream_t st = nullptr, copy_st = nullptr;
+    int nk = 0, nao = 0, naux = 0, neo = 0, nspin = 0, G = 1, klg = 1;
+    long long npair = 0, ldx = 0;
+    const double2* CT = nullptr;
+    double* eri = nullptr;
+    const ZConfig* cfg = nullptr;
+    // workspaces
+    double2* ring = nullptr;     // [2G][naux][nao][nao]
+    int ring_slots = 0, ring_next = 0;
+    std::vector<cudaEvent_t> ring_free;   // recorded after the launch that last read a slot
+    std::vector<char> ring_busy;
+    const double2* store = nullptr;
+    int store_slots = 0;
+    double2* Xt = nullptr;       // [nspin][G][naux][neo][nao]
+    double2* S_sym = nullptr;    // [nspin][naux][neo][neo]
+    double2* S_pln = nullptr;
+    bool sym_init = false, pln_init = false;
+    double* XT = nullptr;        // [nspin][npair][ldx]
+    long long xt_cols = 0;
+    double xt_alpha = 0.0;
+    int kl_in_panel = 0;
+    CUtensorMap tmRing, tmStore, tmCT, tmXt;
+    bool have_store_map = false, have_ring_map = false;
+    std::vector<PendingBlock> pending;
+    int64_t launches0 = 0, h2d_bytes = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
+};
+
+static size_t block_elems(const EriPlan* p) { return (size_t)p->naux * p->nao * p->nao; }
+
+static int plan_timed_begin(EriPlan* p, int kind) {
+    cudaEvent_t a, b;
+    LDM_CUDA_OK(cudaEventCreate(&a));
+    LDM_CUDA_OK(cudaEventCreate(&b));
+    LDM_CUDA_OK(cudaEventRecord(a, p->st));
+    p->ev[kind].push_back({a, b});
+    return 0;
+}
+static int plan_timed_end(EriPlan* p, int kind) {
+    LDM_CUDA_OK(cudaEventRecord(p->ev[kind].back().second, p->st));
+    return 0;
+}
+
+static int ensure_ring(ldm_handle h) {
+    EriPlan* p = h->plan;
+    if (p->ring) return 0;
+    p->ring_slots = 2 * p->G;
+    LDM_CUDA_OK(cudaMalloc(&p->ring, (size_t)p->ring_slots * block_elems(p) * 16));
+    p->ring_free.resize(p->ring_slots);
+    p->ring_busy.assign(p->ring_slots, 0);
+    for (auto& e : p->ring_free) LDM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = encode_tmap_f64_3d(&p->tmRing, p->ring, 2ull * p->nao, (uint64_t)p->naux * p->nao,
+                                (uint64_t)p->ring_slots, 16ull * p->nao, 16ull * block_elems(p), 16, p->cfg->BM, true);
+    if (rc) return rc;
+    p->have_ring_map = true;
+    return 0;
+}
+
+// stage 1 for the pending group: (a) half transform with C_j, written transposed; (b) second half transform with
+// conj(C_i), chained over the blocks of the group, accumulated into S_sym / S_pln.
+static int flush_group(ldm_handle h) {
+    EriPlan* p = h->plan;
+    if (p->pending.empty()) return 0;
+    const int nb = (int)p->pending.size();
+    const int src = p->pending[0].source;
+    const size_t xt_slice = (size_t)p->naux * p->neo * p->nao;
+    // ---- (a) Xt[s][g][L][n][p] = sum_q L_g[L][p][q] * CT[s][kj][n][q]
+    {
+        std::vector<ZSeg> segs;
+        std::vector<long long> offs;
+        for (int s = 0; s < p->nspin; ++s)
+            for (int g = 0; g < nb; ++g) {
+                segs.push_back(ZSeg{p->pending[g].slot, s * p->nk + p->pending[g].kj, 0u, 0u});
+                offs.push_back((long long)((size_t)(s * p->G + g) * xt_slice));
+            }
+        int rc = plan_timed_begin(p, 0);
+        if (rc) return rc;
+        rc = launch_zgemm(h, p->st, *p->cfg, src == 0 ? p->tmRing : p->tmStore, p->tmCT, p->naux * p->nao, p->neo,
+                          p->nao, 1, p->nspin * nb, segs.data(), p->Xt, offs.data(), p->nao,
+                          (long long)p->neo * p->nao, 1, p->nao, 1.0, 0);
+        if (rc) return rc;
+        if (src == 0)
+            for (int g = 0; g < nb; ++g) {
+                LDM_CUDA_OK(cudaEventRecord(p->ring_free[p->pending[g].slot], p->st));
+                p->ring_busy[p->pending[g].slot] = 1;
+            }
+    }
+    // ---- (b) S[s][L][n][m] (+)= sum_g sum_p Xt[s][g][L][n][p] * conj(CT[s][ki_g][m][p])
+    for (int pass = 0; pass < 2; ++pass) {
+        const int want_sym = pass == 0 ? 1 : 0;
+        std::vector<int> members;
+        for (int g = 0; g < nb; ++g)
+            if ((p->pending[g].sym != 0) == (want_sym != 0)) members.push_back(g);
+        if (members.empty()) continue;
+        std::vector<ZSeg> segs;
+        std::vector<long long> offs;
+        for (int s = 0; s < p->nspin; ++s) {
+            for (int g : members) segs.push_back(ZSeg{s * p->G + g, s * p->nk + p->pending[g].ki, 0u, 0x80000000u});
+            offs.push_back((long long)((size_t)s * p->naux * p->neo * p->neo));
+        }
+        double2* S = want_sym ? p->S_sym : p->S_pln;
+        bool& init = want_sym ? p->sym_init : p->pln_init;
+        int rc = launch_zgemm(h, p->st, *p->cfg, p->tmXt, p->tmCT, p->naux * p->neo, p->neo, p->nao,
+                              (int)members.size(), p->nspin, segs.data(), S, offs.data(), 1, p->neo, 0, 1, 1.0,
+                              init ? 1 : 0);
+        if (rc) return rc;
+        init = true;
+    }
+    int rc = plan_timed_end(p, 0);
+    if (rc) return rc;
+    p->pending.clear();
+    return 0;
+}
+
+static int flush_panel(ldm_handle h) {
+    EriPlan* p = h->plan;
+    if (p->xt_cols == 0) return 0;
+    const int K = (int)p->xt_cols;
+    const size_t xt_spin = (size_t)p->npair * p->ldx;
+    const size_t eri_blk = (size_t)p->npair * p->npair;
+    int rc = plan_timed_begin(p, 1);
+    if (rc) return rc;
+    if (p->nspin == 1) {
+        rc = launch_dgemm(h, p->st, p->XT, p->ldx, p->XT, p->ldx, (int)p->npair, (int)p->npair, K, p->eri, p->npair,
+                          p->xt_alpha, 1, 1);
+        if (rc) return rc;
+    } else {
+        // incore order of the reference: aa, ab, bb  (eri_transform.py:463-478)
+        rc = launch_dgemm(h, p->st, p->XT, p->ldx, p->XT, p->ldx, (int)p->npair, (int)p->npair, K, p->eri, p->npair,
+                          p->xt_alpha, 1, 1);
+        if (rc) return rc;
+        rc = launch_dgemm(h, p->st, p->XT, p->ldx, p->XT + xt_spin, p->ldx, (int)p->npair, (int)p->npair, K,
+                          p->eri + eri_blk, p->npair, p->xt_alpha, 1, 0);
+        if (rc) return rc;
+        rc = launch_dgemm(h, p->st, p->XT + xt_spin, p->ldx, p->XT + xt_spin, p->ldx, (int)p->npair, (int)p->npair,
+                          K, p->eri + 2 * eri_blk, p->npair, p->xt_alpha, 1, 1);
+        if (rc) return rc;
+    }
+    rc = plan_timed_end(p, 1);
+    if (rc) return rc;
+    p->xt_cols = 0;
+    p->kl_in_panel = 0;
+    return 0;
+}
+
+extern "C" {
+
+int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int neo, int nspin, const void* CT_d,
+                  double* eri_d, int max_group, int kl_group) {
+    LDM_REQUIRE(h && CT_d && eri_d, "null pointer");
+    LDM_REQUIRE(nkpts > 0 && nao > 0 && naux > 0 && neo > 0 && (nspin == 1 || nspin == 2), "shape");
+    LDM_REQUIRE(h->plan == nullptr, "an ERI build is already open on this handle");
+    LDM_REQUIRE((double)naux * nao < 2147483647.0 && (double)naux * neo < 2147483647.0, "naux*nao too large");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    EriPlan* p = new EriPlan();
+    h->plan = p;
+    p->st = (cudaStream_t)stream;
+    LDM_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
+    p->nk = nkpts; p->nao = nao; p->naux = naux; p->neo = neo; p->nspin = nspin;
+    p->G = std::max(1, max_group);
+    p->klg = std::max(1, kl_group);
+    p->npair = (long long)neo * (neo + 1) / 2;
+    p->ldx = ((long long)p->klg * 2 * naux + 15) / 16 * 16;
+    p->CT = static_cast<const double2*>(CT_d);
+    p->eri = eri_d;
+    p->cfg = &pick_zconfig(neo);
+    p->launches0 = h->launches;
+    const size_t xt_slice = (size_t)naux * neo * nao;
+    const size_t s_elems = (size_t)nspin * naux * neo * neo;
+    LDM_CUDA_OK(cudaMalloc(&p->Xt, (size_t)nspin * p->G * xt_slice * 16));
+    LDM_CUDA_OK(cudaMalloc(&p->S_sym, s_elems * 16));
+    LDM_CUDA_OK(cudaMalloc(&p->S_pln, s_elems * 16));
+    LDM_CUDA_OK(cudaMalloc(&p->XT, (size_t)nspin * p->npair * p->ldx * 8));
+    int rc = encode_tmap_f64_3d(&p->tmCT, CT_d, 2ull * nao, (uint64_t)neo, (uint64_t)nspin * nkpts, 16ull * nao,
+                                16ull * nao * neo, 8, p->cfg->BN, false);
+    if (rc) return rc;
+    rc = encode_tmap_f64_3d(&p->tmXt, p->Xt, 2ull * nao, (uint64_t)naux * neo, (uint64_t)nspin * p->G, 16ull * nao,
+                            16ull * xt_slice, 16, p->cfg->BM, true);
+    if (rc) return rc;
+    return 0;
+}
+
+int ldm_eri_set_store(ldm_handle h, const void* store_d, int nslots) {
+    LDM_REQUIRE(h && h->plan && store_d && nslots > 0, "arguments");
+    EriPlan* p = h->plan;
+    p->store = static_cast<const double2*>(store_d);
+    p->store_slots = nslots;
+    int rc = encode_tmap_f64_3d(&p->tmStore, store_d, 2ull * p->nao, (uint64_t)p->naux * p->nao, (uint64_t)nslots,
+                                16ull * p->nao, 16ull * block_elems(p), 16, p->cfg->BM, true);
+    if (rc) return rc;
+    p->have_store_map = true;
+    return 0;
+}
+
+static int push_block(ldm_handle h, int ki, int kj, int sym, int slot, int source) {
+    EriPlan* p = h->plan;
+    if (!p->pending.empty() && p->pending[0].source != source) {
+        int rc = flush_group(h);
+        if (rc) return rc;
+    }
+    p->pending.push_back(PendingBlock{ki, kj, sym, slot, source});
+    if ((int)p->pending.size() >= p->G) return flush_group(h);
+    return 0;
+}
+
+static int ring_acquire(ldm_handle h, int* slot) {
+    EriPlan* p = h->plan;
+    int rc = ensure_ring(h);
+    if (rc) return rc;
+    *slot = p->ring_next;
+    p->ring_next = (p->ring_next + 1) % p->ring_slots;
+    // the slot may still be read by the stage-1 launch of two groups ago
+    if (p->ring_busy[*slot]) {
+        LDM_CUDA_OK(cudaEventSynchronize(p->ring_free[*slot]));
+        p->ring_busy[*slot] = 0;
+    }
+    return 0;
+}
+
+int ldm_eri_block_host(ldm_handle h, int ki, int kj, int sym, const void* L_h) {
+    LDM_REQUIRE(h && h->plan && L_h, "arguments");
+    EriPlan* p = h->plan;
+    LDM_REQUIRE(ki >= 0 && ki < p->nk && kj >= 0 && kj < p->nk, "k index");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    // a slot that is part of the not-yet-launched group must not be recycled: the ring has 2G slots and a group
+    // holds at most G, so ring_next never laps the pending group.
+    int slot;
+    int rc = ring_acquire(h, &slot);
+    if (rc) return rc;
+    const size_t bytes = block_elems(p) * 16;
+    LDM_CUDA_OK(cudaMemcpyAsync(p->ring + (size_t)slot * block_elems(p), L_h, bytes, cudaMemcpyHostToDevice,
+                                p->copy_st));
+    LDM_CUDA_OK(cudaStreamSynchronize(p->copy_st));   // source buffer is consumed when we return
+    p->h2d_bytes += (int64_t)bytes;
+    return push_block(h, ki, kj, sym, slot, 0);
+}
+
+int ldm_eri_block_store(ldm_handle h, int ki, int kj, int sym, int slot) {
+    LDM_REQUIRE(h && h->plan, "arguments");
+    EriPlan* p = h->plan;
+    LDM_REQUIRE(p->have_store_map, "no resident store registered (ldm_eri_set_store)");
+    LDM_REQUIRE(slot >= 0 && slot < p->store_slots, "store slot");
+    LDM_REQUIRE(ki >= 0 && ki < p->nk && kj >= 0 && kj < p->nk, "k index");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    return push_block(h, ki, kj, sym, slot, 1);
+}
+
+int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, uint32_t key_ij, uint32_t key_ji, uint32_t key_mij,
+                        uint32_t key_mji, double scale) {
+    LDM_REQUIRE(h && h->plan, "arguments");
+    EriPlan* p = h->plan;
+    LDM_REQUIRE(ki >= 0 && ki < p->nk && kj >= 0 && kj < p->nk, "k index");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    int slot;
+    int rc = ring_acquire(h, &slot);
+    if (rc) return rc;
+    rc = ldm_synth_block(h, p->st, p->ring + (size_t)slot * block_elems(p), p->naux, p->nao, key_ij, key_ji, key_mij,
+                         key_mji, scale);
+    if (rc) return rc;
+    return push_block(h, ki, kj, sym, slot, 0);
+}
+
+int ldm_eri_end_kl(ldm_handle h, int weight) {
+    LDM_REQUIRE(h && h->plan, "arguments");
+    LDM_REQUIRE(weight >= 0 && weight <= 2, "weight must be 0 (no time reversal), 1 or 2");
+    EriPlan* p = h->plan;
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    int rc = flush_group(h);
+    if (rc) return rc;
+    LDM_REQUIRE(p->sym_init || p->pln_init, "transfer momentum without blocks");
+    const double alpha = weight == 2 ? 2.0 : 1.0;
+    const int ncols = (weight == 1 ? 1 : 2) * p->naux;
+    if (p->xt_cols > 0 && (p->xt_alpha != alpha || p->xt_cols + ncols > p->ldx || p->kl_in_panel >= p->klg)) {
+        rc = flush_panel(h);
+        if (rc) return rc;
+    }
+    p->xt_alpha = alpha;
+    const long long col_re = p->xt_cols;
+    const long long col_im = weight == 1 ? -1 : p->xt_cols + p->naux;
+    const int t = (p->neo + 15) / 16;
+    const size_t s_spin = (size_t)p->naux * p->neo * p->neo;
+    for (int s = 0; s < p->nspin; ++s) {
+        pack_sym_kernel<<<dim3(t, t, (p->naux + 15) / 16), 256, 16 * 16 * 17 * 16, p->st>>>(
+            p->sym_init ? p->S_sym + s * s_spin : nullptr, p->pln_init ? p->S_pln + s * s_spin : nullptr,
+            p->XT + (size_t)s * p->npair * p->ldx, p->naux, p->neo, p->ldx, col_re, col_im);
+        LDM_CUDA_OK(cudaGetLastError());
+        h->launches++;
+    }
+    p->xt_cols += ncols;
+    p->kl_in_panel++;
+    p->sym_init = p->pln_init = false;
+    return 0;
+}
+
+int ldm_eri_finish(ldm_handle h) {
+    LDM_REQUIRE(h && h->plan, "arguments");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    int rc = flush_group(h);
+    if (rc) return rc;
+    LDM_REQUIRE(!h->plan->sym_init && !h->plan->pln_init, "ldm_eri_end_kl missing before ldm_eri_finish");
+    return flush_panel(h);
+}
+
+int ldm_eri_stats(ldm_handle h, int64_t* launches, int64_t* h2d_bytes) {
+    LDM_REQUIRE(h && h->plan, "arguments");
+    if (launches) *launches = h->launches - h->plan->launches0;
+    if (h2d_bytes) *h2d_bytes = h->plan->h2d_bytes;
+    return 0;
+}
+
+int ldm_eri_kernel_time(ldm_handle h, int kind, double* ms, int64_t* launches) {
+    LDM_REQUIRE(h && h->plan && (kind == 0 || kind == 1), "arguments");
+    EriPlan* p = h->plan;
+    LDM_CUDA_OK(cudaStreamSynchronize(p->st));
+    double tot = 0.0;
+    for (auto& e : p->ev[kind]) {
+        float t = 0.f;
+        LDM_CUDA_OK(cudaEventElapsedTime(&t, e.first, e.second));
+        tot += t;
+    }
+    if (ms) *ms = tot;
+    if (launches) *launches = (int64_t)p->ev[kind].size();
+    return 0;
+}
+
+int ldm_eri_end(ldm_handle h) {
+    if (!h || !h->plan) return 0;
+    EriPlan* p = h->plan;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(p->st);
+    cudaStreamSynchronize(p->copy_st);
+    for (int k = 0; k < 2; ++k)
+        for (auto& e : p->ev[k]) {
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+    for (auto& e : p->ring_free) cudaEventDestroy(e);
+    if (p->ring) cudaFree(p->ring);
+    if (p->Xt) cudaFree(p->Xt);
+    if (p->S_sym) cudaFree(p->S_sym);
+    if (p->S_pln) cudaFree(p->S_pln);
+    if (p->XT) cudaFree(p->XT);
+    cudaStreamDestroy(p->copy_st);
+    delete p;
+    h->plan = nullptr;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// Complex-FP64 "TN" GEMM on the FP64 tensor cores (DMMA.8x8x4 via mma.sync) with TMA-staged operand tiles.
+//
+//   C[b][r, c] (+)= alpha * sum_{s < nseg} sum_{k < K}  opA(A[az(b,s)][r, k]) * opB(B[bz(b,s)][c, k])
+//
+// Both operands are row-major with the contraction index k contiguous ("TN"): A is (Z_A, M, K), B is (Z_B, N, K),
+// complex128 interleaved.  The contraction may be chained over `nseg` (A-slice, B-slice) segments per output
+// tile -- this is how the sum over (k_i, k_j) blocks of the reference's inner loop
+// (libdmet/basis_transform/eri_transform.py:344-378) is folded into one K loop.  opA/opB are optional complex
+// conjugations, applied by flipping sign bits of the imaginary fragments.
+//
+// Replaces PySCF `_ao2mo.r_e2` (two zgemm per auxiliary row; call site eri_transform.py:432-433) and the
+// numpy.dot loops of make_basis.py:548-557 / slater_helper.py:46.
+//
+// Structure: persistent CTAs (one per SM); warps 0..WM*WN-1 (two warpgroups) are MMA consumers holding the
+// accumulators in registers (setmaxnreg.inc to 232), the third warpgroup gives its registers away and one
+// elected lane of it is the TMA producer.  A STAGES-deep ring of smem stages is handed over with full/empty mbarriers.
+// One stage = 8 complex k:  A tile  BM rows x 128 B, 128-byte swizzled by TMA;
+//                           B tile  2 slabs (k 0-3, 4-7) of BN rows x 64 B, unswizzled.
+// Fragment loads are LDS.128 (re, im) and bank-conflict free by construction:
+//   A: MMA row g of a fragment reads tile row perm(g) = (g>>1)|((g&1)<<2), so the two rows a quarter-warp
+//      touches differ in bit 2 and the swizzle sends them to disjoint bank groups;
+//   B: rows 2q, 2q+1 of a 64-byte slab are one 128-byte line.
+#pragma once
+#include "common.cuh"
+
+namespace ldm {
+
+struct ZSeg {          // one K-segment of one batch entry
+    int az;            // slice of A (3rd tensor-map coordinate)
+    int bz;            // slice of B
+    uint32_t conjA;    // 0 or 0x80000000
+    uint32_t conjB;    // 0 or 0x80000000
+};
+
+struct ZGemmArgs {
+    int M, N, K;                 // per segment, complex elements
+    int nseg, nbatch;
+    const ZSeg* segs;            // [nbatch * nseg], device
+    double2* C;
+    const long long* c_off;      // [nbatch] element offsets into C, device (may be null -> 0)
+    // output addressing (complex elements): off = (r / rdiv) * s_outer + (r % rdiv) * s_inner + c * s_col
+    int rdiv;
+    long long s_outer, s_inner, s_col;
+    double alpha;
+    int accumulate;              // 1: C += result
+    int tiles_m, tiles_n;
+};
+
+template <int WM, int WN, int FA, int FB>
+struct ZTile {
+    static constexpr int BM = WM * FA * 8;
+    static constexpr int BN = WN * FB * 8;
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_SLAB = BN * 64;
+    static constexpr int STAGE_BYTES = A_BYTES + 2 * B_SLAB;
+    static constexpr int NCONS = WM * WN;
+    static constexpr int THREADS = (NCONS + 4) * 32;   // + one producer warpgroup
+    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 2 * STAGES * 8;
+};
+
+template <int WM, int WN, int FA, int FB>
+__global__ void __launch_bounds__((WM * WN + 4) * 32, 1)
+zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const ZGemmArgs args) {
+    using T = ZTile<WM, WN, FA, FB>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + T::STAGES * T::STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T::STAGES; ++s) {
+            mbar_init(bar_base + 8 * s, 1);
+            mbar_init(bar_base + 8 * (T::STAGES + s), T::NCONS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int ktiles = (args.K + 7) >> 3;
+    const int tiles_per_batch = args.tiles_m * args.tiles_n;
+    const int ntiles = tiles_per_batch * args.nbatch;
+
+    if (warp >= T::NCONS) {
+        // ===================== TMA producer warpgroup (one elected lane works) =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == T::NCONS && lane == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int b = tile / tiles_per_batch;
+                const int rem = tile - b * tiles_per_batch;
+                const int tm = rem / args.tiles_n;
+                const int tn = rem - tm * args.tiles_n;
+                const ZSeg* segs = args.segs + (size_t)b * args.nseg;
+                for (int s = 0; s < args.nseg; ++s) {
+                    const int az = segs[s].az, bz = segs[s].bz;
+                    for (int kt = 0; kt < ktiles; ++kt) {
+                        mbar_wait(bar_base + 8 * (T::STAGES + stage), phase ^ 1);
+                        const uint32_t full = bar_base + 8 * stage;
+                        const uint32_t dst = smem_base + stage * T::STAGE_BYTES;
+                        mbar_expect_tx(full, T::STAGE_BYTES);
+                        tma_load_3d(dst, &tmA, full, kt * 16, tm * T::BM, az);
+                        tma_load_3d(dst + T::A_BYTES, &tmB, full, kt * 16, tn * T::BN, bz);
+                        tma_load_3d(dst + T::A_BYTES + T::B_SLAB, &tmB, full, kt * 16 + 8, tn * T::BN, bz);
+                        if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== MMA consumers =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) | ((g & 1) << 2);
+    // per-thread smem offsets inside a stage
+    const uint32_t a_row_off = (uint32_t)((wm * FA * 8 + pg) * 128);
+    const uint32_t a_c0 = (uint32_t)((t ^ pg) * 16);       // k-step 0 ; k-step 1 is a_c0 ^ 64
+    const uint32_t b_off = (uint32_t)(T::A_BYTES + (wn * FB * 8 + g) * 64 + t * 16);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int rem = tile - b * tiles_per_batch;
+        const int tm = rem / args.tiles_n;
+        const int tn = rem - tm * args.tiles_n;
+        const ZSeg* segs = args.segs + (size_t)b * args.nseg;
+
+        double cr[FA][FB][2], ci[FA][FB][2];
+#pragma unroll
+        for (int i = 0; i < FA; ++i)
+#pragma unroll
+            for (int j = 0; j < FB; ++j) {
+                cr[i][j][0] = cr[i][j][1] = 0.0;
+                ci[i][j][0] = ci[i][j][1] = 0.0;
+            }
+
+        for (int s = 0; s < args.nseg; ++s) {
+            const uint32_t mA = segs[s].conjA;   // sa = -1 -> flip
+            const uint32_t mB = segs[s].conjB;
+            for (int kt = 0; kt < ktiles; ++kt) {
+                mbar_wait(bar_base + 8 * stage, phase);
+                const uint32_t sbase = smem_base + stage * T::STAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    double ar[FA], aip[FA], ain[FA];
+                    const uint32_t a_addr = sbase + a_row_off + (a_c0 ^ (kk * 64));
+#pragma unroll
+                    for (int i = 0; i < FA; ++i) {
+                        double x, y;
+                        lds128(a_addr + i * 1024, x, y);
+                        ar[i] = x;
+                        aip[i] = xor_hi(y, mA);               //  sa * Ai
+                        ain[i] = xor_hi(y, mA ^ 0x80000000u); // -sa * Ai
+                    }
+                    const uint32_t b_addr = sbase + b_off + kk * T::B_SLAB;
+#pragma unroll
+                    for (int j = 0; j < FB; ++j) {
+                        double br, bi;
+                        lds128(b_addr + j * 512, br, bi);
+                        bi = xor_hi(bi, mB);                  //  sb * Bi
+#pragma unroll
+                        for (int i = 0; i < FA; ++i) {
+                            dmma884(cr[i][j][0], cr[i][j][1], ar[i], br);
+                            dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi);
+                            dmma884(cr[i][j][0], cr[i][j][1], ain[i], bi);
+                            dmma884(ci[i][j][0], ci[i][j][1], aip[i], br);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8 * (T::STAGES + stage));
+                if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+
+        // ---------------- epilogue: registers -> global ----------------
+        double2* Cb = args.C + (args.c_off ? args.c_off[b] : 0ll);
+        const double alpha = args.alpha;
+#pragma unroll
+        for (int i = 0; i < FA; ++i) {
+            const int r = tm * T::BM + wm * FA * 8 + i * 8 + pg;
+            if (r >= args.M) continue;
+            const long long roff = (long long)(r / args.rdiv) * args.s_outer + (long long)(r % args.rdiv) * args.s_inner;
+#pragma unroll
+            for (int j = 0; j < FB; ++j) {
+                const int c = tn * T::BN + wn * FB * 8 + j * 8 + 2 * t;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (c + e >= args.N) continue;
+                    double2* p = Cb + roff + (long long)(c + e) * args.s_col;
+                    double2 v = make_double2(alpha * cr[i][j][e], alpha * ci[i][j][e]);
+                    if (args.accumulate) {
+                        const double2 o = *p;
+                        v.x += o.x;
+                        v.y += o.y;
+                    }
+                    *p = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace ldm
