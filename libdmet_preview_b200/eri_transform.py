@@ -1,0 +1,339 @@
+"""Embedding ERI from Gaussian-density-fitting integrals -- drop-in for
+`libdmet.basis_transform.eri_transform.get_emb_eri` / `get_emb_eri_fast_gdf` / `get_unit_eri` (GDF path, restricted and
+unrestricted, s1 / s4 / s8, with or without time-reversal symmetry; eri_transform.py:44-112, 235-399).
+
+What runs where
+    host (this file)    argument handling, the k-point schedule (schedule.py), fetching blocks from the GDF provider
+    libldm_b200.so      everything numerical: C_ao_emb = C_ao_lo . FT(basis) / Nk^(3/4), the two half transformations
+                        per (k_i, k_j) block, symmetrise + pack, the Gram products, mirror and s1/s8 re-layout
+There is no CPU fallback; the module raises if the CUDA library is missing.
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+import torch
+
+from ._lib import check
+from .device import get_device, _ptr
+from .schedule import build_schedule, assign_units, KPT_DIFF_TOL
+from . import fourier
+from .make_basis import add_spin_dim
+
+ERI_IMAG_TOL = 1e-6     # eri_transform.py:32
+DEFAULT_GROUP = 4       # (k_i, k_j) blocks per stage-1 launch
+DEFAULT_KL_GROUP = 4    # transfer momenta per stage-3 launch
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GDF providers
+# ---------------------------------------------------------------------------------------------------------
+class PyscfGDFProvider(object):
+    """Adapter for a real `pyscf.pbc.df.GDF` (used only when PySCF is installed; it is not in this image).
+    Mirrors `sr_loop` (eri_transform.py:195-227): `_load3c` returns the stored (k_i, k_j) block or the conjugate
+    transpose of the stored (k_j, k_i) one; diagonal blocks may be s2-packed and are unpacked Hermitian."""
+
+    def __init__(self, cell, mydf):
+        from pyscf.pbc.df.df import _load3c      # noqa: F401  (import error = PySCF missing)
+        self._load3c = _load3c
+        self.mydf = mydf
+        self.cell = cell
+        self.kpts = np.asarray(mydf.kpts)
+        self.kpts_scaled = cell.get_scaled_kpts(self.kpts)
+        self.kmesh = fourier.get_kmesh(cell, self.kpts)
+        self.nao = int(cell.nao_nr())
+        if mydf._cderi is None:
+            mydf.build()
+        if cell.dimension == 2 and getattr(cell, "low_dim_ft_type", None) != 'inf_vacuum':
+            raise NotImplementedError      # eri_transform.py:226-227
+        from libdmet.basis_transform.eri_transform import get_naoaux
+        self.naux = int(get_naoaux(mydf))
+
+    def load(self, ki, kj):
+        from pyscf import lib
+        nao = self.nao
+        with self._load3c(self.mydf._cderi, 'j3c', self.kpts[[ki, kj]], 'j3c-kptij') as j3c:
+            Lpq = np.asarray(j3c[:])
+        if Lpq.shape[-1] != nao * nao:
+            Lpq = lib.unpack_tril(Lpq)
+        out = np.zeros((self.naux, nao, nao), dtype=np.complex128)   # aux rows dropped at some k are zero
+        out[:Lpq.shape[0]] = Lpq.reshape(-1, nao, nao)
+        return out
+
+
+def as_provider(cell, mydf):
+    """Accept an in-memory provider (duck-typed: .kpts_scaled .kmesh .nao .naux .load) or a PySCF GDF."""
+    if all(hasattr(mydf, a) for a in ("kpts_scaled", "nao", "naux", "load")):
+        return mydf
+    try:
+        from pyscf.pbc import df as _pdf
+    except ImportError:
+        _pdf = None
+    if _pdf is not None and isinstance(mydf, _pdf.GDF) and not isinstance(mydf, _pdf.MDF):
+        return PyscfGDFProvider(cell, mydf)
+    raise ValueError("Unknown DF type for embedding ERI construction.")     # eri_transform.py:89
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C_ao_emb^T on the device
+# ---------------------------------------------------------------------------------------------------------
+def _to_z(a):
+    dev = get_device()
+    if isinstance(a, torch.Tensor):
+        return (a if a.dtype == torch.complex128 else a.to(torch.complex128)).contiguous()
+    return dev.to_device(np.asarray(a).astype(np.complex128, copy=False), torch.complex128)
+
+
+def build_CT(provider, C_ao_lo=None, basis=None, C_ao_eo=None, unit_eri=False):
+    """(spin, nkpts, nemb, nao) complex128 device tensor: transpose of
+    C_ao_emb = C_ao_lo . sum_R basis[R] exp(-ikR) / nkpts^(3/4)        (eri_transform.py:270-300)."""
+    dev = get_device()
+    nao, nkpts = provider.nao, len(provider.kpts_scaled)
+    scale = 1.0 / (nkpts ** 0.75)
+    if C_ao_eo is not None:
+        if C_ao_lo is not None:
+            raise ValueError("Don't pass both `C_ao_lo` and `C_ao_eo`.")     # l.295
+        C_ao_eo = C_ao_eo if isinstance(C_ao_eo, torch.Tensor) else np.asarray(C_ao_eo)
+        if C_ao_eo.ndim == 3:
+            C_ao_eo = C_ao_eo[None]
+        assert (nkpts, nao) == tuple(C_ao_eo.shape[1:3])                     # l.299
+        Cz = _to_z(C_ao_eo)
+        spin, _, _, nemb = Cz.shape
+        return dev.ztranspose(Cz.reshape(-1, nao, nemb), scale=scale).reshape(spin, nkpts, nemb, nao)
+
+    if C_ao_lo is None:      # k2gamma AO transformation (l.272-274)
+        C_ao_lo = np.zeros((nkpts, nao, nao), dtype=np.complex128)
+        C_ao_lo[:, range(nao), range(nao)] = 1.0
+    C_ao_lo = C_ao_lo if isinstance(C_ao_lo, torch.Tensor) else np.asarray(C_ao_lo)
+    if C_ao_lo.ndim == 3:
+        C_ao_lo = C_ao_lo[None]
+    assert tuple(C_ao_lo.shape[1:3]) == (nkpts, nao)
+    nlo = C_ao_lo.shape[-1]
+    if unit_eri:             # l.288-289 (basis is ignored)
+        Cz = _to_z(C_ao_lo)
+        return dev.ztranspose(Cz.reshape(-1, nao, nlo), scale=scale).reshape(Cz.shape[0], nkpts, nlo, nao)
+
+    if basis is None:        # l.281-282
+        basis = np.eye(nkpts * nao).reshape(1, nkpts, nao, nkpts * nao)
+    basis = basis if isinstance(basis, torch.Tensor) else np.asarray(basis)
+    if basis.ndim == 3:
+        basis = basis[None]
+    spin = max(basis.shape[0], C_ao_lo.shape[0])
+    basis = add_spin_dim(basis, spin)         # l.283-286
+    C_ao_lo = add_spin_dim(C_ao_lo, spin)
+    nemb = basis.shape[-1]
+    assert tuple(basis.shape[1:3]) == (nkpts, nlo)
+    # basis_k[s, k] = sum_R basis[s, R] exp(-i k R)   (get_basis_k, l.118-126); basis is real in practice
+    if isinstance(basis, torch.Tensor):
+        bd = basis.contiguous()
+    elif np.iscomplexobj(basis):
+        bd = dev.to_device(np.ascontiguousarray(basis), torch.complex128)
+    else:
+        bd = dev.to_device(np.ascontiguousarray(basis, dtype=np.float64), torch.float64)
+    phase = fourier.get_phase_R2k_scaled(provider.kmesh, provider.kpts_scaled)      # (R, k)
+    W = dev.to_device(np.ascontiguousarray(phase.T), torch.complex128)
+    basis_k, _ = dev.phase_transform(bd, W)                                           # (spin, nk, nlo, nemb)
+    bkT = dev.ztranspose(basis_k.reshape(-1, nlo, nemb))                              # (spin*nk, nemb, nlo)
+    Cz = _to_z(C_ao_lo).reshape(-1, nao, nlo)
+    nb = spin * nkpts
+    segs = np.zeros((nb, 4), dtype=np.int32)
+    segs[:, 0] = np.arange(nb)
+    segs[:, 1] = np.arange(nb)
+    CT = dev.empty((spin, nkpts, nemb, nao), torch.complex128)
+    # CT[s,k][n][p] = scale * sum_l basis_k^T[n][l] C_ao_lo[p][l]          (multiply_basis, make_basis.py:923-962)
+    dev.zgemm_tn(bkT, Cz, segs, CT, c_off=np.arange(nb, dtype=np.int64) * nemb * nao, s_outer=nao, alpha=scale,
+                 nbatch=nb, nseg=1)
+    return CT
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the pipeline
+# ---------------------------------------------------------------------------------------------------------
+class EriBuild(object):
+    """One open `ldm_eri_*` build on the process-wide handle (context manager)."""
+
+    def __init__(self, CT, naux, eri, group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP):
+        self.dev = get_device()
+        spin, nkpts, nemb, nao = CT.shape
+        self.CT = CT
+        self.eri = eri
+        self.shape = (nkpts, nao, naux, nemb, spin)
+        check(self.dev.lib.ldm_eri_begin(self.dev.h, self.dev.stream, nkpts, nao, naux, nemb, spin, _ptr(CT),
+                                         _ptr(eri), int(group), int(kl_group)))
+        self.open = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def close(self):
+        if self.open:
+            self.open = False
+            check(self.dev.lib.ldm_eri_end(self.dev.h))
+
+    def set_store(self, store):
+        self._store = store
+        check(self.dev.lib.ldm_eri_set_store(self.dev.h, _ptr(store), store.shape[0]))
+
+    def block_host(self, ki, kj, sym, L):
+        nk, nao, naux = self.shape[:3]
+        if isinstance(L, torch.Tensor):
+            assert L.dtype == torch.complex128 and L.is_contiguous() and not L.is_cuda
+            assert L.numel() == naux * nao * nao
+            ptr = C.c_void_p(L.data_ptr())
+        else:
+            L = np.ascontiguousarray(L, dtype=np.complex128)
+            assert L.size == naux * nao * nao, "GDF block has shape %s, expected (%d, %d, %d)" % (
+                L.shape, naux, nao, nao)
+            ptr = L.ctypes.data_as(C.c_void_p)
+        check(self.dev.lib.ldm_eri_block_host(self.dev.h, ki, kj, int(sym), ptr))
+
+    def block_store(self, ki, kj, sym, slot):
+        check(self.dev.lib.ldm_eri_block_store(self.dev.h, ki, kj, int(sym), int(slot)))
+
+    def block_synth(self, ki, kj, sym, keys, scale):
+        check(self.dev.lib.ldm_eri_block_synth(self.dev.h, ki, kj, int(sym), int(keys[0]), int(keys[1]),
+                                               int(keys[2]), int(keys[3]), float(scale)))
+
+    def end_kl(self, weight):
+        check(self.dev.lib.ldm_eri_end_kl(self.dev.h, int(weight)))
+
+    def finish(self):
+        check(self.dev.lib.ldm_eri_finish(self.dev.h))
+
+    def stats(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(self.dev.lib.ldm_eri_stats(self.dev.h, C.byref(a), C.byref(b)))
+        return {"launches": a.value, "h2d_bytes": b.value}
+
+    def kernel_time(self, kind):
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(self.dev.lib.ldm_eri_kernel_time(self.dev.h, kind, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def run_schedule(build, provider, schedule, units=None, source="auto", store_map=None):
+    """Feed the (k_i, k_j) blocks of `units` (indices into schedule.units; default all) to an open build.
+    source: "host"   provider.load(ki, kj) -> host array -> H2D inside the call
+            "synth"  provider.keys(ki, kj) -> device generator (SyntheticGDF only)
+            "store"  store_map[(ki, kj)] -> slot of the resident device store registered with build.set_store
+            "auto"   synth if the provider has .keys, else host"""
+    if source == "auto":
+        source = "synth" if hasattr(provider, "keys") and hasattr(provider, "scale") else "host"
+    idx = range(len(schedule.units)) if units is None else units
+    for u in idx:
+        kL, weight, blocks = schedule.units[u]
+        for (ki, kj, sym) in blocks:
+            if source == "host":
+                build.block_host(ki, kj, sym, provider.load(ki, kj))
+            elif source == "synth":
+                build.block_synth(ki, kj, sym, provider.keys(ki, kj), provider.scale)
+            elif source == "store":
+                build.block_store(ki, kj, sym, store_map[(ki, kj)])
+            else:
+                raise ValueError("unknown block source %s" % source)
+        build.end_kl(weight)
+    build.finish()
+
+
+def finalize_eri(eri, nemb, symmetry, nspin):
+    """mirror the lower triangles of the syrk blocks and re-lay out: the device half of eri_restore
+    (eri_transform.py:523-544).  eri: (spin_pair, npair, npair) device tensor in incore order aa, ab, bb."""
+    dev = get_device()
+    spin_pair = eri.shape[0]
+    for s in range(spin_pair):
+        if not (nspin == 2 and s == 1):          # ab is a full product already
+            dev.mirror_lower(eri[s])
+    if symmetry == 4:
+        return eri
+    if symmetry == 1:
+        return torch.stack([dev.restore_s1(eri[s], nemb) for s in range(spin_pair)])
+    if symmetry == 8:
+        if spin_pair != 1:
+            raise ValueError("Spin unrestricted ERI does not support 8-fold symmetry.")   # l.541
+        return dev.restore_s8(eri[0], nemb)[None]
+    raise ValueError("unknown ERI symmetry %s" % symmetry)
+
+
+def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL, kscaled_center=None,
+                   source="auto", group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, units=None, schedule=None,
+                   store=None, store_map=None, stats=None):
+    """Stages 1-3 on the device.  Returns the (spin_pair, npair, npair) tensor holding the LOWER triangles of the
+    symmetric blocks (sum over `units` of the schedule only, if given)."""
+    dev = get_device()
+    spin, nkpts, nemb, nao = CT.shape
+    npair = nemb * (nemb + 1) // 2
+    if schedule is None:
+        schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
+    eri = dev.zeros((spin * (spin + 1) // 2, npair, npair))
+    with EriBuild(CT, provider.naux, eri, group, kl_group) as b:
+        if store is not None:
+            b.set_store(store)
+            source = "store"
+        run_schedule(b, provider, schedule, units, source, store_map)
+        if stats is not None:
+            stats.update(b.stats())
+            stats["zgemm_ms"], stats["zgemm_launch_groups"] = b.kernel_time(0)
+            stats["dgemm_ms"], stats["dgemm_launch_groups"] = b.kernel_time(1)
+    return eri
+
+
+def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_center=None, symmetry=4,
+                         max_memory=None, C_ao_eo=None, kconserv_tol=KPT_DIFF_TOL, unit_eri=False, swap_idx=None,
+                         t_reversal_symm=True, incore=True, fout="H2.h5", return_device=False, **kwargs):
+    """eri_transform.py:235-399.  Same arguments and return layout:
+    (spin*(spin+1)/2,) + s4 (npair, npair) / s1 (n,n,n,n) / s8 (npair_pair,), float64, C-contiguous, spin order
+    aa, ab, bb.  `max_memory`, `feri`, `swap_idx`, `fout` are accepted for compatibility (`max_memory` only
+    chose the auxiliary chunk length in the reference and does not change results)."""
+    if not incore:
+        raise NotImplementedError("outcore (HDF5) accumulation is outside the GPU path; use incore=True")
+    provider = as_provider(cell, mydf)
+    if getattr(cell, "dimension", 3) == 2 and getattr(cell, "low_dim_ft_type", None) != 'inf_vacuum':
+        raise NotImplementedError                                         # l.226-227
+    assert cell is None or int(cell.nao_nr()) == provider.nao
+    CT = build_CT(provider, C_ao_lo, basis, C_ao_eo, unit_eri)
+    spin, nkpts, nemb, nao = CT.shape
+    eri = emb_eri_device(provider, CT, t_reversal_symm, kconserv_tol, kscaled_center,
+                         source=kwargs.get("source", "auto"), group=kwargs.get("group", DEFAULT_GROUP),
+                         kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None))
+    eri = finalize_eri(eri, nemb, symmetry, spin)
+    if return_device:
+        return eri
+    return eri.cpu().numpy()
+
+
+get_emb_eri_fast = get_emb_eri_fast_gdf
+
+
+def get_emb_eri(cell, mydf, C_ao_lo=None, basis=None, unit_eri=False, symmetry=4, t_reversal_symm=True,
+                max_memory=None, swap_idx=None, feri=None, kscaled_center=None, kconserv_tol=KPT_DIFF_TOL,
+                incore=True, fout="H2.h5", **kwargs):
+    """eri_transform.py:44-94 (GDF branch; `use_mpi=True` shards the transfer momenta over the ranks of the
+    initialised torch.distributed group, see dist.py)."""
+    if kwargs.pop("use_mpi", False):
+        from . import dist
+        return dist.get_emb_eri_sharded(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, kscaled_center=kscaled_center,
+                                        symmetry=symmetry, kconserv_tol=kconserv_tol, unit_eri=unit_eri,
+                                        t_reversal_symm=t_reversal_symm, **kwargs)
+    return get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, feri=feri,
+                                kscaled_center=kscaled_center, symmetry=symmetry, max_memory=max_memory,
+                                kconserv_tol=kconserv_tol, unit_eri=unit_eri, swap_idx=swap_idx,
+                                t_reversal_symm=t_reversal_symm, incore=incore, fout=fout, **kwargs)
+
+
+def get_unit_eri(cell, mydf, C_ao_lo=None, symmetry=4, t_reversal_symm=True, max_memory=None, swap_idx=None,
+                 feri=None, kscaled_center=None, kconserv_tol=KPT_DIFF_TOL, incore=True, fout="H2.h5", **kwargs):
+    """eri_transform.py:96-112."""
+    if not isinstance(C_ao_lo, torch.Tensor):
+        C_ao_lo = np.asarray(C_ao_lo)
+    if C_ao_lo.ndim == 3:
+        C_ao_lo = C_ao_lo[None]
+    return get_emb_eri(cell, mydf, C_ao_lo=C_ao_lo, basis=None, feri=feri, kscaled_center=kscaled_center,
+                       symmetry=symmetry, max_memory=max_memory, kconserv_tol=kconserv_tol, unit_eri=True,
+                       swap_idx=swap_idx, t_reversal_symm=t_reversal_symm, incore=incore, fout=fout, **kwargs)
+
+
+get_unit_eri_fast_gdf = get_unit_eri

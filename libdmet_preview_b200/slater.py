@@ -1,0 +1,359 @@
+"""Embedding basis and embedding Hamiltonian -- drop-in for `libdmet.routine.slater.get_emb_basis` (`embBasis`) and
+`get_emb_Ham` (`embHam`), ab-initio interacting-bath Hartree-Fock branch plus the non-interacting-bath ERI
+(slater.py:98-220, 320-370, 438-476, 478-523, 525-605, 639-643, 690-712).
+
+`embHam` keeps the two-electron integrals on the GPU between the ERI build and the J/K contraction of the one-body
+part; every contraction runs in libldm_b200.so.  `get_emb_basis` gathers the environment-impurity block of the
+density matrix and calls LAPACK's SVD on the host, like the reference (north_star keeps the dense eigen/singular
+value solves on the reference's own route).
+"""
+import warnings
+
+import numpy as np
+import scipy.linalg as la
+import torch
+
+from .device import get_device
+from . import eri_transform
+from .eri_transform import get_emb_eri, get_unit_eri
+from .fourier import IMAG_DISCARD_TOL
+from .integral import Integral, get_eri_format
+from .make_basis import add_spin_dim
+
+
+# ---------------------------------------------------------------------------------------------------------
+# get_emb_basis
+# ---------------------------------------------------------------------------------------------------------
+def _lowdin(s, tol=1e-14):
+    """libdmet/lo/lowdin.py:83-92."""
+    e, v = la.eigh(s)
+    idx = e > tol
+    if not idx.all():
+        warnings.warn("_vec_lowdin has almost zero eigenvalues:\n%s" % e[~idx])
+    return np.dot(v[:, idx] / np.sqrt(e[idx]), v[:, idx].conj().T)
+
+
+def vec_lowdin(c, s=None):
+    """libdmet/lo/lowdin.py:94-101 for an identity metric: c (c^T c)^{-1/2}."""
+    m = c.conj().T.dot(c) if s is None else c.conj().T.dot(s).dot(c)
+    return np.dot(c, _lowdin(m))
+
+
+def get_emb_basis(lattice, rho=None, local=True, kind='svd', **kwargs):
+    """slater.py:98-115."""
+    if rho is None:
+        rho = lattice.rdm1_lo_R
+    if not local:
+        raise NotImplementedError("non-local (particle-hole symmetric model) bath is outside the ab-initio path")
+    rho = rho.cpu().numpy() if isinstance(rho, torch.Tensor) else np.asarray(rho)
+    if kind == 'svd':
+        return _get_emb_basis_svd(lattice, rho.real, **kwargs)
+    elif kind == 'eig':
+        raise NotImplementedError("kind='eig' bath construction is not part of the hot path")
+    else:
+        raise ValueError("get_emb_basis: Unknown kind %s" % kind)
+
+
+embBasis = get_emb_basis
+
+
+def _get_emb_basis_svd(lattice, rdm1, **kwargs):
+    """slater.py:117-220: bath = left singular vectors of rdm1[env, imp]."""
+    imp_idx = list(kwargs.get("imp_idx", lattice.imp_idx))
+    val_idx = list(kwargs.get("val_idx", lattice.val_idx))
+    valence_bath = kwargs.get("valence_bath", True)
+    orth = kwargs.get("orth", True)
+    tol_bath = kwargs.get("tol_bath", 1e-9)
+    nbath = kwargs.get("nbath", None)
+    if kwargs.get("localize_bath", None) is not None:
+        raise NotImplementedError("bath localisation is only defined for model Hamiltonians in the reference")
+
+    ncells, nlo = int(lattice.ncells), int(lattice.nscsites)
+    imp_idx_bath = val_idx if valence_bath else imp_idx
+    in_bath = np.zeros(ncells * nlo, dtype=bool)
+    in_bath[imp_idx_bath] = True
+    in_imp = np.zeros(ncells * nlo, dtype=bool)
+    in_imp[imp_idx] = True
+    env_idx = np.where(~in_bath)[0]
+    virt_mask = in_imp[env_idx]
+    nimp = len(imp_idx)
+
+    rdm1 = np.asarray(rdm1)
+    if rdm1.ndim == 3:
+        rdm1 = rdm1[np.newaxis]
+    assert rdm1.shape[-3:] == (ncells, nlo, nlo)
+    spin = rdm1.shape[0]
+
+    if np.max(imp_idx_bath) >= nlo - 1:      # (sic) l.167: also taken for the last orbital of cell 0
+        rdm1_env_imp = lattice.expand(rdm1)[:, env_idx][:, :, imp_idx_bath]
+        nbath_final = len(imp_idx_bath)
+    else:
+        rdm1_env_imp = rdm1.reshape(spin, ncells * nlo, nlo)[:, env_idx][:, :, imp_idx_bath]
+        nbath_final = nlo
+    basis = np.zeros((spin, ncells * nlo, nimp * 2))
+
+    for s in range(spin):
+        u, sigma, vt = la.svd(rdm1_env_imp[s], full_matrices=False)
+        nbath_s = int((sigma >= tol_bath).sum()) if nbath is None else nbath
+        B = u[:, :nbath_s]
+        if np.sum(np.abs(sigma[:nbath_s]) < tol_bath) > 0:
+            warnings.warn("Zero singular value exists, \nthis may cause numerical instability.")
+        if nbath_s > 0 and orth:
+            B[virt_mask] = 0.0
+            B = vec_lowdin(B)
+        basis[s, imp_idx, :nimp] = np.eye(nimp)
+        basis[s, env_idx, nimp:nimp + nbath_s] = B
+        nbath_final = min(nbath_final, nbath_s)
+
+    basis = basis[:, :, :nimp + nbath_final].reshape(spin, ncells, nlo, nimp + nbath_final)
+    return basis
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one-body pieces on the device
+# ---------------------------------------------------------------------------------------------------------
+def _zdev(a):
+    dev = get_device()
+    if isinstance(a, torch.Tensor):
+        return (a if a.dtype == torch.complex128 else a.to(torch.complex128)).contiguous()
+    return dev.to_device(np.asarray(a).astype(np.complex128, copy=False), torch.complex128)
+
+
+class _BasisK(object):
+    """basis_k (spin, nkpts, nlo, neo) on the device plus its k-contiguous transpose."""
+
+    def __init__(self, basis_k):
+        dev = get_device()
+        self.bk = _zdev(basis_k)
+        self.spin, self.nk, self.nlo, self.neo = self.bk.shape
+        self.bkT = dev.ztranspose(self.bk.reshape(-1, self.nlo, self.neo))      # (spin*nk, neo, nlo)
+
+
+def transform_trans_inv_k_dev(bk, s, H_k_dev, h_spin_index):
+    """Re[ sum_k B_k^dagger H_k B_k ] / nkpts for spin s  (slater_helper.py:37-50) -> (neo, neo) device tensor."""
+    dev = get_device()
+    nk, nlo, neo = bk.nk, bk.nlo, bk.neo
+    a_index = s * nk + np.arange(nk)
+    h_index = h_spin_index * nk + np.arange(nk)
+    # V^T[k][n][l'] = sum_l B_k^T[n][l] H_k[l'][l]  ;  R[k][m][n] = sum_l' conj(B_k^T[m][l']) V^T[k][n][l']
+    VT = dev.empty((nk, neo, nlo), torch.complex128)
+    segs = np.zeros((nk, 4), dtype=np.int32)
+    segs[:, 0] = a_index
+    segs[:, 1] = h_index
+    dev.zgemm_tn(bk.bkT, H_k_dev, segs, VT, c_off=np.arange(nk, dtype=np.int64) * neo * nlo, s_outer=nlo,
+                 nbatch=nk, nseg=1)
+    R = dev.empty((nk, neo, neo), torch.complex128)
+    segs2 = np.zeros((nk, 4), dtype=np.int32)
+    segs2[:, 0] = a_index
+    segs2[:, 1] = np.arange(nk)
+    segs2[:, 2] = 1
+    dev.zgemm_tn(bk.bkT, VT, segs2, R, c_off=np.arange(nk, dtype=np.int64) * neo * neo, s_outer=neo, nbatch=nk,
+                 nseg=1)
+    res, imag = dev.ksum_real(R, scale=1.0 / float(nk))
+    if imag > IMAG_DISCARD_TOL:
+        warnings.warn("transform_trans_inv_k: has imag part %s" % imag)
+    return res
+
+
+def transform_h1_dev(H1_k, bk):
+    """slater.py:690-697 (`transform_h1` / `foldRho_k`) -> (spin, neo, neo) float64 device tensor."""
+    H = _zdev(H1_k)
+    if H.dim() == 3:
+        H = H[None]
+    hs = H.shape[0]
+    H3 = H.reshape(-1, H.shape[-2], H.shape[-1])
+    return torch.stack([transform_trans_inv_k_dev(bk, s, H3, min(s, hs - 1)) for s in range(bk.spin)])
+
+
+def transform_h1(H1_k, basis_k):
+    """slater.py:690-697, numpy in / numpy out."""
+    return transform_h1_dev(H1_k, _BasisK(basis_k)).cpu().numpy()
+
+
+foldRho_k = transform_h1
+
+
+def transform_trans_inv_k(basis_k, H_k):
+    """slater_helper.py:37-50, numpy in / numpy out."""
+    bk = _BasisK(np.asarray(basis_k)[None])
+    return transform_trans_inv_k_dev(bk, 0, _zdev(np.asarray(H_k)), 0).cpu().numpy()
+
+
+def _s4_blocks_dev(H2, norb):
+    """any accepted H2 layout -> list of (npair, npair) device tensors (s4)."""
+    dev = get_device()
+    if isinstance(H2, torch.Tensor) and H2.dim() == 3:
+        return [H2[i] for i in range(H2.shape[0])]
+    H2 = H2.cpu().numpy() if isinstance(H2, torch.Tensor) else np.asarray(H2)
+    fmt, spin_dim = get_eri_format(H2, norb)
+    if spin_dim == 0:
+        H2 = H2[None]
+    npair = norb * (norb + 1) // 2
+    idx = np.tril_indices(norb)
+    out = []
+    for blk in H2:
+        if fmt == 's4':
+            e4 = blk.reshape(npair, npair)
+        elif fmt == 's1':
+            e4 = blk.reshape(norb, norb, norb, norb)[idx[0], idx[1]][:, idx[0], idx[1]]
+        else:   # s8
+            e4 = np.zeros((npair, npair))
+            t = np.tril_indices(npair)
+            e4[t] = blk.reshape(-1)
+            e4[(t[1], t[0])] = blk.reshape(-1)
+        out.append(dev.to_device(np.ascontiguousarray(e4), torch.float64))
+    return out
+
+
+def get_veff_dev(rdm1_emb, eri4_blocks):
+    """HF effective potential from embedding ERI and density (slater.py:478-523 -> solver/scf.py:255-352).
+    rdm1_emb: (spin, n, n) device; eri4_blocks: 1 block (restricted / UHF with one ERI) or 3 blocks aa, bb, ab
+    (the order embHam uses, slater.py:461-462).  Returns (spin, n, n) device."""
+    dev = get_device()
+    spin = rdm1_emb.shape[0]
+    dm = rdm1_emb.contiguous()
+    if spin == 1:
+        vj, vk = dev.jk_s4(eri4_blocks[0], dm[0])
+        return (vj - vk * 0.5)[None]                                    # scf.py:347-348
+    if len(eri4_blocks) == 1:                                            # UHF with a spin-free ERI (scf.py:303-309)
+        vj0, vk0 = dev.jk_s4(eri4_blocks[0], dm[0])
+        vj1, vk1 = dev.jk_s4(eri4_blocks[0], dm[1])
+        return torch.stack([vj0 + vj1 - vk0, vj0 + vj1 - vk1])
+    assert len(eri4_blocks) == 3 and spin == 2                          # UIHF (scf.py:310-331)
+    vj00, vk00 = dev.jk_s4(eri4_blocks[0], dm[0])
+    vj11, vk11 = dev.jk_s4(eri4_blocks[1], dm[1])
+    vj01, _ = dev.jk_s4(eri4_blocks[2], dm[1], with_k=False)            # J on alpha from beta density
+    eri_ba = eri4_blocks[2].t().contiguous()
+    vj10, _ = dev.jk_s4(eri_ba, dm[0], with_k=False)                    # J on beta from alpha density
+    return torch.stack([vj00 + vj01 - vk00, vj11 + vj10 - vk11])        # scf.py:350 with vj=((00,11),(01,10))
+
+
+def get_veff(rdm1, eri, hyb=1.0):
+    """slater.py:478-523 (HF branch), numpy in / numpy out."""
+    if hyb != 1.0:
+        raise NotImplementedError("DFT / hybrid branches are outside the hot path")
+    rdm1 = np.asarray(rdm1, dtype=np.double)
+    if rdm1.ndim == 2:
+        rdm1 = rdm1[None]
+    dev = get_device()
+    n = rdm1.shape[-1]
+    return get_veff_dev(dev.to_device(rdm1, torch.float64), _s4_blocks_dev(eri, n)).cpu().numpy()
+
+
+def unit2emb(H2_unit, neo):
+    """slater_helper.py:494-517 (ndarray branch): zero-pad the impurity-block ERI to the embedding space."""
+    H2_unit = np.asarray(H2_unit)
+    spin_pair = H2_unit.shape[0]
+    npair = neo * (neo + 1) // 2
+    if H2_unit.ndim == 5:
+        H2_emb = np.zeros((spin_pair, neo, neo, neo, neo))
+    elif H2_unit.ndim == 3:
+        H2_emb = np.zeros((spin_pair, npair, npair))
+    elif H2_unit.ndim == 2:
+        H2_emb = np.zeros((spin_pair, npair * (npair + 1) // 2))
+    else:
+        raise ValueError
+    H2_emb[tuple(map(slice, H2_unit.shape))] = H2_unit
+    return H2_emb
+
+
+# ---------------------------------------------------------------------------------------------------------
+# get_emb_Ham
+# ---------------------------------------------------------------------------------------------------------
+def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwargs):
+    """slater.py:372-476, ab-initio branch (438-472).  Returns (H2 numpy in the requested symmetry,
+    s4 device blocks for the J/K step)."""
+    if getattr(lattice, "is_model", False):
+        raise NotImplementedError("model Hamiltonians are outside the ab-initio hot path")
+    nbasis = basis.shape[-1]
+    eri_symmetry = lattice.eri_symmetry
+    cell, mydf, C_ao_lo = lattice.cell, lattice.df, lattice.C_ao_lo
+    common = dict(kscaled_center=kwargs.get("kscaled_center", None), max_memory=kwargs.get("max_memory", None),
+                  swap_idx=kwargs.get("swap_idx", None), t_reversal_symm=kwargs.get("t_reversal_symm", True),
+                  incore=kwargs.get("incore", True), fout=kwargs.get("fout", "H2.h5"),
+                  use_mpi=kwargs.get("use_mpi", False))
+    for k in ("source", "group", "kl_group", "stats"):
+        if k in kwargs:
+            common[k] = kwargs[k]
+    if int_bath:
+        # build once in s4 on the device, keep it there for J/K, re-lay out for the caller
+        eri4 = get_emb_eri(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, symmetry=4, return_device=True, **common)
+        order = [0, 2, 1] if (last_aabb and eri4.shape[0] == 3) else list(range(eri4.shape[0]))   # l.461-462
+        blocks = [eri4[i] for i in order]
+        dev = get_device()
+        if eri_symmetry == 4:
+            H2 = torch.stack(blocks).cpu().numpy()
+        elif eri_symmetry == 1:
+            H2 = np.stack([dev.restore_s1(b, nbasis).cpu().numpy() for b in blocks])
+        elif eri_symmetry == 8:
+            assert len(blocks) == 1
+            H2 = dev.restore_s8(blocks[0], nbasis).cpu().numpy()[None]
+        else:
+            raise ValueError("unknown eri_symmetry %s" % eri_symmetry)
+        return H2, blocks
+    H2 = get_unit_eri(cell, mydf, C_ao_lo=C_ao_lo, symmetry=eri_symmetry, **common)
+    if last_aabb and H2.shape[0] == 3:
+        H2 = H2[[0, 2, 1]]
+    H2 = unit2emb(H2, nbasis)                                            # l.472
+    return H2, None
+
+
+def _embHam1e(lattice, basis, vcor, H2_emb, eri4_blocks, int_bath=True, add_vcor=False, **kwargs):
+    """slater.py:525-688, interacting-bath HF branch (590-605, 639-643).  Side effect: lattice.JK_core."""
+    if not int_bath:
+        raise NotImplementedError("the non-interacting-bath one-body branch is outside the hot path "
+                                  "(its ERI is available through get_unit_eri / unit2emb)")
+    for flag in ("dft", "qsgw"):
+        if kwargs.get(flag, False):
+            raise NotImplementedError("%s branch is outside the hot path" % flag)
+    spin = basis.shape[0]
+    nbasis = basis.shape[-1]
+    bk = _BasisK(lattice.R2k_basis(basis))                               # l.533
+    hcore_emb = transform_h1_dev(lattice.hcore_lo_k, bk)                 # l.542
+    ovlp_emb = transform_h1_dev(lattice.ovlp_lo_k, bk)                   # l.544
+    rdm1_emb = transform_h1_dev(lattice.rdm1_lo_k, bk)                   # l.560 (foldRho_k)
+    fock_k = _zdev(lattice.hcore_lo_k) + _zdev(lattice.vhf_lo_k)         # l.592
+    H1 = transform_h1_dev(fock_k, bk)                                    # l.597
+    if eri4_blocks is None:
+        eri4_blocks = _s4_blocks_dev(H2_emb, nbasis)
+    JK_emb = get_veff_dev(rdm1_emb, eri4_blocks)                         # l.600
+    H1 = H1 - JK_emb                                                     # l.605
+    JK_core = H1 - hcore_emb                                             # l.640
+    H1 = H1.cpu().numpy()
+    lattice.JK_core = JK_core.cpu().numpy()                              # l.643
+    ovlp_emb = ovlp_emb.cpu().numpy()
+    if ovlp_emb.ndim == 3 and ovlp_emb.shape[0] == 1:
+        ovlp_emb = ovlp_emb[0]                                           # l.545-546
+    if add_vcor:                                                         # l.676-687 (small host matrices)
+        b = np.asarray(basis)
+        for s in range(spin):
+            v = np.asarray(vcor.get()[s])
+            H1[s] += sum(b[s, i].T.dot(v).dot(b[s, i]) for i in range(b.shape[1]))
+            if not kwargs.get("fitting", False):
+                H1[s] -= b[s, 0].T.dot(v).dot(b[s, 0])
+    return H1, ovlp_emb
+
+
+def get_emb_Ham(lattice, basis, vcor, local=True, **kwargs):
+    """slater.py:320-370.  Returns (Integral, None); H2 blocks come in the order aa, bb, ab (l.461-462)."""
+    basis = np.asarray(basis)
+    spin = basis.shape[0]
+    nbasis = basis.shape[-1]
+    H2_given = kwargs.get("H2_given", None)
+    blocks = None
+    if H2_given is None:
+        if kwargs.get("H2_fname", None) is not None:
+            raise NotImplementedError("loading H2 from HDF5 needs h5py, which this build does not depend on")
+        H2, blocks = _embHam2e(lattice, basis, vcor, local, **kwargs)
+    else:
+        H2 = H2_given
+    kw1 = {k: v for k, v in kwargs.items() if k != "last_aabb"}
+    H1, ovlp_emb = _embHam1e(lattice, basis, vcor, H2, blocks, **kw1)
+    H0 = lattice.getH0()
+    if isinstance(H2, np.ndarray):
+        H2 = {"ccdd": H2}
+    ImpHam = Integral(nbasis, spin == 1, False, H0, {"cd": H1}, H2, ovlp=ovlp_emb)
+    return ImpHam, None
+
+
+embHam = get_emb_Ham

@@ -1,0 +1,200 @@
+"""Seeded synthetic inputs of the named (nkpts, nao, naux, neo) shapes: a duck-typed cell, a GDF provider with
+PySCF's symmetry structure, localized-orbital coefficients, embedding bases and mean-field matrices.
+
+PySCF and h5py are not available in this image, so benchmarks and parity tests use these providers
+(SURVEY.md section 8d).  The GDF tensor obeys, by construction,
+    L(k_j, k_i)[L, q, p]  = conj(L(k_i, k_j)[L, p, q])          (what pyscf's _load3c returns for swapped pairs)
+    L(-k_i, -k_j)         = conj(L(k_i, k_j))                    (time reversal)
+so the time-reversal path of the reference is physically equivalent to the plain path.  Values come from a
+counter-based 32-bit hash, reproduced bit for bit by the device generator (`synth_block_kernel` in
+csrc/aux_kernels.cuh) so that a 2.6 TB tensor never has to cross PCIe in throughput runs.
+"""
+import numpy as np
+
+from .schedule import make_kpts_scaled, cell_vectors, kpt_member
+
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def lowbias32(x):
+    """32-bit integer hash (same constants as the device twin)."""
+    x = np.asarray(x, dtype=np.uint64) & _M32
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & _M32
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846CA68B)) & _M32
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def _u(key, idx):
+    h = lowbias32(np.asarray(idx, dtype=np.uint64) ^ np.uint64(key)).astype(np.uint32)
+    return h.view(np.int32).astype(np.float64) * 4.656612873077393e-10   # 2^-31
+
+
+class SyntheticCell(object):
+    """The four members of a PySCF Cell the path touches (eri_transform.py:256,266; fourier.py:40,87)."""
+
+    def __init__(self, nao, a=None, dimension=3):
+        self._nao = int(nao)
+        self._a = np.eye(3) * 4.0 if a is None else np.asarray(a, dtype=float)
+        self.dimension = dimension
+        self.low_dim_ft_type = None
+
+    def nao_nr(self):
+        return self._nao
+
+    def lattice_vectors(self):
+        return self._a
+
+    def reciprocal_vectors(self):
+        return 2.0 * np.pi * np.linalg.inv(self._a).T
+
+    def get_scaled_kpts(self, kpts_abs):
+        return np.dot(np.asarray(kpts_abs), self._a.T) / (2.0 * np.pi)
+
+    def get_abs_kpts(self, kpts_scaled):
+        return np.dot(np.asarray(kpts_scaled), self.reciprocal_vectors())
+
+
+class SyntheticGDF(object):
+    """In-memory GDF provider: .kpts / .kpts_scaled / .kmesh / .nao / .naux / .blockdim / .load(ki, kj)."""
+
+    def __init__(self, kmesh, nao, naux, seed=0, scale=None, cell=None):
+        self.kmesh = [int(x) for x in kmesh]
+        self.nao = int(nao)
+        self.naux = int(naux)
+        self.seed = int(seed) & 0xFFFFFFFF
+        self.cell = cell if cell is not None else SyntheticCell(nao)
+        self.kpts_scaled = make_kpts_scaled(self.kmesh)
+        self.kpts = self.cell.get_abs_kpts(self.kpts_scaled)
+        self.nkpts = len(self.kpts_scaled)
+        self.scale = float(scale) if scale is not None else float(np.sqrt(self.nkpts / float(self.naux)))
+        self.blockdim = 240          # pyscf GDF default
+        self.max_memory = 4000
+        self._cderi = "<synthetic>"
+        self.minus = [int(kpt_member(-k, self.kpts_scaled)[0]) for k in self.kpts_scaled]
+        assert 2 * self.naux * self.nao * self.nao < 2 ** 32
+
+    def pair_key(self, a, b):
+        inner = int(lowbias32(np.uint64((a * self.nkpts + b + 0x9E3779B9) & 0xFFFFFFFF)))
+        return int(lowbias32(np.uint64(self.seed ^ inner)))
+
+    def keys(self, ki, kj):
+        mi, mj = self.minus[ki], self.minus[kj]
+        return (self.pair_key(ki, kj), self.pair_key(kj, ki), self.pair_key(mi, mj), self.pair_key(mj, mi))
+
+    def load(self, ki, kj, aux_slice=None):
+        """(naux, nao, nao) complex128 block L(k_i, k_j) (host twin of the device generator)."""
+        nao = self.nao
+        l0, l1 = (0, self.naux) if aux_slice is None else aux_slice
+        k_ij, k_ji, k_mij, k_mji = self.keys(ki, kj)
+        L = np.arange(l0, l1, dtype=np.uint64)[:, None, None]
+        p = np.arange(nao, dtype=np.uint64)[None, :, None]
+        q = np.arange(nao, dtype=np.uint64)[None, None, :]
+        d = np.uint64(2) * ((L * np.uint64(nao) + p) * np.uint64(nao) + q)
+        t = np.uint64(2) * ((L * np.uint64(nao) + q) * np.uint64(nao) + p)
+        one = np.uint64(1)
+        re = _u(k_ij, d) + _u(k_ji, t) + _u(k_mij, d) + _u(k_mji, t)
+        im = _u(k_ij, d + one) - _u(k_ji, t + one) - _u(k_mij, d + one) + _u(k_mji, t + one)
+        s = 0.25 * self.scale
+        out = np.empty((l1 - l0, nao, nao), dtype=np.complex128)
+        out.real = s * re
+        out.imag = s * im
+        return out
+
+
+def _trs_fill(nk, minus, make):
+    """fill out[k] = make(k) for one member of each {k, -k} pair and conj for the partner (real at k = -k)."""
+    out = [None] * nk
+    for k in range(nk):
+        if out[k] is not None:
+            continue
+        v = make(k)
+        if minus[k] == k:
+            v = v.real.astype(np.complex128) if np.iscomplexobj(v) else v
+        out[k] = v
+        out[minus[k]] = v.conj()
+    return np.asarray(out)
+
+
+def make_C_ao_lo(kmesh, nao, nlo=None, seed=1, spin=None):
+    """Unitary (orthonormal-column) C_ao_lo[k] with C(-k) = conj(C(k)); shape ((spin,) nkpts, nao, nlo)."""
+    nlo = nao if nlo is None else nlo
+    ks = make_kpts_scaled(kmesh)
+    nk = len(ks)
+    minus = [int(kpt_member(-k, ks)[0]) for k in ks]
+    rng = np.random.default_rng(seed)
+
+    def one_spin():
+        def make(k):
+            a = rng.standard_normal((nao, nlo)) + 1j * rng.standard_normal((nao, nlo))
+            if minus[k] == k:
+                a = a.real
+            qmat, _ = np.linalg.qr(a)
+            return qmat.astype(np.complex128)
+        return _trs_fill(nk, minus, make)
+
+    if spin is None:
+        return one_spin()
+    return np.asarray([one_spin() for _ in range(spin)])
+
+
+def make_emb_basis(kmesh, nlo, neo, nimp=None, seed=2, spin=1):
+    """Real orthonormal basis (spin, ncells, nlo, neo): identity on the first nimp orbitals of cell 0 (the impurity,
+    libdmet/routine/slater.py:212) and a random orthonormal bath on the environment."""
+    ncells = int(np.prod(kmesh))
+    nimp = min(nlo, neo // 2) if nimp is None else nimp
+    nbath = neo - nimp
+    rng = np.random.default_rng(seed)
+    out = np.zeros((spin, ncells * nlo, neo))
+    for s in range(spin):
+        out[s, :nimp, :nimp] = np.eye(nimp)
+        if nbath > 0:
+            b, _ = np.linalg.qr(rng.standard_normal((ncells * nlo - nimp, nbath)))
+            out[s, nimp:, nimp:] = b
+    return out.reshape(spin, ncells, nlo, neo)
+
+
+def make_hermitian_k(kmesh, n, seed=3, spin=None, scale=1.0, posdef=False):
+    """Hermitian h[k] with h(-k) = conj(h(k)) (real in R space); shape ((spin,) nkpts, n, n)."""
+    ks = make_kpts_scaled(kmesh)
+    nk = len(ks)
+    minus = [int(kpt_member(-k, ks)[0]) for k in ks]
+    rng = np.random.default_rng(seed)
+
+    def one_spin():
+        def make(k):
+            a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+            if minus[k] == k:
+                a = a.real.astype(np.complex128)
+            h = (a + a.conj().T) * (0.5 * scale)
+            if posdef:
+                h = h.dot(h.conj().T) / n + np.eye(n)
+            return h
+        return _trs_fill(nk, minus, make)
+
+    if spin is None:
+        return one_spin()
+    return np.asarray([one_spin() for _ in range(spin)])
+
+
+def make_rdm1_k(fock_k, nocc):
+    """Idempotent per-k density matrix from the lowest `nocc` eigenvectors of fock_k (nkpts, n, n) (orthonormal
+    basis).  Keeps the time-reversal structure of fock_k."""
+    out = np.zeros_like(fock_k)
+    for k in range(fock_k.shape[0]):
+        e, v = np.linalg.eigh(fock_k[k])
+        out[k] = v[:, :nocc].dot(v[:, :nocc].conj().T)
+    return out
+
+
+def trs_block_count(kmesh, t_reversal_symm=True):
+    """number of (k_i, k_j) blocks / Gram products in the reference schedule of a mesh."""
+    from .schedule import build_schedule
+    sch = build_schedule(make_kpts_scaled(kmesh), t_reversal_symm)
+    return sch.nblocks, sch.ngram
+
+
+__all__ = ["SyntheticCell", "SyntheticGDF", "make_C_ao_lo", "make_emb_basis", "make_hermitian_k", "make_rdm1_k",
+           "trs_block_count", "cell_vectors"]
