@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the embedding-ERI hot path (`get_emb_eri`, GDF, restricted, s4, time-reversal symmetry).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload target|small|...]
+
+One "step" = one complete `get_emb_eri` build of the named workload: C_ao_emb construction, stage 1 (two half
+transformations per (k_i,k_j) block), symmetrise + pack, stage 3 (Gram products), mirror.  Prints ONE JSON line.
+
+value      algorithmic FP64 TFLOP/s of the whole job, (F1 + F3) / time, inputs resident in HBM (BASELINE.md section 3:
+           F1 = 8 naux nao neo (nao+neo) B,  F3 = naux npair (npair+1) G)
+e2e        same metric through the public API with HOST inputs: GDF blocks are fetched from a (pinned) host provider
+           and copied host->device inside the timed region, the ERI is copied back to the host
+roofline   stage-1 complex GEMM kernel (DMMA), timed live with CUDA events on its launch stream
+cpu_baseline / --impl reference
+           the numpy oracle (the reference cannot be imported here: PySCF / h5py are absent) on the host cores,
+           on a bounded sample of the same workload (a few (k_i,k_j) blocks + one Gram product), scaled by block
+           and Gram counts to the whole job
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kmesh, nao, naux, neo)
+    "target": ([4, 4, 4], 200, 1000, 150),       # BASELINE.json north_star / BASELINE.md section 3
+    "mid": ([2, 2, 4], 200, 1000, 150),
+    "small": ([2, 2, 2], 100, 500, 50),          # sweep minimum
+    "tiny": ([1, 2, 3], 24, 64, 20),
+}
+
+
+def flops(kmesh, nao, naux, neo, nspin=1):
+    from libdmet_preview_b200.synthetic import trs_block_count
+    B, G = trs_block_count(kmesh, True)
+    npair = neo * (neo + 1) // 2
+    F1 = 8.0 * naux * nao * neo * (nao + neo) * nspin * B
+    F3 = float(naux) * npair * (npair + 1) * G
+    return F1, F3, B, G
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = False
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle) on a bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def cpu_sample(kmesh, nao, naux, neo, nblocks=2, budget_s=25.0):
+    """Time the oracle's stage 1 (transform_ao_to_emb + hermi_sum + pack_tril + accumulate, in the reference's
+    240-row chunks) on `nblocks` blocks and one stage-3 Gram product; scale to the whole job."""
+    from oracle import eri_transform as o
+    from oracle import pyscf_lib as olib
+    from libdmet_preview_b200 import synthetic
+    F1, F3, B, G = flops(kmesh, nao, naux, neo)
+    nk = int(np.prod(kmesh))
+    npair = neo * (neo + 1) // 2
+    rng = np.random.default_rng(0)
+    C_ao_emb = (rng.standard_normal((1, nk, nao, neo)) + 1j * rng.standard_normal((1, nk, nao, neo))) / nk ** 0.75
+    Lblk = (rng.standard_normal((naux, nao * nao)) + 1j * rng.standard_normal((naux, nao * nao)))
+    Lij_s4 = np.zeros((1, naux, npair), dtype=np.complex128)
+    blksize = 240
+    t_blocks = []
+    t0 = time.perf_counter()
+    for b in range(nblocks):
+        tb = time.perf_counter()
+        for l0 in range(0, naux, blksize):
+            Lpq = Lblk[l0:l0 + blksize]
+            Lij = o.transform_ao_to_emb(Lpq, C_ao_emb, b % nk, (b + 1) % nk).reshape(-1, neo, neo)
+            olib.hermi_sum(Lij, axes=(0, 2, 1), hermi=olib.SYMMETRIC, inplace=True)
+            Lij_s4[:, l0:l0 + Lpq.shape[0]] += olib.pack_tril(Lij).reshape(1, -1, npair)
+        t_blocks.append(time.perf_counter() - tb)
+        if time.perf_counter() - t0 > budget_s * 0.6:
+            break
+    t_block = min(t_blocks)
+    X = np.ascontiguousarray(Lij_s4[0].real)
+    eri = np.zeros((npair, npair))
+    tg = time.perf_counter()
+    olib.dot(X.T, X, 1.0, eri, 1)
+    t_gram = time.perf_counter() - tg
+    t_job = t_block * B + t_gram * G
+    return {"t_block_s": t_block, "t_gram_s": t_gram, "t_job_s": t_job, "tflops": (F1 + F3) / t_job / 1e12,
+            "sample": "%d of %d (ki,kj) blocks of stage 1 (240-row chunks) + 1 of %d Gram products, extrapolated "
+                      "linearly by block/Gram count" % (len(t_blocks), B, G)}
+
+
+def run_reference(args):
+    kmesh, nao, naux, neo = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    F1, F3, B, G = flops(kmesh, nao, naux, neo)
+    times = []
+    res = None
+    for it in range(args.warmup + args.steps):
+        res = cpu_sample(kmesh, nao, naux, neo, nblocks=1 if it < args.warmup else 2, budget_s=20.0)
+        if it >= args.warmup:
+            times.append(res["t_job_s"])
+    t = float(np.mean(times))
+    val = (F1 + F3) / t / 1e12
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    line = {"impl": "reference", "metric": "get_emb_eri_fp64_tflops", "value": val, "unit": "TFLOP/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128 GEMMs)",
+            "data": "synthetic", "config": config_dict(args, kmesh, nao, naux, neo, B, G),
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                             "sample": res["sample"] + "; numpy/OpenBLAS zgemm+dgemm, all host threads; the "
+                             "reference itself cannot be imported (PySCF, h5py absent)"},
+            "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "get_emb_eri_seconds": t}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, kmesh, nao, naux, neo, B, G):
+    return {"workload": "%s: get_emb_eri GDF restricted s4 time-reversal, kmesh %s nkpts %d nao %d naux %d neo %d "
+                        "(%d (ki,kj) blocks, %d Gram products)" % (args.workload, "x".join(map(str, kmesh)),
+                                                                  int(np.prod(kmesh)), nao, naux, neo, B, G),
+            "kmesh": kmesh, "nao": nao, "naux": naux, "neo": neo, "symmetry": 4, "t_reversal_symm": True}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+class HostPoolProvider(object):
+    """GDF provider over pinned host memory: `npool` distinct synthetic blocks, block (ki,kj) -> pool slot by a fixed
+    map.  What a host-RAM resident cderi looks like to `get_emb_eri` (the full 758 GB tensor of the target shape is
+    not materialised on the host; every block still crosses PCIe inside the timed region)."""
+
+    def __init__(self, gdf, npool):
+        import torch
+        from libdmet_preview_b200.device import get_device
+        dev = get_device()
+        self.kpts_scaled, self.kmesh, self.nao, self.naux = gdf.kpts_scaled, gdf.kmesh, gdf.nao, gdf.naux
+        self.kpts, self.cell = gdf.kpts, gdf.cell
+        nk = len(self.kpts_scaled)
+        self.npool = npool
+        self.pool = torch.empty((npool, gdf.naux, gdf.nao, gdf.nao), dtype=torch.complex128, pin_memory=True)
+        tmp = dev.empty((gdf.naux, gdf.nao, gdf.nao), torch.complex128)
+        for s in range(npool):
+            dev.synth_block(tmp, gdf.naux, gdf.nao, gdf.keys(s % nk, (s // nk) % nk), gdf.scale)
+            self.pool[s].copy_(tmp)
+        dev.synchronize()
+        self.nk = nk
+
+    def load(self, ki, kj):
+        return self.pool[(ki * self.nk + kj) % self.npool]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    from libdmet_preview_b200 import synthetic, eri_transform as et
+    from libdmet_preview_b200 import dist as ldist
+    from libdmet_preview_b200.device import get_device
+    from libdmet_preview_b200.schedule import build_schedule
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = get_device(local_rank)
+
+    kmesh, nao, naux, neo = WORKLOADS[args.workload]
+    F1, F3, B, G = flops(kmesh, nao, naux, neo)
+    gdf = synthetic.SyntheticGDF(kmesh, nao, naux, seed=2026)
+    C_ao_lo_h = synthetic.make_C_ao_lo(kmesh, nao, seed=1)
+    basis_h = synthetic.make_emb_basis(kmesh, nao, neo, seed=2)
+    C_ao_lo = dev.to_device(C_ao_lo_h, torch.complex128)
+    basis = dev.to_device(basis_h, torch.float64)
+    schedule = build_schedule(gdf.kpts_scaled, True)
+    my_units = ldist.rank_units(schedule, nao, naux, neo, 1, world)[rank]
+    my_blocks = [(u, blk) for u in my_units for blk in schedule.units[u][2]]
+
+    # ---- resident store of L blocks (inputs in HBM before the timed region) ----
+    blk_bytes = naux * nao * nao * 16
+    free_b, total_b = torch.cuda.mem_get_info()
+    npair = neo * (neo + 1) // 2
+    work_b = (2 * args.group * blk_bytes * 0 + args.group * naux * neo * nao * 16 + 2 * naux * neo * neo * 16 +
+              npair * args.kl_group * 2 * naux * 8 + 2 * npair * npair * 8) + (6 << 30)
+    nslots = int(max(1, min(len(my_blocks), (free_b - work_b) // blk_bytes)))
+    if args.store_slots:
+        nslots = min(nslots, args.store_slots)
+    store = dev.empty((nslots, naux, nao, nao), torch.complex128)
+    store_map = {}
+    for n, (u, (ki, kj, sym)) in enumerate(my_blocks):
+        slot = n % nslots
+        if n < nslots:
+            dev.synth_block(store[slot], naux, nao, gdf.keys(ki, kj), gdf.scale)
+        store_map[(ki, kj)] = slot
+    dev.synchronize()
+
+    stats = {}
+
+    def step(collect=None):
+        CT = et.build_CT(gdf, C_ao_lo, basis)
+        eri = et.emb_eri_device(gdf, CT, schedule=schedule, units=my_units, store=store, store_map=store_map,
+                                group=args.group, kl_group=args.kl_group, stats=collect)
+        if world > 1:
+            dist.reduce(eri, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            eri = et.finalize_eri(eri, neo, 4, 1)
+        return eri
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = dev.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    zg_ms = dg_ms = 0.0
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            st = {}
+            out = step(st)
+            zg_ms += st["zgemm_ms"]
+            dg_ms += st["dgemm_ms"]
+        e1.record()
+        barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = dev.launch_count() - l0
+    checksum = float(out.sum().item()) if rank == 0 else 0.0
+    del out
+    tt = torch.tensor([t_dev, zg_ms, dg_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_step = tt[0].item() / args.steps
+    value = (F1 + F3) / t_step / 1e12
+
+    # ---- roofline of the dominant kernel (stage-1 zgemm), events recorded on its launch stream ----
+    F1_mine = F1 * len(my_blocks) / float(B)
+    with open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")) as f:
+        pk = json.load(f)
+    peak = pk["dgemm_8192_sustained_tflops"]
+    ach = F1_mine * args.steps / (zg_ms * 1e-3) / 1e12 if zg_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "zgemm_traffic_r01.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "zgemm_tn_kernel (stage 1: both half transformations)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+                "traffic": traffic,
+                "peak_source": "cuBLAS DGEMM 8192^3 sustained 4 s on this pool's B200 (tools/probe_peaks.py -> "
+                               "profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json carries no FP64 figure",
+                "share_of_step": zg_ms * 1e-3 / (t_step * args.steps),
+                "stage3_dgemm": {"achieved": (F3 * len(my_units) / len(schedule.units)) * args.steps /
+                                 (dg_ms * 1e-3) / 1e12 if dg_ms > 0 else None, "unit": "TFLOP/s"}}
+
+    # ---- end to end through the public API with host buffers (N=1 only) ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        del store
+        torch.cuda.empty_cache()
+        host = HostPoolProvider(gdf, args.host_pool)
+        n_e2e = max(1, args.e2e_steps)
+        st = {}
+        et.get_emb_eri(gdf.cell, host, C_ao_lo=C_ao_lo_h, basis=basis_h, symmetry=4, source="host",
+                       group=args.group, kl_group=args.kl_group)          # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            res = et.get_emb_eri(gdf.cell, host, C_ao_lo=C_ao_lo_h, basis=basis_h, symmetry=4, source="host",
+                                 group=args.group, kl_group=args.kl_group, stats=st)
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": (F1 + F3) / t_e2e / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": int(st["h2d_bytes"] + C_ao_lo_h.nbytes + basis_h.nbytes),
+               "d2h_bytes_per_step": int(res.nbytes), "seconds_per_step": t_e2e, "steps": n_e2e,
+               "note": "get_emb_eri(cell, host_provider, numpy C_ao_lo, numpy basis) -> numpy; every (ki,kj) block "
+                       "is copied from pinned host memory inside the call (PCIe-bound at this shape)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu:
+        c = cpu_sample(kmesh, nao, naux, neo)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        cpu = {"value": c["tflops"], "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": c["sample"],
+               "seconds_whole_job_extrapolated": c["t_job_s"]}
+
+    line = {"metric": "get_emb_eri_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128 GEMMs, DMMA)",
+            "data": "synthetic (seeded counter-based GDF tensor generated on the device; %d resident blocks per GPU, "
+                    "the %d-block schedule cycles over them)" % (nslots, len(my_blocks)),
+            "config": dict(config_dict(args, kmesh, nao, naux, neo, B, G), parallelism="kL-sharded x%d" % world,
+                           l2_policy="inputs larger than L2 (each GDF block %.0f MB, ERI %.0f MB)" %
+                           (blk_bytes / 1e6, npair * npair * 8 / 1e6), group=args.group, kl_group=args.kl_group),
+            "get_emb_eri_seconds": t_step, "flops_per_step": F1 + F3, "clocks": clk.summary(),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "checksum": checksum}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
+    ap.add_argument("--group", type=int, default=4)
+    ap.add_argument("--kl-group", dest="kl_group", type=int, default=4)
+    ap.add_argument("--store-slots", dest="store_slots", type=int, default=0)
+    ap.add_argument("--host-pool", dest="host_pool", type=int, default=16)
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=1)
+    ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

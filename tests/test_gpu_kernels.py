@@ -1,0 +1,137 @@
+"""GPU: each kernel of libldm_b200.so, called through the C ABI, against numpy on the same seeded inputs.
+Tolerances are absolute on O(1)..O(10) data; FP64 throughout."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _z(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+@pytest.mark.parametrize("za,zb,M,N,K,nseg,nbatch,cA,cB,acc", [
+    (1, 1, 64, 40, 8, 1, 1, 0, 0, False),
+    (1, 1, 200, 150, 200, 1, 1, 0, 0, False),
+    (3, 2, 333, 37, 26, 2, 3, 0, 1, False),
+    (3, 2, 1000, 150, 52, 3, 2, 1, 0, True),
+    (2, 4, 1031, 100, 201, 2, 2, 1, 1, False),
+    (2, 2, 700, 6, 3, 1, 2, 0, 0, False),
+    (1, 1, 1, 1, 1, 1, 1, 1, 1, True),
+    (2, 3, 129, 161, 9, 2, 1, 0, 0, False),      # two N tiles
+    (1, 1, 517, 200, 31, 1, 1, 0, 1, False),     # N = 200 -> 256x40 tile family
+    (1, 1, 300, 48, 17, 1, 1, 0, 0, False),      # N = 48 -> b=3 family
+])
+def test_zgemm_tn(dev, za, zb, M, N, K, nseg, nbatch, cA, cB, acc):
+    rng = np.random.default_rng(M + N + K)
+    A, B = _z(rng, za, M, K), _z(rng, zb, N, K)
+    segs = np.zeros((nbatch, nseg, 4), dtype=np.int32)
+    segs[..., 0] = rng.integers(0, za, (nbatch, nseg))
+    segs[..., 1] = rng.integers(0, zb, (nbatch, nseg))
+    segs[..., 2], segs[..., 3] = cA, cB
+    C0 = _z(rng, nbatch, M, N)
+    ref = C0.copy() if acc else np.zeros_like(C0)
+    for b in range(nbatch):
+        for s in range(nseg):
+            a = A[segs[b, s, 0]].conj() if cA else A[segs[b, s, 0]]
+            bb = B[segs[b, s, 1]].conj() if cB else B[segs[b, s, 1]]
+            ref[b] += 0.75 * (a @ bb.T)
+    Cd = dev.to_device(C0, torch.complex128)
+    dev.zgemm_tn(dev.to_device(A, torch.complex128), dev.to_device(B, torch.complex128), segs, Cd,
+                 c_off=np.arange(nbatch) * M * N, s_outer=N, alpha=0.75, accumulate=acc, nbatch=nbatch, nseg=nseg)
+    assert np.abs(Cd.cpu().numpy() - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def test_zgemm_strided_output(dev):
+    """the stage-1a epilogue: rows r = (L, p) written transposed as out[L][c][p]"""
+    rng = np.random.default_rng(7)
+    naux, nao, neo = 5, 13, 11
+    A, B = _z(rng, 1, naux * nao, nao), _z(rng, 1, neo, nao)
+    out = dev.empty((naux, neo, nao), torch.complex128)
+    dev.zgemm_tn(dev.to_device(A, torch.complex128), dev.to_device(B, torch.complex128), [[0, 0, 0, 0]], out,
+                 rdiv=nao, s_outer=neo * nao, s_inner=1, s_col=nao)
+    ref = (A[0] @ B[0].T).reshape(naux, nao, neo).transpose(0, 2, 1)
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("M,N,K,lower,acc,pad", [
+    (128, 128, 16, False, False, 0), (300, 200, 100, False, True, 0), (1000, 1000, 333, True, True, 1),
+    (515, 515, 48, True, False, 0), (130, 77, 5, False, False, 3), (1, 1, 1, True, False, 1),
+])
+def test_dgemm_tn_and_mirror(dev, M, N, K, lower, acc, pad):
+    rng = np.random.default_rng(M + K)
+    A = rng.standard_normal((M, K + pad))
+    B = A if lower else rng.standard_normal((N, K + pad))
+    C0 = rng.standard_normal((M, N))
+    ref = (C0 if acc else 0.0) + 2.0 * (A[:, :K] @ B[:, :K].T)
+    Ad = dev.to_device(np.ascontiguousarray(np.pad(A, ((0, 0), (0, (K + pad) % 2)))), torch.float64)
+    Bd = Ad if lower else dev.to_device(np.ascontiguousarray(np.pad(B, ((0, 0), (0, (K + pad) % 2)))), torch.float64)
+    Cd = dev.to_device(C0, torch.float64)
+    dev.dgemm_tn(Ad, Bd, Cd, K=K, alpha=2.0, accumulate=acc, lower_only=lower)
+    got = Cd.cpu().numpy()
+    if lower:
+        tm = np.arange(M) // 128
+        mask = tm[:, None] >= tm[None, :]
+        assert np.abs((got - ref) * mask).max() < 1e-11 * max(1.0, np.abs(ref).max())
+        assert np.array_equal(got[~mask], C0[~mask])                   # tiles above the diagonal untouched
+        dev.mirror_lower(Cd)
+        full = np.tril(ref) + np.tril(ref, -1).T
+        assert np.abs(Cd.cpu().numpy() - full).max() < 1e-11 * max(1.0, np.abs(ref).max())
+    else:
+        assert np.abs(got - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def test_transpose_d2z_ksum(dev):
+    rng = np.random.default_rng(3)
+    x = _z(rng, 3, 37, 70)
+    xd = dev.to_device(x, torch.complex128)
+    assert np.array_equal(dev.ztranspose(xd).cpu().numpy(), x.transpose(0, 2, 1))
+    got = dev.ztranspose(xd, conj=True, scale=0.5).cpu().numpy()
+    assert np.abs(got - 0.5 * x.conj().transpose(0, 2, 1)).max() < 1e-15
+    r = rng.standard_normal((4, 9))
+    assert np.array_equal(dev.d2z(dev.to_device(r, torch.float64)).cpu().numpy(), r.astype(np.complex128))
+    out, imag = dev.ksum_real(xd, scale=0.25)
+    assert np.abs(out.cpu().numpy() - 0.25 * x.sum(0).real).max() < 1e-14
+    assert abs(imag - np.abs(x.sum(0).imag).max()) < 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 4, 11, 30])
+def test_restore_and_jk(dev, n):
+    from oracle import pyscf_lib as olib
+    rng = np.random.default_rng(n)
+    npair = n * (n + 1) // 2
+    x = rng.standard_normal((npair, npair))
+    e4 = x + x.T
+    e4d = dev.to_device(e4, torch.float64)
+    assert np.array_equal(dev.restore_s1(e4d, n).cpu().numpy(), olib.restore(1, e4, n))
+    assert np.array_equal(dev.restore_s8(e4d, n).cpu().numpy(), olib.restore(8, e4, n))
+    d = rng.standard_normal((n, n))
+    d = d + d.T
+    vj, vk = dev.jk_s4(e4d, dev.to_device(d, torch.float64))
+    rj, rk = olib.dot_eri_dm(e4, d, hermi=1)
+    assert np.abs(vj.cpu().numpy() - rj).max() < 1e-11 * max(1, np.abs(rj).max())
+    assert np.abs(vk.cpu().numpy() - rk).max() < 1e-11 * max(1, np.abs(rk).max())
+    # non-symmetric ERI block (the ab block): J only, PySCF convention J_ij = sum_kl (ij|kl) D_kl
+    eab = rng.standard_normal((npair, npair))
+    vj2, none = dev.jk_s4(dev.to_device(eab, torch.float64), dev.to_device(d, torch.float64), with_k=False)
+    assert none is None
+    assert np.abs(vj2.cpu().numpy() - olib.dot_eri_dm(eab, d, with_k=False)[0]).max() < 1e-11 * max(1, np.abs(rj).max())
+
+
+def test_synth_block_bit_exact(dev):
+    from libdmet_preview_b200 import synthetic
+    g = synthetic.SyntheticGDF([2, 1, 3], 9, 14, seed=77)
+    for (i, j) in [(0, 0), (1, 4), (5, 2)]:
+        out = dev.empty((14, 9, 9), torch.complex128)
+        dev.synth_block(out, 14, 9, g.keys(i, j), g.scale)
+        assert np.array_equal(out.cpu().numpy(), g.load(i, j))           # bit for bit
+
+
+def test_error_reporting(dev):
+    from libdmet_preview_b200._lib import LdmError
+    A = dev.empty((1, 4, 4), torch.complex128)
+    with pytest.raises(LdmError):
+        dev.zgemm_tn(A, A, [[5, 0, 0, 0]], dev.empty((4, 4), torch.complex128))     # slice out of range
+    with pytest.raises(LdmError):
+        dev.dgemm_tn(dev.empty((4, 3)), dev.empty((4, 3)), dev.empty((4, 4)))       # odd leading dimension
