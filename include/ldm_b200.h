@@ -90,10 +90,10 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
               int n);
 
 /* ---- synthetic GDF block generator -----------------------------------------------------------------------
- * Writes L(k_i,k_j) (naux, nao, nao) complex for the seeded synthetic provider (host twin:
- * libdmet_preview_b200/synthetic.py); keys are the four 32-bit pair keys of that scheme.                      */
-int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, uint32_t key_ij, uint32_t key_ji,
-                    uint32_t key_mij, uint32_t key_mji, double scale);
+ * Writes rows [aux_offset, aux_offset + naux) of L(k_i,k_j) (.., nao, nao) complex for the seeded synthetic
+ * provider (host twin: libdmet_preview_b200/synthetic.py); keys are the four 32-bit pair keys of that scheme. */
+int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, int aux_offset, uint32_t key_ij,
+                    uint32_t key_ji, uint32_t key_mij, uint32_t key_mji, double scale);
 
 /* ---- embedding ERI from GDF blocks: the get_emb_eri_fast_gdf pipeline ------------------------------------
  * Replaces the loop nest of libdmet/basis_transform/eri_transform.py:338-386 (transform_ao_to_emb, hermi_sum,
@@ -111,6 +111,8 @@ int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, 
  *
  * eri_d: (nspin*(nspin+1)/2, npair, npair) doubles owned by the caller, accumulated in place (zero it first;
  * partial results of several ranks can be summed with NCCL before ldm_mirror_lower).
+ * naux may be a slice of the auxiliary index: rows of Lambda are independent through stage 1 and additive in
+ * stage 3, so (kL, aux-range) work items can be dealt to different GPUs and their eri_d summed.
  * max_group: how many (i, j) blocks are staged and processed per kernel launch (>= 1).
  * Block sources: a host pointer (pageable or pinned; consumed before the call returns), a slot of a resident
  * device store registered with ldm_eri_set_store, or the synthetic generator.                                */
@@ -119,8 +121,8 @@ int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int 
 int ldm_eri_set_store(ldm_handle h, const void* store_d, int nslots);
 int ldm_eri_block_host(ldm_handle h, int ki, int kj, int sym, const void* L_h);
 int ldm_eri_block_store(ldm_handle h, int ki, int kj, int sym, int slot);
-int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, uint32_t key_ij, uint32_t key_ji, uint32_t key_mij,
-                        uint32_t key_mji, double scale);
+int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, int aux_offset, uint32_t key_ij, uint32_t key_ji,
+                        uint32_t key_mij, uint32_t key_mji, double scale);
 int ldm_eri_end_kl(ldm_handle h, int weight);
 int ldm_eri_finish(ldm_handle h);
 int ldm_eri_end(ldm_handle h);

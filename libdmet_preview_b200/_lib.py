@@ -41,14 +41,14 @@ SIGNATURES = {
     "ldm_restore_s1": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "ldm_restore_s8": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "ldm_jk_s4": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
-    "ldm_synth_block": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                  C.c_double]),
+    "ldm_synth_block": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.c_uint32, C.c_double]),
     "ldm_eri_begin": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int]),
     "ldm_eri_set_store": (C.c_int, [vp, vp, C.c_int]),
     "ldm_eri_block_host": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_eri_block_store": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "ldm_eri_block_synth": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                      C.c_double]),
+    "ldm_eri_block_synth": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.c_uint32, C.c_double]),
     "ldm_eri_end_kl": (C.c_int, [vp, C.c_int]),
     "ldm_eri_finish": (C.c_int, [vp]),
     "ldm_eri_end": (C.c_int, [vp]),

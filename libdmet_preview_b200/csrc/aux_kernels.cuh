@@ -337,15 +337,15 @@ __device__ __forceinline__ double synth_u(uint32_t key, uint32_t idx) {
     return (double)(int32_t)lowbias32(idx ^ key) * 4.656612873077393e-10;   // 2^-31
 }
 __global__ void __launch_bounds__(256)
-synth_block_kernel(double2* __restrict__ out, int naux, int nao, uint32_t key_ij, uint32_t key_ji, uint32_t key_mij,
-                   uint32_t key_mji, double scale) {
+synth_block_kernel(double2* __restrict__ out, int naux, int nao, int aux_offset, uint32_t key_ij, uint32_t key_ji,
+                   uint32_t key_mij, uint32_t key_mji, double scale) {
     const size_t total = (size_t)naux * nao * nao;
     const double s = 0.25 * scale;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const uint32_t q = (uint32_t)(e % nao);
         const uint32_t lp = (uint32_t)(e / nao);
-        const uint32_t p = lp % nao, L = lp / nao;
-        const uint32_t d = 2u * (uint32_t)e;                              // (L, p, q)
+        const uint32_t p = lp % nao, L = lp / nao + (uint32_t)aux_offset;
+        const uint32_t d = 2u * ((L * nao + p) * nao + q);                // (L, p, q)
         const uint32_t tt = 2u * ((L * nao + q) * nao + p);               // (L, q, p)
         const double re = synth_u(key_ij, d) + synth_u(key_ji, tt) + synth_u(key_mij, d) + synth_u(key_mji, tt);
         const double im = synth_u(key_ij, d + 1) - synth_u(key_ji, tt + 1) - synth_u(key_mij, d + 1) +

@@ -470,12 +470,14 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
     return 0;
 }
 
-int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, uint32_t key_ij, uint32_t key_ji,
-                    uint32_t key_mij, uint32_t key_mji, double scale) {
+int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, int aux_offset, uint32_t key_ij,
+                    uint32_t key_ji, uint32_t key_mij, uint32_t key_mji, double scale) {
     LDM_CUDA_OK(cudaSetDevice(h->device));
-    LDM_REQUIRE(2.0 * naux * nao * (double)nao < 4294967296.0, "block too large for the 32-bit counter");
+    LDM_REQUIRE(aux_offset >= 0 && 2.0 * ((double)naux + aux_offset) * nao * (double)nao < 4294967296.0,
+                "block too large for the 32-bit counter");
     synth_block_kernel<<<h->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(static_cast<double2*>(out_d), naux, nao,
-                                                                          key_ij, key_ji, key_mij, key_mji, scale);
+                                                                          aux_offset, key_ij, key_ji, key_mij,
+                                                                          key_mji, scale);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -740,8 +742,8 @@ int ldm_eri_block_store(ldm_handle h, int ki, int kj, int sym, int slot) {
     return push_block(h, ki, kj, sym, slot, 1);
 }
 
-int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, uint32_t key_ij, uint32_t key_ji, uint32_t key_mij,
-                        uint32_t key_mji, double scale) {
+int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, int aux_offset, uint32_t key_ij, uint32_t key_ji,
+                        uint32_t key_mij, uint32_t key_mji, double scale) {
     LDM_REQUIRE(h && h->plan, "arguments");
     EriPlan* p = h->plan;
     LDM_REQUIRE(ki >= 0 && ki < p->nk && kj >= 0 && kj < p->nk, "k index");
@@ -749,8 +751,8 @@ int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, uint32_t key_ij, 
     int slot;
     int rc = ring_acquire(h, &slot);
     if (rc) return rc;
-    rc = ldm_synth_block(h, p->st, p->ring + (size_t)slot * block_elems(p), p->naux, p->nao, key_ij, key_ji, key_mij,
-                         key_mji, scale);
+    rc = ldm_synth_block(h, p->st, p->ring + (size_t)slot * block_elems(p), p->naux, p->nao, aux_offset, key_ij,
+                         key_ji, key_mij, key_mji, scale);
     if (rc) return rc;
     return push_block(h, ki, kj, sym, slot, 0);
 }

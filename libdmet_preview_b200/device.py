@@ -170,9 +170,9 @@ class Device(object):
                                  n))
         return vj, vk
 
-    def synth_block(self, out, naux, nao, keys, scale):
-        check(self.lib.ldm_synth_block(self.h, self.stream, _ptr(out), naux, nao, int(keys[0]), int(keys[1]),
-                                       int(keys[2]), int(keys[3]), float(scale)))
+    def synth_block(self, out, naux, nao, keys, scale, aux_offset=0):
+        check(self.lib.ldm_synth_block(self.h, self.stream, _ptr(out), naux, nao, int(aux_offset), int(keys[0]),
+                                       int(keys[1]), int(keys[2]), int(keys[3]), float(scale)))
         return out
 
 

@@ -16,7 +16,7 @@ import torch
 
 from ._lib import check
 from .device import get_device, _ptr
-from .schedule import build_schedule, assign_units, KPT_DIFF_TOL
+from .schedule import build_schedule, work_items, KPT_DIFF_TOL
 from . import fourier
 from .make_basis import add_spin_dim
 
@@ -194,9 +194,9 @@ class EriBuild(object):
     def block_store(self, ki, kj, sym, slot):
         check(self.dev.lib.ldm_eri_block_store(self.dev.h, ki, kj, int(sym), int(slot)))
 
-    def block_synth(self, ki, kj, sym, keys, scale):
-        check(self.dev.lib.ldm_eri_block_synth(self.dev.h, ki, kj, int(sym), int(keys[0]), int(keys[1]),
-                                               int(keys[2]), int(keys[3]), float(scale)))
+    def block_synth(self, ki, kj, sym, keys, scale, aux_offset=0):
+        check(self.dev.lib.ldm_eri_block_synth(self.dev.h, ki, kj, int(sym), int(aux_offset), int(keys[0]),
+                                               int(keys[1]), int(keys[2]), int(keys[3]), float(scale)))
 
     def end_kl(self, weight):
         check(self.dev.lib.ldm_eri_end_kl(self.dev.h, int(weight)))
@@ -215,24 +215,30 @@ class EriBuild(object):
         return ms.value, n.value
 
 
-def run_schedule(build, provider, schedule, units=None, source="auto", store_map=None):
-    """Feed the (k_i, k_j) blocks of `units` (indices into schedule.units; default all) to an open build.
-    source: "host"   provider.load(ki, kj) -> host array -> H2D inside the call
+def _host_block(provider, ki, kj, l0, l1, naux_full):
+    if l0 == 0 and l1 == naux_full:
+        return provider.load(ki, kj)
+    L = provider.load(ki, kj)
+    return L[l0:l1]                      # leading-index slice of a C-contiguous block: still contiguous
+
+
+def run_items(build, provider, schedule, items, source="auto", store_map=None):
+    """Feed the (k_i, k_j) blocks of `items` -- (unit index, l0, l1) with one common aux range -- to an open build.
+    source: "host"   provider.load(ki, kj)[l0:l1] -> host array -> H2D inside the call
             "synth"  provider.keys(ki, kj) -> device generator (SyntheticGDF only)
-            "store"  store_map[(ki, kj)] -> slot of the resident device store registered with build.set_store
+            "store"  store_map[(ki, kj, l0)] -> slot of the resident device store registered with build.set_store
             "auto"   synth if the provider has .keys, else host"""
     if source == "auto":
         source = "synth" if hasattr(provider, "keys") and hasattr(provider, "scale") else "host"
-    idx = range(len(schedule.units)) if units is None else units
-    for u in idx:
+    for (u, l0, l1) in items:
         kL, weight, blocks = schedule.units[u]
         for (ki, kj, sym) in blocks:
             if source == "host":
-                build.block_host(ki, kj, sym, provider.load(ki, kj))
+                build.block_host(ki, kj, sym, _host_block(provider, ki, kj, l0, l1, provider.naux))
             elif source == "synth":
-                build.block_synth(ki, kj, sym, provider.keys(ki, kj), provider.scale)
+                build.block_synth(ki, kj, sym, provider.keys(ki, kj), provider.scale, l0)
             elif source == "store":
-                build.block_store(ki, kj, sym, store_map[(ki, kj)])
+                build.block_store(ki, kj, sym, store_map[(ki, kj, l0)])
             else:
                 raise ValueError("unknown block source %s" % source)
         build.end_kl(weight)
@@ -259,25 +265,40 @@ def finalize_eri(eri, nemb, symmetry, nspin):
 
 
 def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL, kscaled_center=None,
-                   source="auto", group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, units=None, schedule=None,
-                   store=None, store_map=None, stats=None):
+                   source="auto", group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, items=None, schedule=None,
+                   stores=None, store_map=None, stats=None):
     """Stages 1-3 on the device.  Returns the (spin_pair, npair, npair) tensor holding the LOWER triangles of the
-    symmetric blocks (sum over `units` of the schedule only, if given)."""
+    symmetric blocks, summed over `items` = [(unit index, l0, l1)] (default: every unit, full aux range).
+    stores: {(l0, l1): resident device tensor (nslots, l1-l0, nao, nao)} for source "store"."""
     dev = get_device()
     spin, nkpts, nemb, nao = CT.shape
     npair = nemb * (nemb + 1) // 2
     if schedule is None:
         schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
+    if items is None:
+        items = work_items(schedule, provider.naux, 1)
     eri = dev.zeros((spin * (spin + 1) // 2, npair, npair))
-    with EriBuild(CT, provider.naux, eri, group, kl_group) as b:
-        if store is not None:
-            b.set_store(store)
-            source = "store"
-        run_schedule(b, provider, schedule, units, source, store_map)
-        if stats is not None:
-            stats.update(b.stats())
-            stats["zgemm_ms"], stats["zgemm_launch_groups"] = b.kernel_time(0)
-            stats["dgemm_ms"], stats["dgemm_launch_groups"] = b.kernel_time(1)
+    if stores is not None:
+        source = "store"
+    tot = {"launches": 0, "h2d_bytes": 0, "zgemm_ms": 0.0, "dgemm_ms": 0.0, "zgemm_launch_groups": 0,
+           "dgemm_launch_groups": 0}
+    ranges = sorted({(l0, l1) for (_, l0, l1) in items})
+    for (l0, l1) in ranges:                 # one build per distinct aux range (workspaces are sized by it)
+        sub = [it for it in items if (it[1], it[2]) == (l0, l1)]
+        with EriBuild(CT, l1 - l0, eri, group, kl_group) as b:
+            if stores is not None:
+                b.set_store(stores[(l0, l1)])
+            run_items(b, provider, schedule, sub, source, store_map)
+            if stats is not None:
+                st = b.stats()
+                tot["launches"] += st["launches"]
+                tot["h2d_bytes"] += st["h2d_bytes"]
+                for kind, name in ((0, "zgemm"), (1, "dgemm")):
+                    ms, n = b.kernel_time(kind)
+                    tot[name + "_ms"] += ms
+                    tot[name + "_launch_groups"] += n
+    if stats is not None:
+        stats.update(tot)
     return eri
 
 
@@ -296,7 +317,9 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
     assert cell is None or int(cell.nao_nr()) == provider.nao
     CT = build_CT(provider, C_ao_lo, basis, C_ao_eo, unit_eri)
     spin, nkpts, nemb, nao = CT.shape
-    eri = emb_eri_device(provider, CT, t_reversal_symm, kconserv_tol, kscaled_center,
+    schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
+    eri = emb_eri_device(provider, CT, schedule=schedule,
+                         items=work_items(schedule, provider.naux, kwargs.get("nsplit", 1)),
                          source=kwargs.get("source", "auto"), group=kwargs.get("group", DEFAULT_GROUP),
                          kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None))
     eri = finalize_eri(eri, nemb, symmetry, spin)

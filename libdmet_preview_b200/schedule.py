@@ -126,6 +126,29 @@ def build_schedule(kpts_scaled, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL,
     return EriSchedule(nk, t_reversal_symm, weights, units)
 
 
+def work_items(schedule, naux, nsplit=1, units=None):
+    """Independent work items (unit index, l0, l1): a transfer momentum restricted to the auxiliary rows [l0, l1).
+    Rows of the packed 3-index tensor are independent through stage 1 and enter `eri` additively in stage 3
+    (eri += sum_L X[L,P] X[L,Q]), so items can run on different GPUs with no exchange but the final sum."""
+    idx = range(len(schedule.units)) if units is None else units
+    nsplit = max(1, min(int(nsplit), naux))
+    cuts = [(naux * s) // nsplit for s in range(nsplit + 1)]
+    return [(u, cuts[s], cuts[s + 1]) for u in idx for s in range(nsplit) if cuts[s + 1] > cuts[s]]
+
+
+def choose_split(costs, nranks, max_split=4, tol=0.03):
+    """smallest aux split whose LPT assignment is balanced to `tol` (1 when the units already divide evenly)."""
+    best = 1
+    for ns in range(1, max_split + 1):
+        c = [x / ns for x in costs for _ in range(ns)]
+        parts = assign_units(c, nranks)
+        loads = [sum(c[u] for u in p) for p in parts]
+        if max(loads) <= (1.0 + tol) * sum(loads) / nranks:
+            return ns
+        best = ns
+    return best
+
+
 def assign_units(costs, nranks):
     """Longest-processing-time assignment of schedule units to ranks (the reference's MPI variant deals the units
     out round-robin, eri_transform_mpi.py:35-55; LPT balances unequal block counts better).  Returns a list of

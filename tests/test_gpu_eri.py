@@ -126,3 +126,14 @@ def test_properties_at_bench_shape_sample(dev):
     e2 = et.get_emb_eri(g2.cell, g2, C_ao_lo=C, basis=basis)
     assert np.abs(e2 - 4.0 * e).max() < 1e-10 * max(1.0, np.abs(e2).max())
     assert st["launches"] > 0 and st["h2d_bytes"] == 0
+
+
+@pytest.mark.parametrize("nsplit", [2, 3])
+def test_aux_split_items(dev, nsplit):
+    """(kL, aux-range) work items are independent and additive: splitting changes nothing beyond rounding"""
+    gdf, C, basis = problem([1, 2, 2], 9, 29, 8)
+    got, ref = both(gdf, C_ao_lo=C, basis=basis)
+    from libdmet_preview_b200 import eri_transform as et
+    for source in ("synth", "host"):
+        sp = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, nsplit=nsplit, source=source)
+        assert np.abs(sp - ref).max() < TOL
