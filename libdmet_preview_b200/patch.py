@@ -1,0 +1,68 @@
+"""Drop-in installation into an existing libDMET (when `libdmet` and PySCF are importable):
+
+    import libdmet_preview_b200.patch as p; p.install()
+
+rebinds the names the reference's callers actually resolve:
+  * `libdmet.basis_transform.eri_transform.get_emb_eri / get_unit_eri / get_emb_eri_fast_gdf`
+  * `libdmet.routine.slater.get_emb_eri / get_unit_eri` -- imported BY NAME at module load (slater.py:32-33), so the
+    attribute on `slater` must be replaced too
+  * `libdmet.system.fourier.k2R / R2k / FFTtoK / FFTtoT` and the copies `libdmet.system.lattice` pulled in with
+    `from libdmet.system.fourier import *` (lattice.py:23)
+  * `libdmet.basis_transform.make_basis.transform_h1_to_lo / multiply_basis` (looked up through the module at call
+    time, lattice.py:609)
+  * `libdmet.routine.slater.get_emb_basis / embBasis / get_emb_Ham / embHam`
+Non-GDF density-fitting objects keep going to the reference's own drivers.
+`uninstall()` restores the originals.
+"""
+_saved = {}
+
+
+def _swap(mod, name, new):
+    _saved.setdefault((mod, name), getattr(mod, name))
+    setattr(mod, name, new)
+
+
+def install():
+    import libdmet.basis_transform.eri_transform as r_eri
+    import libdmet.basis_transform.make_basis as r_mb
+    import libdmet.routine.slater as r_sl
+    import libdmet.system.fourier as r_f
+    import libdmet.system.lattice as r_lat
+    from pyscf.pbc import df as pdf
+    from . import eri_transform as eri, fourier, make_basis, slater
+
+    ref_get_emb_eri = r_eri.get_emb_eri
+
+    def get_emb_eri(cell, mydf, *args, **kwargs):
+        gdf_like = hasattr(mydf, "load") or (isinstance(mydf, pdf.GDF) and not isinstance(mydf, pdf.MDF))
+        if gdf_like and kwargs.get("incore", True):
+            return eri.get_emb_eri(cell, mydf, *args, **kwargs)
+        return ref_get_emb_eri(cell, mydf, *args, **kwargs)       # MDF / FFTDF / AFTDF / outcore: reference route
+
+    def get_unit_eri(cell, mydf, *args, **kwargs):
+        gdf_like = hasattr(mydf, "load") or (isinstance(mydf, pdf.GDF) and not isinstance(mydf, pdf.MDF))
+        if gdf_like and kwargs.get("incore", True):
+            return eri.get_unit_eri(cell, mydf, *args, **kwargs)
+        return _saved[(r_eri, "get_unit_eri")](cell, mydf, *args, **kwargs)
+
+    _swap(r_eri, "get_unit_eri", get_unit_eri)
+    _swap(r_eri, "get_emb_eri", get_emb_eri)
+    _swap(r_eri, "get_emb_eri_fast_gdf", eri.get_emb_eri_fast_gdf)
+    _swap(r_sl, "get_emb_eri", get_emb_eri)
+    _swap(r_sl, "get_unit_eri", get_unit_eri)
+    for m in (r_f, r_lat):
+        for n in ("k2R", "R2k", "FFTtoK", "FFTtoT"):
+            _swap(m, n, getattr(fourier, n))
+    _swap(r_mb, "transform_h1_to_lo", make_basis.transform_h1_to_lo)
+    _swap(r_mb, "multiply_basis", make_basis.multiply_basis)
+    for n in ("get_emb_basis", "embBasis"):
+        _swap(r_sl, n, slater.get_emb_basis)
+    for n in ("get_emb_Ham", "embHam"):
+        _swap(r_sl, n, slater.get_emb_Ham)
+    return sorted("%s.%s" % (m.__name__, n) for (m, n) in _saved)
+
+
+def uninstall():
+    for (mod, name), old in _saved.items():
+        setattr(mod, name, old)
+    _saved.clear()

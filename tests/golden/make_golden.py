@@ -1,0 +1,157 @@
+"""Generate the golden fixtures of tests/golden/*.npz by running the reference's OWN Python, imported unmodified from
+/root/reference, over the stub environment of ref_stubs.py (PySCF / h5py are not installed; see that file for what is
+stubbed).  Run once in the build container:
+
+    python tests/golden/make_golden.py
+
+Functions executed from the reference:
+    libdmet.basis_transform.eri_transform.get_emb_eri / get_unit_eri          (eri_transform.py:44-112, 235-399)
+    libdmet.system.fourier.R2k / k2R                                           (fourier.py:129-177)
+    libdmet.basis_transform.make_basis.transform_h1_to_lo / multiply_basis     (make_basis.py:524-558, 923-962)
+    libdmet.system.lattice.Lattice(...).set_Ham(...)                           (lattice.py:31-56, 416-515, 591-673)
+    libdmet.routine.slater.get_emb_basis / get_emb_Ham                         (slater.py:98-220, 320-370, ...)
+Inputs are the seeded synthetic problems of tests/helpers.py; small inputs are stored next to the outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "tests"), HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import ref_stubs  # noqa: E402
+
+ref_stubs.install()
+
+from helpers import problem, mean_field  # noqa: E402
+from libdmet_preview_b200 import synthetic  # noqa: E402
+from pyscf.pbc import df as stub_df  # noqa: E402
+import libdmet.basis_transform.eri_transform as ref_eri  # noqa: E402
+import libdmet.basis_transform.make_basis as ref_mb  # noqa: E402
+import libdmet.system.fourier as ref_fourier  # noqa: E402
+import libdmet.system.lattice as ref_lattice  # noqa: E402
+import libdmet.routine.slater as ref_slater  # noqa: E402
+from libdmet.utils import logger as ref_log  # noqa: E402
+
+ref_log.verbose = "RESULT"
+
+
+class GoldenCell(synthetic.SyntheticCell):
+    """adds the members the reference's Lattice constructor touches (lattice.py:33-56)"""
+    pbc_intor = True
+
+    def __init__(self, nao):
+        super().__init__(nao)
+        self._atom = [("H", (0.0, 0.0, 0.0))]
+
+    def super_cell(self, kmesh):
+        big = GoldenCell(self._nao * int(np.prod(kmesh)))
+        return big
+
+
+def ref_gdf(gdf, key):
+    mydf = stub_df.GDF(gdf.cell, gdf.kpts)
+    mydf._cderi = key
+    mydf.cell = gdf.cell
+    ref_stubs.GDF_REGISTRY[key] = gdf
+    return mydf
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %-28s %s" % (name + ".npz", {k: np.asarray(v).shape for k, v in arrays.items()}))
+
+
+def gen_eri():
+    cases = {
+        "eri_r_113": dict(kmesh=[1, 1, 3], nao=4, naux=10, neo=6, spin=1),
+        "eri_r_222": dict(kmesh=[2, 2, 2], nao=6, naux=14, neo=7, spin=1),
+        "eri_r_331": dict(kmesh=[3, 3, 1], nao=5, naux=9, neo=5, spin=1),
+        "eri_u_122": dict(kmesh=[1, 2, 2], nao=5, naux=11, neo=6, spin=2),
+    }
+    for name, c in cases.items():
+        gdf, C, basis = problem(c["kmesh"], c["nao"], c["naux"], c["neo"], spin=c["spin"])
+        gdf.cell = GoldenCell(c["nao"])
+        mydf = ref_gdf(gdf, name)
+        out = dict(kmesh=np.array(c["kmesh"]), nao=c["nao"], naux=c["naux"], neo=c["neo"], spin=c["spin"],
+                   gdf_seed=gdf.seed, gdf_scale=gdf.scale, C_ao_lo=C, basis=basis)
+        out["s4_trs"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4)
+        out["s4_plain"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4,
+                                              t_reversal_symm=False)
+        out["s1_trs"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=1)
+        out["s4_chunk16"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4, max_memory=0.02)
+        if c["spin"] == 1:
+            out["s8_trs"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=8)
+        out["unit_s4"] = ref_eri.get_unit_eri(gdf.cell, mydf, C_ao_lo=C, symmetry=4)
+        save(name, **out)
+
+
+def gen_fourier_basis():
+    rng = np.random.default_rng(42)
+    kmesh = [2, 3, 2]
+    nk = 12
+    A_R = rng.standard_normal((nk, 4, 5))
+    B_k = rng.standard_normal((2, nk, 3, 3)) + 1j * rng.standard_normal((2, nk, 3, 3))
+    C = synthetic.make_C_ao_lo(kmesh, 6, 4, seed=9, spin=2)
+    h = rng.standard_normal((nk, 6, 6)) + 1j * rng.standard_normal((nk, 6, 6))
+    b = rng.standard_normal((nk, 4, 3))
+    ref_log.verbose = "FATAL"     # k2R of a non-physical array warns about its imaginary part
+    save("fourier_basis", kmesh=np.array(kmesh), A_R=A_R, B_k=B_k, C=C, h=h, b=b,
+         R2k_A=ref_fourier.R2k(A_R, kmesh), k2R_B=ref_fourier.k2R(B_k, kmesh),
+         roundtrip=ref_fourier.k2R(ref_fourier.R2k(A_R, kmesh), kmesh),
+         h1_lo=ref_mb.transform_h1_to_lo(h, C), h1_lo_r=ref_mb.transform_h1_to_lo(h, C[0]),
+         mult=ref_mb.multiply_basis(C, b))
+    ref_log.verbose = "RESULT"
+
+
+def make_ref_lattice(kmesh, nao, naux, nval, spin, sym, key):
+    gdf, C, _ = problem(kmesh, nao, naux, 2, spin=spin)
+    cell = GoldenCell(nao)
+    gdf.cell = cell
+    hcore, ovlp, vhf, rdm1 = mean_field(kmesh, nao, nval // 2 + 1, spin=spin)
+    Lat = ref_lattice.Lattice(cell, kmesh)
+    Lat.set_val_virt_core(nval, nao - nval, 0)
+    mydf = ref_gdf(gdf, key)
+    Lat.set_Ham(object(), mydf, C, eri_symmetry=sym, ovlp=ovlp, hcore=hcore, rdm1=rdm1, vhf=vhf, veff=vhf,
+                vj=np.zeros_like(vhf), vk=np.zeros_like(vhf), H0=1.5)
+    return Lat, gdf, C, (hcore, ovlp, vhf, rdm1)
+
+
+def gen_embham():
+    for name, (kmesh, nao, naux, nval, spin, sym) in {
+            "embham_r_s4": ([1, 1, 3], 5, 11, 3, 1, 4), "embham_r_s1": ([1, 2, 2], 4, 9, 2, 1, 1),
+            "embham_u_s4": ([1, 1, 3], 5, 11, 3, 2, 4)}.items():
+        Lat, gdf, C, (hcore, ovlp, vhf, rdm1) = make_ref_lattice(kmesh, nao, naux, nval, spin, sym, name)
+        rho = Lat.rdm1_lo_R * (0.5 if spin == 1 else 1.0)
+        basis = ref_slater.get_emb_basis(Lat, rho)
+        Ham, _ = ref_slater.get_emb_Ham(Lat, basis, None)
+        save(name, kmesh=np.array(kmesh), nao=nao, naux=naux, nval=nval, spin=spin, sym=sym, gdf_seed=gdf.seed,
+             gdf_scale=gdf.scale, C_ao_lo=C, hcore=hcore, ovlp=ovlp, vhf=vhf, rdm1=rdm1,
+             hcore_lo_k=Lat.hcore_lo_k, rdm1_lo_k=Lat.rdm1_lo_k, rdm1_lo_R=Lat.rdm1_lo_R, vhf_lo_k=Lat.vhf_lo_k,
+             rho=rho, basis=basis, H1=Ham.H1["cd"], H2=Ham.H2["ccdd"], ovlp_emb=Ham.ovlp, JK_core=Lat.JK_core,
+             H0=Ham.H0, norb=Ham.norb)
+
+
+def gen_emb_basis_hchain():
+    """the reference's own fixture libdmet/routine/test/rdm1_lo (H chain 321g, 1x1x3, nval = nvirt = 2;
+    test_slater.py:20-54) through the reference's get_emb_basis"""
+    rdm1_lo = np.load(os.path.join(ref_stubs.REF_ROOT, "libdmet", "routine", "test", "rdm1_lo"))
+    cell = GoldenCell(4)
+    Lat = ref_lattice.Lattice(cell, [1, 1, 3])
+    Lat.set_val_virt_core(2, 2, 0)
+    basis = ref_slater.get_emb_basis(Lat, rdm1_lo)
+    Lat.val_idx, Lat.virt_idx = list(range(4)), []
+    basis_trunc = ref_slater.get_emb_basis(Lat, rdm1_lo, nbath=2, valence_bath=False)
+    save("emb_basis_hchain", rdm1_lo=rdm1_lo, basis=basis, basis_trunc=basis_trunc)
+
+
+if __name__ == "__main__":
+    gen_eri()
+    gen_fourier_basis()
+    gen_embham()
+    gen_emb_basis_hchain()
