@@ -249,14 +249,29 @@ def run_ours(args):
 
     stats = {}
 
+    debug = bool(os.environ.get("BENCH_DEBUG"))
+
     def step(collect=None):
+        t0 = time.perf_counter()
         CT = et.build_CT(gdf, C_ao_lo, basis)
         eri = et.emb_eri_device(gdf, CT, schedule=schedule, items=my_items, stores=stores, store_map=store_map,
                                 group=args.group, kl_group=args.kl_group, stats=collect)
+        if debug:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
         if world > 1:
             dist.reduce(eri, dst=0, op=dist.ReduceOp.SUM)
+        if debug:
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
         if rank == 0:
             eri = et.finalize_eri(eri, neo, 4, 1)
+        if debug:
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            print("[rank %d] build %.1f ms (zgemm %.1f dgemm %.1f) reduce %.1f ms finalize %.1f ms" % (
+                rank, (t1 - t0) * 1e3, (collect or {}).get("zgemm_ms", -1), (collect or {}).get("dgemm_ms", -1),
+                (t2 - t1) * 1e3, (t3 - t2) * 1e3), file=sys.stderr, flush=True)
         return eri
 
     def barrier():
@@ -307,6 +322,7 @@ def run_ours(args):
                 "peak_source": "cuBLAS DGEMM 8192^3 sustained 4 s on this pool's B200 (tools/probe_peaks.py -> "
                                "profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json carries no FP64 figure",
                 "share_of_step": zg_ms * 1e-3 / (t_step * args.steps),
+                "stage3_share_of_step": dg_ms * 1e-3 / (t_step * args.steps),
                 "stage3_dgemm": {"achieved": (F3 * sum((1 if schedule.units[u][1] == 1 else 2) * (l1 - l0)
                                                            for (u, l0, l1) in my_items) / float(G * naux)) *
                                  args.steps / (dg_ms * 1e-3) / 1e12 if dg_ms > 0 else None, "unit": "TFLOP/s"}}

@@ -107,7 +107,7 @@ int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, 
  *                                               weight 0: complex Lambda^dagger Lambda, real part (no time reversal)
  *   ldm_eri_finish(h)                           flushes pending products; eri_d then holds the LOWER triangles of
  *                                               the aa, (ab,) (bb) s4 blocks in the reference's incore order
- *   ldm_eri_end(h)                              releases the workspaces
+ *   ldm_eri_end(h)                              closes the build (workspaces stay cached in the handle)
  *
  * eri_d: (nspin*(nspin+1)/2, npair, npair) doubles owned by the caller, accumulated in place (zero it first;
  * partial results of several ranks can be summed with NCCL before ldm_mirror_lower).
@@ -126,6 +126,8 @@ int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, int aux_offset, u
 int ldm_eri_end_kl(ldm_handle h, int weight);
 int ldm_eri_finish(ldm_handle h);
 int ldm_eri_end(ldm_handle h);
+/* the pipeline's device workspaces are kept in the handle between builds (grow-only); this frees them */
+int ldm_release_workspaces(ldm_handle h);
 /* counters since ldm_eri_begin: kernels launched by this library, bytes copied host->device */
 int ldm_eri_stats(ldm_handle h, int64_t* launches, int64_t* h2d_bytes);
 /* total kernels launched through this handle since creation */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ldm_eri_end_kl": (C.c_int, [vp, C.c_int]),
     "ldm_eri_finish": (C.c_int, [vp]),
     "ldm_eri_end": (C.c_int, [vp]),
+    "ldm_release_workspaces": (C.c_int, [vp]),
     "ldm_eri_stats": (C.c_int, [vp, c_i64p, c_i64p]),
     "ldm_launch_count": (C.c_int64, [vp]),
     "ldm_eri_kernel_time": (C.c_int, [vp, C.c_int, c_f64p, c_i64p]),

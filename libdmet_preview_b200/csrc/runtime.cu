@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -81,22 +82,39 @@ static ZConfig make_zconfig() {
     return ZConfig{T::BM, T::BN, T::THREADS, T::SMEM, zgemm_tn_kernel<WM, WN, FA, FB>};
 }
 
+template <int FB>
+static void add_wide(std::vector<ZConfig>& v) {
+    v.push_back(make_zconfig<8, 1, 1, FB>());
+    if constexpr (FB > 1) add_wide<FB - 1>(v);
+}
+
+// Tile family.  First the register-blocked 32x(8*FB) warp tiles (least shared-memory traffic), then the "wide"
+// family 64 x (8*FB) with one 8-row fragment per warp and FB up to 25 column fragments, which removes N padding
+// for any neo <= 200 (neo = 150 runs as 64x152 instead of 64x160).
 static const std::vector<ZConfig>& zconfigs() {
-    static std::vector<ZConfig> v = {
-        make_zconfig<2, 4, 4, 5>(), make_zconfig<4, 2, 4, 5>(), make_zconfig<8, 1, 4, 5>(),
-        make_zconfig<2, 4, 4, 4>(), make_zconfig<4, 2, 4, 4>(), make_zconfig<8, 1, 4, 4>(),
-        make_zconfig<2, 4, 4, 3>(), make_zconfig<4, 2, 4, 3>(), make_zconfig<8, 1, 4, 3>(),
-    };
+    static std::vector<ZConfig> v = [] {
+        std::vector<ZConfig> c = {
+            make_zconfig<2, 4, 4, 5>(), make_zconfig<4, 2, 4, 5>(), make_zconfig<8, 1, 4, 5>(),
+            make_zconfig<2, 4, 4, 4>(), make_zconfig<4, 2, 4, 4>(), make_zconfig<8, 1, 4, 4>(),
+            make_zconfig<2, 4, 4, 3>(), make_zconfig<4, 2, 4, 3>(), make_zconfig<8, 1, 4, 3>(),
+        };
+        add_wide<25>(c);
+        return c;
+    }();
     return v;
 }
 
 static const ZConfig& pick_zconfig(int N) {
     const auto& v = zconfigs();
+    if (const char* f = getenv("LDM_FORCE_ZCFG")) {       // development aid: force a tile configuration
+        int idx = atoi(f);
+        if (idx >= 0 && idx < (int)v.size()) return v[idx];
+    }
     int best = 0;
     long best_pad = -1;
     for (size_t i = 0; i < v.size(); ++i) {
         long pad = (long)((N + v[i].BN - 1) / v[i].BN) * v[i].BN;
-        if (best_pad < 0 || pad < best_pad || (pad == best_pad && v[i].BN > v[best].BN)) {
+        if (best_pad < 0 || pad < best_pad) {              // ties: the earlier (more register-blocked) entry wins
             best = (int)i;
             best_pad = pad;
         }
@@ -128,7 +146,36 @@ struct ldm_context {
     size_t jk_part_bytes = 0;
     EriPlan* plan = nullptr;
     bool attrs_set = false;
+    // grow-only workspace pool of the ERI pipeline (X, S_sym, S_pln, panel, ring): cudaMalloc/cudaFree of GB-sized
+    // buffers costs tens of ms per build and cudaFree synchronises the device, so they are kept across builds
+    void* ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[5] = {0, 0, 0, 0, 0};
 };
+
+enum { WS_XT = 0, WS_SSYM = 1, WS_SPLN = 2, WS_PANEL = 3, WS_RING = 4 };
+
+static int ws_get(ldm_handle h, int slot, size_t bytes, void** out) {
+    if (h->ws_bytes[slot] < bytes) {
+        if (h->ws[slot]) {
+            LDM_CUDA_OK(cudaDeviceSynchronize());
+            LDM_CUDA_OK(cudaFree(h->ws[slot]));
+            h->ws[slot] = nullptr;
+            h->ws_bytes[slot] = 0;
+        }
+        LDM_CUDA_OK(cudaMalloc(&h->ws[slot], bytes));
+        h->ws_bytes[slot] = bytes;
+    }
+    *out = h->ws[slot];
+    return 0;
+}
+
+static void ws_release(ldm_handle h) {
+    for (int i = 0; i < 5; ++i) {
+        if (h->ws[i]) cudaFree(h->ws[i]);
+        h->ws[i] = nullptr;
+        h->ws_bytes[i] = 0;
+    }
+}
 
 static int ensure_attrs(ldm_handle h) {
     if (h->attrs_set) return 0;
@@ -199,6 +246,7 @@ int ldm_destroy(ldm_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->plan) ldm_eri_end(h);
+    ws_release(h);
     if (h->scratch_d) cudaFree(h->scratch_d);
     if (h->scratch_h) cudaFreeHost(h->scratch_h);
     if (h->imag_d) cudaFree(h->imag_d);
@@ -542,7 +590,12 @@ static int ensure_ring(ldm_handle h) {
     EriPlan* p = h->plan;
     if (p->ring) return 0;
     p->ring_slots = 2 * p->G;
-    LDM_CUDA_OK(cudaMalloc(&p->ring, (size_t)p->ring_slots * block_elems(p) * 16));
+    {
+        void* q = nullptr;
+        int rc0 = ws_get(h, WS_RING, (size_t)p->ring_slots * block_elems(p) * 16, &q);
+        if (rc0) return rc0;
+        p->ring = static_cast<double2*>(q);
+    }
     p->ring_free.resize(p->ring_slots);
     p->ring_busy.assign(p->ring_slots, 0);
     for (auto& e : p->ring_free) LDM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -664,11 +717,20 @@ int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int 
     p->launches0 = h->launches;
     const size_t xt_slice = (size_t)naux * neo * nao;
     const size_t s_elems = (size_t)nspin * naux * neo * neo;
-    LDM_CUDA_OK(cudaMalloc(&p->Xt, (size_t)nspin * p->G * xt_slice * 16));
-    LDM_CUDA_OK(cudaMalloc(&p->S_sym, s_elems * 16));
-    LDM_CUDA_OK(cudaMalloc(&p->S_pln, s_elems * 16));
-    LDM_CUDA_OK(cudaMalloc(&p->XT, (size_t)nspin * p->npair * p->ldx * 8));
-    int rc = encode_tmap_f64_3d(&p->tmCT, CT_d, 2ull * nao, (uint64_t)neo, (uint64_t)nspin * nkpts, 16ull * nao,
+    void* q = nullptr;
+    int rc = ws_get(h, WS_XT, (size_t)nspin * p->G * xt_slice * 16, &q);
+    if (rc) return rc;
+    p->Xt = static_cast<double2*>(q);
+    rc = ws_get(h, WS_SSYM, s_elems * 16, &q);
+    if (rc) return rc;
+    p->S_sym = static_cast<double2*>(q);
+    rc = ws_get(h, WS_SPLN, s_elems * 16, &q);
+    if (rc) return rc;
+    p->S_pln = static_cast<double2*>(q);
+    rc = ws_get(h, WS_PANEL, (size_t)nspin * p->npair * p->ldx * 8, &q);
+    if (rc) return rc;
+    p->XT = static_cast<double*>(q);
+    rc = encode_tmap_f64_3d(&p->tmCT, CT_d, 2ull * nao, (uint64_t)neo, (uint64_t)nspin * nkpts, 16ull * nao,
                                 16ull * nao * neo, 8, p->cfg->BN, false);
     if (rc) return rc;
     rc = encode_tmap_f64_3d(&p->tmXt, p->Xt, 2ull * nao, (uint64_t)naux * neo, (uint64_t)nspin * p->G, 16ull * nao,
@@ -824,7 +886,9 @@ int ldm_eri_end(ldm_handle h) {
     if (!h || !h->plan) return 0;
     EriPlan* p = h->plan;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(p->st);
+    // workspaces stay in the handle's pool and later builds queue behind this one on the same stream; only host
+    // staging through the copy stream needs the compute stream drained before the ring can be overwritten again
+    if (p->h2d_bytes > 0) cudaStreamSynchronize(p->st);
     cudaStreamSynchronize(p->copy_st);
     for (int k = 0; k < 2; ++k)
         for (auto& e : p->ev[k]) {
@@ -832,14 +896,17 @@ int ldm_eri_end(ldm_handle h) {
             cudaEventDestroy(e.second);
         }
     for (auto& e : p->ring_free) cudaEventDestroy(e);
-    if (p->ring) cudaFree(p->ring);
-    if (p->Xt) cudaFree(p->Xt);
-    if (p->S_sym) cudaFree(p->S_sym);
-    if (p->S_pln) cudaFree(p->S_pln);
-    if (p->XT) cudaFree(p->XT);
     cudaStreamDestroy(p->copy_st);
     delete p;
     h->plan = nullptr;
+    return 0;
+}
+
+int ldm_release_workspaces(ldm_handle h) {
+    LDM_REQUIRE(h && !h->plan, "no build may be open");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    LDM_CUDA_OK(cudaDeviceSynchronize());
+    ws_release(h);
     return 0;
 }
 

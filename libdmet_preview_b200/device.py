@@ -60,6 +60,10 @@ class Device(object):
     def zeros(self, shape, dtype=torch.float64):
         return torch.zeros(shape, dtype=dtype, device=self.torch_device)
 
+    def release_workspaces(self):
+        """free the ERI pipeline's cached device workspaces (they are kept between builds otherwise)"""
+        check(self.lib.ldm_release_workspaces(self.h))
+
     def launch_count(self):
         return int(self.lib.ldm_launch_count(self.h))
 

@@ -285,6 +285,7 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
     ranges = sorted({(l0, l1) for (_, l0, l1) in items})
     for (l0, l1) in ranges:                 # one build per distinct aux range (workspaces are sized by it)
         sub = [it for it in items if (it[1], it[2]) == (l0, l1)]
+        sub.sort(key=lambda it: (schedule.units[it[0]][1], it[0]))     # equal weights share stage-3 launches
         with EriBuild(CT, l1 - l0, eri, group, kl_group) as b:
             if stores is not None:
                 b.set_store(stores[(l0, l1)])
