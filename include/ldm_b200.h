@@ -119,6 +119,10 @@ int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, 
 int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int neo, int nspin, const void* CT_d,
                   double* eri_d, int max_group, int kl_group);
 int ldm_eri_set_store(ldm_handle h, const void* store_d, int nslots);
+/* gso = 1 (nspin must be 2): the two "spins" are the alpha / beta halves of generalised spin orbitals and ONE ERI
+ * block eri_d (1, npair, npair) is built from Lambda_a - Lambda_b  (reference: get_emb_eri_gso / _Lij_s4_to_eri_gso,
+ * eri_transform.py:1104-1284).  Call right after ldm_eri_begin.                                              */
+int ldm_eri_set_mode(ldm_handle h, int gso);
 int ldm_eri_block_host(ldm_handle h, int ki, int kj, int sym, const void* L_h);
 int ldm_eri_block_store(ldm_handle h, int ki, int kj, int sym, int slot);
 int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, int aux_offset, uint32_t key_ij, uint32_t key_ji,

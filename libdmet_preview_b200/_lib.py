@@ -45,6 +45,7 @@ SIGNATURES = {
                                   C.c_uint32, C.c_double]),
     "ldm_eri_begin": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int]),
     "ldm_eri_set_store": (C.c_int, [vp, vp, C.c_int]),
+    "ldm_eri_set_mode": (C.c_int, [vp, C.c_int]),
     "ldm_eri_block_host": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_eri_block_store": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ldm_eri_block_synth": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,

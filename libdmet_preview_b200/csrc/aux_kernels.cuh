@@ -117,8 +117,12 @@ __global__ void d2z_kernel(const double* __restrict__ in, double2* __restrict__ 
 // One CTA handles a 16x16 (m, n) tile for 16 consecutive L: reads are 256-byte rows, writes are 128-byte rows.
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack_sym_kernel(const double2* __restrict__ S_sym, const double2* __restrict__ S_pln, double* __restrict__ XT,
+pack_sym_kernel(const double2* __restrict__ S_sym, const double2* __restrict__ S_pln,
+                const double2* __restrict__ S_sym2, const double2* __restrict__ S_pln2, double* __restrict__ XT,
                 int naux, int neo, long long ldx, long long col_re, long long col_im) {
+    // the optional second set (S_sym2, S_pln2) is SUBTRACTED: Lambda_a - Lambda_b of the generalised-spin-orbital
+    // (GSO) embedding ERI (reference: _Lij_s4_to_eri_gso, eri_transform.py:1252-1284, whose four signed Gram
+    // products equal one Gram product of the difference)
     extern __shared__ double2 v_raw[];
     double2 (*v)[16][17] = reinterpret_cast<double2 (*)[16][17]>(v_raw);   // [L][m][n]
     const int tm = blockIdx.x, tn = blockIdx.y;
@@ -128,21 +132,26 @@ pack_sym_kernel(const double2* __restrict__ S_sym, const double2* __restrict__ S
     const size_t n2 = (size_t)neo * neo;
     for (int l = 0; l < 16; ++l) {
         const int L = L0 + l;
-        double2 acc = make_double2(0.0, 0.0);
         const int m = tm * 16 + ty, n = tn * 16 + tx;      // contiguous reads along n:  S[L][m][n]
         const int m2 = tm * 16 + tx, n2i = tn * 16 + ty;    // contiguous reads along m:  S[L][n][m]
         double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
         if (L < naux) {
-            if (S_sym && m < neo && n < neo) a = S_sym[(size_t)L * n2 + (size_t)m * neo + n];
+            const size_t o1 = (size_t)L * n2 + (size_t)m * neo + n;
+            const size_t o2 = (size_t)L * n2 + (size_t)n2i * neo + m2;
+            if (m < neo && n < neo) {
+                if (S_sym) { const double2 q = S_sym[o1]; a.x += q.x; a.y += q.y; }
+                if (S_sym2) { const double2 q = S_sym2[o1]; a.x -= q.x; a.y -= q.y; }
+            }
             if (m2 < neo && n2i < neo) {
-                if (S_sym) { const double2 q = S_sym[(size_t)L * n2 + (size_t)n2i * neo + m2]; b.x += q.x; b.y += q.y; }
-                if (S_pln) { const double2 q = S_pln[(size_t)L * n2 + (size_t)n2i * neo + m2]; b.x += q.x; b.y += q.y; }
+                if (S_sym) { const double2 q = S_sym[o2]; b.x += q.x; b.y += q.y; }
+                if (S_pln) { const double2 q = S_pln[o2]; b.x += q.x; b.y += q.y; }
+                if (S_sym2) { const double2 q = S_sym2[o2]; b.x -= q.x; b.y -= q.y; }
+                if (S_pln2) { const double2 q = S_pln2[o2]; b.x -= q.x; b.y -= q.y; }
             }
         }
         v[l][ty][tx] = a;                 // (m = ty, n = tx)
         __syncthreads();
-        // add the transposed-read contribution: element (m = tx, n = ty) was read by this thread as b
-        acc = v[l][tx][ty];
+        double2 acc = v[l][tx][ty];       // element (m = tx, n = ty), whose transposed-read part is this thread's b
         __syncthreads();
         acc.x += b.x;
         acc.y += b.y;

@@ -545,6 +545,7 @@ struct PendingBlock {
 struct EriPlan {
     cudaStream_t st = nullptr, copy_st = nullptr;
     int nk = 0, nao = 0, naux = 0, neo = 0, nspin = 0, G = 1, klg = 1;
+    int gso = 0;                 // 1: two spin flavours, one ERI from Lambda_a - Lambda_b
     long long npair = 0, ldx = 0;
     const double2* CT = nullptr;
     double* eri = nullptr;
@@ -670,7 +671,7 @@ static int flush_panel(ldm_handle h) {
     const size_t eri_blk = (size_t)p->npair * p->npair;
     int rc = plan_timed_begin(p, 1);
     if (rc) return rc;
-    if (p->nspin == 1) {
+    if (p->nspin == 1 || p->gso) {
         rc = launch_dgemm(h, p->st, p->XT, p->ldx, p->XT, p->ldx, (int)p->npair, (int)p->npair, K, p->eri, p->npair,
                           p->xt_alpha, 1, 1);
         if (rc) return rc;
@@ -736,6 +737,14 @@ int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int 
     rc = encode_tmap_f64_3d(&p->tmXt, p->Xt, 2ull * nao, (uint64_t)naux * neo, (uint64_t)nspin * p->G, 16ull * nao,
                             16ull * xt_slice, 16, p->cfg->BM, true);
     if (rc) return rc;
+    return 0;
+}
+
+int ldm_eri_set_mode(ldm_handle h, int gso) {
+    LDM_REQUIRE(h && h->plan, "arguments");
+    LDM_REQUIRE(!gso || h->plan->nspin == 2, "GSO mode needs two spin flavours");
+    LDM_REQUIRE(h->plan->pending.empty() && h->plan->xt_cols == 0, "mode must be set before the first block");
+    h->plan->gso = gso ? 1 : 0;
     return 0;
 }
 
@@ -838,12 +847,21 @@ int ldm_eri_end_kl(ldm_handle h, int weight) {
     const long long col_im = weight == 1 ? -1 : p->xt_cols + p->naux;
     const int t = (p->neo + 15) / 16;
     const size_t s_spin = (size_t)p->naux * p->neo * p->neo;
-    for (int s = 0; s < p->nspin; ++s) {
+    if (p->gso) {
         pack_sym_kernel<<<dim3(t, t, (p->naux + 15) / 16), 256, 16 * 16 * 17 * 16, p->st>>>(
-            p->sym_init ? p->S_sym + s * s_spin : nullptr, p->pln_init ? p->S_pln + s * s_spin : nullptr,
-            p->XT + (size_t)s * p->npair * p->ldx, p->naux, p->neo, p->ldx, col_re, col_im);
+            p->sym_init ? p->S_sym : nullptr, p->pln_init ? p->S_pln : nullptr,
+            p->sym_init ? p->S_sym + s_spin : nullptr, p->pln_init ? p->S_pln + s_spin : nullptr, p->XT, p->naux,
+            p->neo, p->ldx, col_re, col_im);
         LDM_CUDA_OK(cudaGetLastError());
         h->launches++;
+    } else {
+        for (int s = 0; s < p->nspin; ++s) {
+            pack_sym_kernel<<<dim3(t, t, (p->naux + 15) / 16), 256, 16 * 16 * 17 * 16, p->st>>>(
+                p->sym_init ? p->S_sym + s * s_spin : nullptr, p->pln_init ? p->S_pln + s * s_spin : nullptr, nullptr,
+                nullptr, p->XT + (size_t)s * p->npair * p->ldx, p->naux, p->neo, p->ldx, col_re, col_im);
+            LDM_CUDA_OK(cudaGetLastError());
+            h->launches++;
+        }
     }
     p->xt_cols += ncols;
     p->kl_in_panel++;

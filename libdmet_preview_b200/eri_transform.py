@@ -152,7 +152,7 @@ def build_CT(provider, C_ao_lo=None, basis=None, C_ao_eo=None, unit_eri=False):
 class EriBuild(object):
     """One open `ldm_eri_*` build on the process-wide handle (context manager)."""
 
-    def __init__(self, CT, naux, eri, group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP):
+    def __init__(self, CT, naux, eri, group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, gso=False):
         self.dev = get_device()
         spin, nkpts, nemb, nao = CT.shape
         self.CT = CT
@@ -161,6 +161,8 @@ class EriBuild(object):
         check(self.dev.lib.ldm_eri_begin(self.dev.h, self.dev.stream, nkpts, nao, naux, nemb, spin, _ptr(CT),
                                          _ptr(eri), int(group), int(kl_group)))
         self.open = True
+        if gso:
+            check(self.dev.lib.ldm_eri_set_mode(self.dev.h, 1))
 
     def __enter__(self):
         return self
@@ -266,7 +268,7 @@ def finalize_eri(eri, nemb, symmetry, nspin):
 
 def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL, kscaled_center=None,
                    source="auto", group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, items=None, schedule=None,
-                   stores=None, store_map=None, stats=None):
+                   stores=None, store_map=None, stats=None, gso=False):
     """Stages 1-3 on the device.  Returns the (spin_pair, npair, npair) tensor holding the LOWER triangles of the
     symmetric blocks, summed over `items` = [(unit index, l0, l1)] (default: every unit, full aux range).
     stores: {(l0, l1): resident device tensor (nslots, l1-l0, nao, nao)} for source "store"."""
@@ -277,7 +279,7 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
         schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
     if items is None:
         items = work_items(schedule, provider.naux, 1)
-    eri = dev.zeros((spin * (spin + 1) // 2, npair, npair))
+    eri = dev.zeros((1 if gso else spin * (spin + 1) // 2, npair, npair))
     if stores is not None:
         source = "store"
     tot = {"launches": 0, "h2d_bytes": 0, "zgemm_ms": 0.0, "dgemm_ms": 0.0, "zgemm_launch_groups": 0,
@@ -286,7 +288,7 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
     for (l0, l1) in ranges:                 # one build per distinct aux range (workspaces are sized by it)
         sub = [it for it in items if (it[1], it[2]) == (l0, l1)]
         sub.sort(key=lambda it: (schedule.units[it[0]][1], it[0]))     # equal weights share stage-3 launches
-        with EriBuild(CT, l1 - l0, eri, group, kl_group) as b:
+        with EriBuild(CT, l1 - l0, eri, group, kl_group, gso=gso) as b:
             if stores is not None:
                 b.set_store(stores[(l0, l1)])
             run_items(b, provider, schedule, sub, source, store_map)
@@ -361,3 +363,74 @@ def get_unit_eri(cell, mydf, C_ao_lo=None, symmetry=4, t_reversal_symm=True, max
 
 
 get_unit_eri_fast_gdf = get_unit_eri
+
+
+def separate_basis(basis):
+    """alpha / beta halves of a generalised-spin-orbital basis (nkpts, 2*nao, nbasis)
+    (libdmet/routine/spinless_helper.py:31-46)."""
+    nao = basis.shape[1] // 2
+    return basis[:, :nao], basis[:, nao:]
+
+
+def build_CT_gso(provider, C_ao_lo, basis=None, basis_k=None, unit_eri=False):
+    """(2, nkpts, nemb, nao) device tensor for the GSO build (eri_transform.py:1132-1154): C_ao_lo gets two spin
+    flavours, the R-space basis (ncells, 2*nlo, nemb) is Fourier transformed and split into its alpha / beta rows."""
+    dev = get_device()
+    nao, nkpts = provider.nao, len(provider.kpts_scaled)
+    scale = 1.0 / (nkpts ** 0.75)
+    C_ao_lo = C_ao_lo if isinstance(C_ao_lo, torch.Tensor) else np.asarray(C_ao_lo)
+    C_ao_lo = add_spin_dim(C_ao_lo, 2)
+    nlo = C_ao_lo.shape[-1]
+    if unit_eri:
+        Cz = _to_z(C_ao_lo)
+        return dev.ztranspose(Cz.reshape(-1, nao, nlo), scale=scale).reshape(2, nkpts, nlo, nao)
+    if basis_k is None:
+        basis = basis if isinstance(basis, torch.Tensor) else np.asarray(basis)
+        assert basis is not None and basis.ndim == 3
+        if isinstance(basis, torch.Tensor):
+            bd = basis.contiguous()[None]
+        elif np.iscomplexobj(basis):
+            bd = dev.to_device(np.ascontiguousarray(basis), torch.complex128)[None]
+        else:
+            bd = dev.to_device(np.ascontiguousarray(basis, dtype=np.float64), torch.float64)[None]
+        phase = fourier.get_phase_R2k_scaled(provider.kmesh, provider.kpts_scaled)
+        W = dev.to_device(np.ascontiguousarray(phase.T), torch.complex128)
+        bk, _ = dev.phase_transform(bd, W)
+        bk = bk[0]                                                     # (nk, 2*nlo, nemb)
+    else:
+        bk = _to_z(basis_k)
+    if bk.dim() == 3:
+        a, b = separate_basis(bk)
+        bk = torch.stack([a, b]).contiguous()                          # (2, nk, nlo, nemb)
+    nemb = bk.shape[-1]
+    assert tuple(bk.shape[:3]) == (2, nkpts, nlo)
+    bkT = dev.ztranspose(bk.reshape(-1, nlo, nemb))
+    Cz = _to_z(C_ao_lo).reshape(-1, nao, nlo)
+    nb = 2 * nkpts
+    segs = np.zeros((nb, 4), dtype=np.int32)
+    segs[:, 0] = np.arange(nb)
+    segs[:, 1] = np.arange(nb)
+    CT = dev.empty((2, nkpts, nemb, nao), torch.complex128)
+    dev.zgemm_tn(bkT, Cz, segs, CT, c_off=np.arange(nb, dtype=np.int64) * nemb * nao, s_outer=nao, alpha=scale,
+                 nbatch=nb, nseg=1)
+    return CT
+
+
+def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_center=None, symmetry=4,
+                    max_memory=None, kconserv_tol=KPT_DIFF_TOL, unit_eri=False, swap_idx=None, t_reversal_symm=True,
+                    basis_k=None, incore=True, fout="H2.h5", return_device=False, **kwargs):
+    """eri_transform.py:1104-1250: embedding ERI with partial particle-hole transform (generalised spin orbitals).
+    Same stage-1 pipeline with two spin flavours; stage 3 is one Gram product of Lambda_a - Lambda_b
+    (= the four signed products of `_Lij_s4_to_eri_gso`, l.1252-1284).  Returns (1,) + s4 / s1 / s8 layout."""
+    if not incore:
+        raise NotImplementedError("outcore (HDF5) accumulation is outside the GPU path; use incore=True")
+    provider = as_provider(cell, mydf)
+    CT = build_CT_gso(provider, C_ao_lo, basis, basis_k, unit_eri)
+    nemb = CT.shape[2]
+    schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
+    eri = emb_eri_device(provider, CT, schedule=schedule,
+                         items=work_items(schedule, provider.naux, kwargs.get("nsplit", 1)),
+                         source=kwargs.get("source", "auto"), group=kwargs.get("group", DEFAULT_GROUP),
+                         kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None), gso=True)
+    eri = finalize_eri(eri, nemb, symmetry, 1)
+    return eri if return_device else eri.cpu().numpy()

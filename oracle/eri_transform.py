@@ -263,3 +263,99 @@ def get_unit_eri(cell, mydf, C_ao_lo=None, symmetry=4, t_reversal_symm=True, max
     return get_emb_eri(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, feri=feri, kscaled_center=kscaled_center,
                        symmetry=symmetry, max_memory=max_memory, kconserv_tol=kconserv_tol, unit_eri=True,
                        swap_idx=swap_idx, t_reversal_symm=t_reversal_symm, incore=incore, fout=fout, **kwargs)
+
+
+def _Lij_s4_to_eri_gso(Lij_s4, eri, weight=1, t_reversal_symm=False):
+    """eri_transform.py:1252-1284 (incore branch)."""
+    if t_reversal_symm:
+        Lij_loc_a, Lij_loc_b = np.asarray(Lij_s4.real, order='C')
+        if weight == 1:
+            lib.dot(Lij_loc_a.T, Lij_loc_a, 1.0, eri[0], 1)
+            lib.dot(Lij_loc_b.T, Lij_loc_b, 1.0, eri[0], 1)
+            lib.dot(Lij_loc_a.T, Lij_loc_b, -1.0, eri[0], 1)
+            lib.dot(Lij_loc_b.T, Lij_loc_a, -1.0, eri[0], 1)
+        elif weight == 2:
+            for part in (Lij_s4.real, Lij_s4.imag):
+                Lij_loc_a, Lij_loc_b = np.asarray(part, order='C')
+                lib.dot(Lij_loc_a.T, Lij_loc_a, 2.0, eri[0], 1)
+                lib.dot(Lij_loc_b.T, Lij_loc_b, 2.0, eri[0], 1)
+                lib.dot(Lij_loc_a.T, Lij_loc_b, -2.0, eri[0], 1)
+                lib.dot(Lij_loc_b.T, Lij_loc_a, -2.0, eri[0], 1)
+        else:
+            raise ValueError
+    else:
+        lib.dot(Lij_s4[0].conj().T, Lij_s4[0], 1.0, eri[0], 1)
+        lib.dot(Lij_s4[1].conj().T, Lij_s4[1], 1.0, eri[0], 1)
+        tmp_ab = lib.dot(Lij_s4[0].conj().T, Lij_s4[1], -1.0)
+        eri[0] += tmp_ab
+        eri[0] += tmp_ab.conj().T
+
+
+def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_center=None, symmetry=4,
+                    max_memory=None, kconserv_tol=KPT_DIFF_TOL, unit_eri=False, swap_idx=None,
+                    t_reversal_symm=True, basis_k=None, incore=True, fout="H2.h5"):
+    """eri_transform.py:1104-1250 (incore): GSO embedding ERI with partial particle-hole transform."""
+    assert incore
+    nao = mydf.nao
+    nkpts = len(mydf.kpts_scaled)
+    naux = mydf.naux
+    C_ao_lo = add_spin_dim(C_ao_lo, 2)
+    kscaled = np.array(mydf.kpts_scaled, dtype=float)
+    if kscaled_center is not None:
+        kscaled = kscaled - kscaled_center
+    if basis_k is None:
+        assert basis is not None and basis.ndim == 3
+        phase = get_phase_R2k_scaled(mydf.kmesh, mydf.kpts_scaled)
+        basis_k = get_basis_k(basis[None], phase)[0]
+    if basis_k.ndim == 3:
+        nso = basis_k.shape[1] // 2          # separate_basis, libdmet/routine/spinless_helper.py:31-46
+        basis_k = np.asarray((basis_k[:, :nso], basis_k[:, nso:]))
+    if unit_eri:
+        C_ao_emb = C_ao_lo / (nkpts ** 0.75)
+    else:
+        C_ao_emb = multiply_basis(C_ao_lo, basis_k) / (nkpts ** 0.75)
+    spin, _, _, nemb = C_ao_emb.shape
+    nemb_pair = nemb * (nemb + 1) // 2
+    res_shape = (1, nemb_pair, nemb_pair)
+    if t_reversal_symm:
+        weights = get_weights_t_reversal(mydf.kpts_scaled)
+        eri = np.zeros(res_shape)
+    else:
+        weights = np.ones((nkpts,), dtype=int)
+        eri = np.zeros(res_shape, dtype=np.complex128)
+    if max_memory is None:
+        max_memory = 2000
+    blksize = max_memory * 1e6 / 16 / (nao ** 2 * 2)
+    blksize = max(16, min(int(blksize), getattr(mydf, "blockdim", 240)))
+    Lij_s4 = np.empty((spin, naux, nemb_pair), dtype=np.complex128)
+    for kL in range(nkpts):
+        if weights[kL] <= 0:
+            continue
+        Lij_s4[:] = 0.0
+        i_visited = np.zeros((nkpts,), dtype=bool)
+        for i in range(nkpts):
+            if i_visited[i]:
+                continue
+            i_visited[i] = True
+            for j in range(nkpts):
+                kconserv = -kscaled[i] + kscaled[j] + kscaled[kL]
+                if max_abs(np.round(kconserv) - kconserv) > kconserv_tol:
+                    continue
+                if t_reversal_symm:
+                    jm = kpt_member(-kscaled[j], kscaled)
+                    assert len(jm) == 1
+                    jm = jm[0]
+                step0, step1 = 0, 0
+                for Lpq in sr_loop(mydf, i, j, blksize):
+                    lchunk = Lpq.shape[0]
+                    step0, step1 = step1, step1 + lchunk
+                    Lij_loc = transform_ao_to_emb(Lpq, C_ao_emb, i, j).reshape(-1, nemb, nemb)
+                    if t_reversal_symm and (not i_visited[jm]):
+                        lib.hermi_sum(Lij_loc, axes=(0, 2, 1), hermi=lib.SYMMETRIC, inplace=True)
+                    Lij_s4[:, step0:step1] += lib.pack_tril(Lij_loc).reshape(spin, lchunk, nemb_pair)
+                if t_reversal_symm:
+                    i_visited[jm] = True
+        _Lij_s4_to_eri_gso(Lij_s4, eri, weight=weights[kL], t_reversal_symm=t_reversal_symm)
+    if not t_reversal_symm:
+        eri = eri.real
+    return eri_restore(eri, symmetry, nemb)

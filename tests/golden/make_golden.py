@@ -150,7 +150,29 @@ def gen_emb_basis_hchain():
     save("emb_basis_hchain", rdm1_lo=rdm1_lo, basis=basis, basis_trunc=basis_trunc)
 
 
+def gen_gso():
+    """GSO embedding ERI (eri_transform.py:1104-1284); the reference itself imports
+    libdmet.routine.spinless.separate_basis inside the function"""
+    for name, (kmesh, nao, naux, nemb, cspin) in {"gso_113": ([1, 1, 3], 4, 9, 6, 1), "gso_122": ([1, 2, 2], 3, 8, 5, 2)}.items():
+        gdf, C, _ = problem(kmesh, nao, naux, 2, spin=cspin)
+        gdf.cell = GoldenCell(nao)
+        mydf = ref_gdf(gdf, name)
+        nk = int(np.prod(kmesh))
+        rng = np.random.default_rng(77)
+        basis, _ = np.linalg.qr(rng.standard_normal((nk * 2 * nao, nemb)))
+        basis = basis.reshape(nk, 2 * nao, nemb)
+        out = dict(kmesh=np.array(kmesh), nao=nao, naux=naux, nemb=nemb, gdf_seed=gdf.seed, gdf_scale=gdf.scale,
+                   C_ao_lo=C, basis=basis)
+        out["s4_trs"] = ref_eri.get_emb_eri_gso(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4)
+        out["s4_plain"] = ref_eri.get_emb_eri_gso(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4,
+                                                  t_reversal_symm=False)
+        out["s1_trs"] = ref_eri.get_emb_eri_gso(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=1)
+        out["unit_s4"] = ref_eri.get_emb_eri_gso(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4, unit_eri=True)
+        save(name, **out)
+
+
 if __name__ == "__main__":
+    gen_gso()
     gen_eri()
     gen_fourier_basis()
     gen_embham()

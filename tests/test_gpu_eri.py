@@ -137,3 +137,23 @@ def test_aux_split_items(dev, nsplit):
     for source in ("synth", "host"):
         sp = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, nsplit=nsplit, source=source)
         assert np.abs(sp - ref).max() < TOL
+
+
+def test_gso_eri(dev):
+    """GSO embedding ERI at a less trivial size against the oracle, incl. a basis with time-reversal structure
+    for which the two schedules must agree (test_eri_transform_gso.py:155)."""
+    from libdmet_preview_b200 import eri_transform as et
+    from oracle import eri_transform as oe
+    gdf, C, _ = problem([2, 1, 2], 7, 20, 4, spin=2)
+    rng = np.random.default_rng(3)
+    basis, _ = np.linalg.qr(rng.standard_normal((4 * 14, 9)))
+    basis = basis.reshape(4, 14, 9)                 # real in R space -> time-reversal symmetric in k space
+    got = et.get_emb_eri_gso(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+    ref = oe.get_emb_eri_gso(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+    assert got.shape == ref.shape == (1, 45, 45) and np.abs(got - ref).max() < TOL
+    plain = et.get_emb_eri_gso(gdf.cell, gdf, C_ao_lo=C, basis=basis, t_reversal_symm=False)
+    assert np.abs(plain - got).max() < TOL
+    bk = np.einsum("Rim,Rk->kim", basis, __import__("oracle.fourier", fromlist=["x"]).get_phase_R2k_scaled(
+        gdf.kmesh, gdf.kpts_scaled))
+    via_k = et.get_emb_eri_gso(gdf.cell, gdf, C_ao_lo=C, basis_k=bk, nsplit=2, group=3)
+    assert np.abs(via_k - ref).max() < TOL
