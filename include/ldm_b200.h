@@ -71,6 +71,11 @@ int ldm_mirror_lower(ldm_handle h, void* stream, double* C_d, int n, int64_t ldc
 int ldm_phase_transform(ldm_handle h, void* stream, const void* in_d, void* out_d, const void* W_d, int nin,
                         int nout, int64_t X, int batch, double scale, int in_real, int out_real,
                         double* imag_max_h);
+/* The same transform for the k-points of the mesh itself, factorised over the mesh axes (kmesh3 = {n0,n1,n2}, each
+ * 1..8): out[b][k][x] = scale * sum_R exp(-+2 pi i k.R) in[b][R][x], forward != 0 -> minus sign (R2k / FFTtoK),
+ * forward == 0 -> plus sign (k2R / FFTtoT, pass scale = 1/Nk).  HBM-bound.                                    */
+int ldm_lattice_dft(ldm_handle h, void* stream, const void* in_d, void* out_d, const int32_t* kmesh3, int64_t X,
+                    int batch, int forward, double scale, int in_real, int out_real, double* imag_max_h);
 /* out[b][c][r] = scale * op(in[b][r][c]) for complex matrices (op = conj if conj != 0) */
 int ldm_ztranspose(ldm_handle h, void* stream, const void* in_d, void* out_d, int batch, int rows, int cols,
                    int conj, double scale);

@@ -35,6 +35,8 @@ SIGNATURES = {
     "ldm_mirror_lower": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64]),
     "ldm_phase_transform": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double,
                                       C.c_int, C.c_int, c_f64p]),
+    "ldm_lattice_dft": (C.c_int, [vp, vp, vp, vp, c_i32p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                  c_f64p]),
     "ldm_ztranspose": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "ldm_d2z": (C.c_int, [vp, vp, vp, vp, C.c_int64]),
     "ldm_ksum_real": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int64, C.c_double, c_f64p]),

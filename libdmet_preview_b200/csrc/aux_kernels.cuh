@@ -77,6 +77,151 @@ phase_transform_kernel(const double* __restrict__ in, double* __restrict__ out, 
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// Lattice Fourier transform on the k-mesh itself, factorised over the (<= 3) mesh axes:
+//     out[b][k][x] = scale * sum_R exp(-+ 2 pi i k.R) in[b][R][x]        (R2k: minus, k2R: plus and scale = 1/Nk)
+// One CTA stages a [Nk][TX] tile of TX consecutive x in shared memory (512-byte coalesced rows), runs one dense
+// n_d-point DFT pass per mesh axis in place (each thread owns whole lines, one __syncthreads per pass) and streams
+// the result out (the first pass reads straight from global memory, the last one writes straight to it).
+// 12 complex MACs per element at 4x4x4 instead of 64 for the dense phase matrix, so the kernel is
+// bound by HBM: algorithmic bytes 8|16 Nk X in + 8|16 Nk X out.  Replaces scipy fftn / ifftn
+// (libdmet/system/fourier.py:160-177).  Mesh axes up to 8 points; larger meshes use phase_transform_kernel.
+// ----------------------------------------------------------------------------------------------------------
+struct DftTables {
+    double2 w[3][64];     // w[d][k * n_d + r] = exp(-+ 2 pi i k r / n_d), filled on the host
+};
+
+// one n-point DFT over a line held in registers
+template <int ND>
+__device__ __forceinline__ void dft_line(double2 (&v)[ND], const double2* __restrict__ tw, double2 (&o)[ND]) {
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        double re = 0.0, im = 0.0;
+#pragma unroll
+        for (int r = 0; r < ND; ++r) {
+            const double2 w = tw[k * ND + r];
+            re = fma(w.x, v[r].x, re);
+            re = fma(-w.y, v[r].y, re);
+            im = fma(w.x, v[r].y, im);
+            im = fma(w.y, v[r].x, im);
+        }
+        o[k] = make_double2(re, im);
+    }
+}
+
+// pass over mesh axis 0: global -> registers -> shared tile
+template <int ND>
+__device__ __forceinline__ void dft_pass_in(const double* __restrict__ in, double2* tile, const double2* tw, int s0,
+                                            int TX, long long X, long long x0, size_t boff, int in_real) {
+    for (int ln = threadIdx.x; ln < s0 * TX; ln += blockDim.x) {
+        const int tx = ln % TX, inner = ln / TX;
+        double2 v[ND], o[ND];
+        const bool ok = x0 + tx < X;
+#pragma unroll
+        for (int r = 0; r < ND; ++r) {
+            v[r] = make_double2(0.0, 0.0);
+            if (ok) {
+                const size_t g = boff + (size_t)(r * s0 + inner) * X + x0 + tx;
+                if (in_real) v[r].x = in[g];
+                else v[r] = reinterpret_cast<const double2*>(in)[g];
+            }
+        }
+        dft_line<ND>(v, tw, o);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) tile[(k * s0 + inner) * TX + tx] = o[k];
+    }
+}
+
+// pass over mesh axis 1: shared -> shared, in place
+template <int ND>
+__device__ __forceinline__ void dft_pass_mid(double2* tile, const double2* tw, int n0, int s1, int TX) {
+    for (int ln = threadIdx.x; ln < n0 * s1 * TX; ln += blockDim.x) {
+        const int tx = ln % TX, rest = ln / TX;
+        const int outer = rest / s1, inner = rest - outer * s1;
+        const int base = (outer * ND * s1 + inner) * TX + tx;
+        double2 v[ND], o[ND];
+#pragma unroll
+        for (int r = 0; r < ND; ++r) v[r] = tile[base + r * s1 * TX];
+        dft_line<ND>(v, tw, o);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) tile[base + k * s1 * TX] = o[k];
+    }
+}
+
+// pass over mesh axis 2: shared -> registers -> global
+template <int ND>
+__device__ __forceinline__ double dft_pass_out(double* __restrict__ out, const double2* tile, const double2* tw,
+                                               int nouter, int TX, long long X, long long x0, size_t boff,
+                                               double scale, int out_real) {
+    double im_max = 0.0;
+    for (int ln = threadIdx.x; ln < nouter * TX; ln += blockDim.x) {
+        const int tx = ln % TX, outer = ln / TX;
+        double2 v[ND], o[ND];
+#pragma unroll
+        for (int r = 0; r < ND; ++r) v[r] = tile[(outer * ND + r) * TX + tx];
+        dft_line<ND>(v, tw, o);
+        if (x0 + tx < X) {
+#pragma unroll
+            for (int k = 0; k < ND; ++k) {
+                const size_t g = boff + (size_t)(outer * ND + k) * X + x0 + tx;
+                if (out_real) {
+                    out[g] = o[k].x * scale;
+                    im_max = fmax(im_max, fabs(o[k].y * scale));
+                } else {
+                    reinterpret_cast<double2*>(out)[g] = make_double2(o[k].x * scale, o[k].y * scale);
+                }
+            }
+        }
+    }
+    return im_max;
+}
+
+// dispatch on the axis length; MAXND bounds the instantiated line lengths so that the common small meshes (axes of
+// <= 4 points) compile to <= 64 registers and four CTAs share an SM (load, compute and store phases overlap)
+#define LDM_DFT_SWITCH(nd, CALL)                                              \
+    switch (nd) {                                                            \
+        case 1: { constexpr int ND = 1; CALL; } break;                       \
+        case 2: { constexpr int ND = 2; CALL; } break;                       \
+        case 3: { constexpr int ND = 3; CALL; } break;                       \
+        case 4: { constexpr int ND = 4; CALL; } break;                       \
+        default:                                                             \
+            if constexpr (MAXND > 4) {                                       \
+                switch (nd) {                                                \
+                    case 5: { constexpr int ND = 5; CALL; } break;           \
+                    case 6: { constexpr int ND = 6; CALL; } break;           \
+                    case 7: { constexpr int ND = 7; CALL; } break;           \
+                    default: { constexpr int ND = 8; CALL; } break;          \
+                }                                                            \
+            }                                                                \
+            break;                                                           \
+    }
+
+template <int MAXND>
+__global__ void __launch_bounds__(256, MAXND <= 4 ? 4 : 1)
+lattice_dft_kernel(const double* __restrict__ in, double* __restrict__ out, const __grid_constant__ DftTables tb,
+                   int n0, int n1, int n2, long long X, int TX, double scale, int in_real, int out_real,
+                   unsigned long long* imag_max) {
+    extern __shared__ double2 dft_smem[];
+    const int nk = n0 * n1 * n2;
+    double2* tile = dft_smem;                 // [nk][TX]
+    const long long x0 = (long long)blockIdx.x * TX;
+    const size_t boff = (size_t)blockIdx.y * nk * X;
+    LDM_DFT_SWITCH(n0, dft_pass_in<ND>(in, tile, tb.w[0], n1 * n2, TX, X, x0, boff, in_real));
+    __syncthreads();
+    if (n1 > 1) {
+        LDM_DFT_SWITCH(n1, dft_pass_mid<ND>(tile, tb.w[1], n0, n2, TX));
+        __syncthreads();
+    }
+    double im_max = 0.0;
+    LDM_DFT_SWITCH(n2, im_max = dft_pass_out<ND>(out, tile, tb.w[2], n0 * n1, TX, X, x0, boff, scale, out_real));
+    if (out_real && imag_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) im_max = fmax(im_max, __shfl_xor_sync(0xffffffffu, im_max, o));
+        if ((threadIdx.x & 31) == 0 && im_max > 0.0)
+            atomicMax(imag_max, (unsigned long long)__double_as_longlong(im_max));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // Batched complex transpose with optional conjugation and real scale:  out[b][c][r] = scale * op(in[b][r][c]).
 // Used to lay coefficient matrices out with the contraction index contiguous for the TN GEMM.
 // ----------------------------------------------------------------------------------------------------------

@@ -429,6 +429,66 @@ int ldm_phase_transform(ldm_handle h, void* stream, const void* in_d, void* out_
     return 0;
 }
 
+int ldm_lattice_dft(ldm_handle h, void* stream, const void* in_d, void* out_d, const int32_t* kmesh3, int64_t X,
+                    int batch, int forward, double scale, int in_real, int out_real, double* imag_max_h) {
+    LDM_REQUIRE(h && in_d && out_d && kmesh3, "null pointer");
+    const int n0 = kmesh3[0], n1 = kmesh3[1], n2 = kmesh3[2];
+    LDM_REQUIRE(n0 >= 1 && n1 >= 1 && n2 >= 1 && n0 <= 8 && n1 <= 8 && n2 <= 8, "mesh axes must have 1..8 points");
+    LDM_REQUIRE(X > 0 && batch > 0, "shape");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nk = n0 * n1 * n2;
+    int TX = 32;
+    while (TX > 1 && (size_t)nk * TX * 16 > 96 * 1024) TX >>= 1;
+    const size_t smem = (size_t)nk * TX * 16;
+    DftTables tb;
+    {
+        const int nd[3] = {n0, n1, n2};
+        const double sgn = forward ? -1.0 : 1.0;
+        for (int d = 0; d < 3; ++d)
+            for (int k = 0; k < nd[d]; ++k)
+                for (int r = 0; r < nd[d]; ++r) {
+                    const int m = (k * r) % nd[d];
+                    double c = std::cos(2.0 * M_PI * m / nd[d]), sn = std::sin(2.0 * M_PI * m / nd[d]);
+                    if (4 * m == nd[d]) { c = 0.0; sn = 1.0; }            // exact quarter turns
+                    else if (2 * m == nd[d]) { c = -1.0; sn = 0.0; }
+                    else if (4 * m == 3 * nd[d]) { c = 0.0; sn = -1.0; }
+                    else if (m == 0) { c = 1.0; sn = 0.0; }
+                    tb.w[d][k * nd[d] + r] = make_double2(c, sgn * sn);
+                }
+    }
+    LDM_REQUIRE(smem <= 200 * 1024, "mesh too large for the shared-memory DFT");
+    static bool attr = false;
+    if (!attr) {
+        LDM_CUDA_OK(cudaFuncSetAttribute((const void*)lattice_dft_kernel<4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LDM_CUDA_OK(cudaFuncSetAttribute((const void*)lattice_dft_kernel<8>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    if (out_real) LDM_CUDA_OK(cudaMemsetAsync(h->imag_d, 0, sizeof(unsigned long long), st));
+    dim3 grid((unsigned)((X + TX - 1) / TX), (unsigned)batch);
+    if (n0 <= 4 && n1 <= 4 && n2 <= 4)
+        lattice_dft_kernel<4><<<grid, 256, smem, st>>>(static_cast<const double*>(in_d), static_cast<double*>(out_d), tb,
+                                                       n0, n1, n2, (long long)X, TX, scale, in_real, out_real,
+                                                       out_real ? h->imag_d : nullptr);
+    else
+        lattice_dft_kernel<8><<<grid, 256, smem, st>>>(static_cast<const double*>(in_d), static_cast<double*>(out_d), tb,
+                                                       n0, n1, n2, (long long)X, TX, scale, in_real, out_real,
+                                                       out_real ? h->imag_d : nullptr);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    if (out_real && imag_max_h) {
+        unsigned long long bits = 0;
+        LDM_CUDA_OK(cudaMemcpyAsync(&bits, h->imag_d, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        LDM_CUDA_OK(cudaStreamSynchronize(st));
+        double v;
+        std::memcpy(&v, &bits, sizeof(v));
+        *imag_max_h = v;
+    }
+    return 0;
+}
+
 int ldm_ztranspose(ldm_handle h, void* stream, const void* in_d, void* out_d, int batch, int rows, int cols,
                    int conj, double scale) {
     LDM_REQUIRE(h && in_d && out_d && batch > 0 && rows > 0 && cols > 0, "arguments");

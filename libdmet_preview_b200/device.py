@@ -131,6 +131,22 @@ class Device(object):
                                            C.byref(imag) if (out_real and want_imag) else None))
         return out, (imag.value if (out_real and want_imag) else None)
 
+    def lattice_dft(self, x, kmesh, forward, out_real=False, scale=1.0, want_imag=True):
+        """factorised lattice DFT on the mesh's own k-points: x (batch, ncells, ...) real or complex ->
+        (batch, nkpts, ...) complex (or real part only).  Returns (out, max|imag| or None)."""
+        in_real = x.dtype == torch.float64
+        assert in_real or x.dtype == torch.complex128
+        assert x.is_contiguous() and x.shape[1] == int(np.prod(kmesh))
+        km = (list(kmesh) + [1, 1, 1])[:3]
+        X = int(np.prod(x.shape[2:]))
+        out = self.empty(tuple(x.shape), torch.float64 if out_real else torch.complex128)
+        imag = C.c_double(0.0)
+        km_arr = (C.c_int32 * 3)(*[int(v) for v in km])
+        check(self.lib.ldm_lattice_dft(self.h, self.stream, _ptr(x), _ptr(out), km_arr, X, x.shape[0],
+                                       int(bool(forward)), float(scale), int(in_real), int(out_real),
+                                       C.byref(imag) if (out_real and want_imag) else None))
+        return out, (imag.value if (out_real and want_imag) else None)
+
     def ztranspose(self, x, conj=False, scale=1.0):
         """(batch, rows, cols) complex128 -> (batch, cols, rows)."""
         assert x.dtype == torch.complex128 and x.is_contiguous() and x.dim() == 3

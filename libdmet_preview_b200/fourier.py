@@ -77,8 +77,12 @@ def _transform(A, kmesh, forward, out_real, tol):
     assert x.shape[-3] == nk, "first (non-spin) dimension must be the number of cells / k-points"
     dev = get_device()
     x4 = x.reshape((-1,) + tuple(x.shape[-3:]))
-    W = _phase_dev(kmesh, forward)
-    out, imag = dev.phase_transform(x4, W, out_real=out_real, scale=1.0 if forward else 1.0 / nk)
+    if len(kmesh) <= 3 and max(int(v) for v in kmesh) <= 8:
+        # factorised, HBM-bound kernel on the mesh's own k-points
+        out, imag = dev.lattice_dft(x4, kmesh, forward, out_real=out_real, scale=1.0 if forward else 1.0 / nk)
+    else:
+        W = _phase_dev(kmesh, forward)
+        out, imag = dev.phase_transform(x4, W, out_real=out_real, scale=1.0 if forward else 1.0 / nk)
     out = out.reshape(tuple(x.shape))
     if out_real and imag is not None and imag > tol:
         warnings.warn("k2R: non-zero imaginary part: %15.8g" % imag)     # fourier.py:174-175
