@@ -94,6 +94,11 @@ int ldm_restore_s8(ldm_handle h, void* stream, const double* eri4_d, double* out
 int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm_d, double* vj_d, double* vk_d,
               int n);
 
+/* DMET energy weights, in place (reference: get_H2_scaled, libdmet/routine/slater.py:1734-1778).
+ * symmetry 4: eri (npair, npair) *= (w[P] + w[Q]) / 4 with weights_d[npair] = impurity count of each pair (0,1,2);
+ * symmetry 1: eri (n,n,n,n) *= (m[i]+m[j]+m[k]+m[l]) / 4 with weights_d[n] = 0/1 impurity flags.              */
+int ldm_scale_eri(ldm_handle h, void* stream, double* eri_d, int n, int symmetry, const int32_t* weights_d);
+
 /* ---- synthetic GDF block generator -----------------------------------------------------------------------
  * Writes rows [aux_offset, aux_offset + naux) of L(k_i,k_j) (.., nao, nao) complex for the seeded synthetic
  * provider (host twin: libdmet_preview_b200/synthetic.py); keys are the four 32-bit pair keys of that scheme. */

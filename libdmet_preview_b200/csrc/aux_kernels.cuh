@@ -441,6 +441,30 @@ jk_reduce_kernel(const double* __restrict__ kpart, double* __restrict__ vk, int 
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// DMET energy weights (reference: get_H2_scaled, libdmet/routine/slater.py:1734-1778): every two-electron
+// integral is scaled by (number of impurity indices among its four) / 4.
+//   s4: E[P][Q] *= (w[P] + w[Q]) / 4,  w[P] = impurity count of the pair P in {0, 1, 2}
+//   s1: E[i][j][k][l] *= (m[i] + m[j] + m[k] + m[l]) / 4,  m = 0/1 impurity flag
+// ----------------------------------------------------------------------------------------------------------
+__global__ void scale_s4_kernel(double* __restrict__ E, const int* __restrict__ w, long long npair) {
+    const long long P = blockIdx.x;
+    const double wp = (double)w[P];
+    double* row = E + P * npair;
+    for (long long Q = threadIdx.x; Q < npair; Q += blockDim.x) row[Q] *= (wp + (double)w[Q]) * 0.25;
+}
+
+__global__ void scale_s1_kernel(double* __restrict__ E, const int* __restrict__ m, int n) {
+    const int ij = blockIdx.x;
+    const int i = ij / n, j = ij - i * n;
+    const double mij = (double)(m[i] + m[j]);
+    double* dst = E + (long long)ij * n * n;
+    for (int kl = threadIdx.x; kl < n * n; kl += blockDim.x) {
+        const int k = kl / n, l = kl - k * n;
+        dst[kl] *= (mij + (double)(m[k] + m[l])) * 0.25;
+    }
+}
+
 // unpack a packed symmetric vector to a full (n, n) matrix
 __global__ void unpack_sym_kernel(const double* __restrict__ packed, double* __restrict__ full, int n) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {

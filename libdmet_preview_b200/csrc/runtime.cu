@@ -578,6 +578,19 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
     return 0;
 }
 
+int ldm_scale_eri(ldm_handle h, void* stream, double* eri_d, int n, int symmetry, const int32_t* weights_d) {
+    LDM_REQUIRE(h && eri_d && weights_d && n > 0 && (symmetry == 1 || symmetry == 4), "arguments");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    const long long npair = (long long)n * (n + 1) / 2;
+    if (symmetry == 4)
+        scale_s4_kernel<<<(unsigned)npair, 256, 0, (cudaStream_t)stream>>>(eri_d, weights_d, npair);
+    else
+        scale_s1_kernel<<<n * n, 256, 0, (cudaStream_t)stream>>>(eri_d, weights_d, n);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
 int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, int aux_offset, uint32_t key_ij,
                     uint32_t key_ji, uint32_t key_mij, uint32_t key_mji, double scale) {
     LDM_CUDA_OK(cudaSetDevice(h->device));

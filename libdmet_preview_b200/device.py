@@ -190,6 +190,12 @@ class Device(object):
                                  n))
         return vj, vk
 
+    def scale_eri(self, eri, n, symmetry, weights):
+        """in place: s4 (npair, npair) with per-pair impurity counts, or s1 (n,n,n,n) with 0/1 flags (int32)"""
+        assert eri.dtype == torch.float64 and eri.is_contiguous() and weights.dtype == torch.int32
+        check(self.lib.ldm_scale_eri(self.h, self.stream, _ptr(eri), n, int(symmetry), _ptr(weights)))
+        return eri
+
     def synth_block(self, out, naux, nao, keys, scale, aux_offset=0):
         check(self.lib.ldm_synth_block(self.h, self.stream, _ptr(out), naux, nao, int(aux_offset), int(keys[0]),
                                        int(keys[1]), int(keys[2]), int(keys[3]), float(scale)))

@@ -357,3 +357,141 @@ def get_emb_Ham(lattice, basis, vcor, local=True, **kwargs):
 
 
 embHam = get_emb_Ham
+
+
+# ---------------------------------------------------------------------------------------------------------
+# energy side of the iteration: scaled DMET Hamiltonian and result transformation
+# ---------------------------------------------------------------------------------------------------------
+def _env_idx(nbasis, imp_idx, env_idx):
+    if env_idx is None:
+        imp = set(int(i) for i in imp_idx)
+        env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp], dtype=int)
+    return np.asarray(env_idx, dtype=int)
+
+
+def get_H1_scaled(H1, imp_idx, env_idx=None):
+    """slater.py:1716-1732 (in place): imp-env blocks halved, env-env block zeroed."""
+    assert H1.ndim == 3
+    nbasis = H1.shape[-1]
+    imp_idx = np.asarray(imp_idx, dtype=int)
+    env_idx = _env_idx(nbasis, imp_idx, env_idx)
+    for s in range(H1.shape[0]):
+        H1[s][np.ix_(imp_idx, env_idx)] *= 0.5
+        H1[s][np.ix_(env_idx, imp_idx)] *= 0.5
+        H1[s][np.ix_(env_idx, env_idx)] = 0.0
+    return H1
+
+
+def get_H2_scaled(H2, imp_idx, env_idx=None):
+    """slater.py:1734-1778: scale every integral by (number of impurity indices) / 4; s4 (3-d) or s1 (5-d) layout.
+    numpy arrays are scaled in place (through the device), torch CUDA tensors stay on the device."""
+    dev = get_device()
+    on_dev = isinstance(H2, torch.Tensor)
+    if H2.ndim == 3:
+        npair = H2.shape[-1]
+        nbasis = int(np.sqrt(npair * 2))
+        tri = np.tril_indices(nbasis)
+        member = np.zeros(nbasis, dtype=np.int32)
+        member[np.asarray(imp_idx, dtype=int)] = 1
+        w = dev.to_device((member[tri[0]] + member[tri[1]]).astype(np.int32), torch.int32)
+        sym = 4
+    elif H2.ndim == 5:
+        nbasis = H2.shape[-1]
+        member = np.zeros(nbasis, dtype=np.int32)
+        member[np.asarray(imp_idx, dtype=int)] = 1
+        w = dev.to_device(member, torch.int32)
+        sym = 1
+    else:
+        raise ValueError("Unknown H2 shape to scale: %s" % (str(tuple(H2.shape))))
+    d = H2 if on_dev else dev.to_device(np.ascontiguousarray(H2), torch.float64)
+    for blk in range(d.shape[0]):
+        dev.scale_eri(d[blk], nbasis, sym, w)
+    if on_dev:
+        return d
+    H2[...] = d.cpu().numpy()
+    return H2
+
+
+def get_H_dmet(basis, lattice, ImpHam, last_dmu, imp_idx=None, dmu_idx=None, add_vcor_to_E=False, vcor=None,
+               compact=True, rdm1_emb=None, veff=None, rebuild_veff=False, E1=None, **kwargs):
+    """slater.py:1957-2032: the DMET Hamiltonian scaled by the number of impurity indices, whose expectation value
+    is the fragment energy.  The branches that rebuild J/K from a global density matrix through the lattice
+    mean-field object (`veff`, `rebuild_veff`) stay with the reference."""
+    if veff is not None or rebuild_veff:
+        raise NotImplementedError("rebuilding JK_core from the global density needs the lattice mean-field object")
+    basis = np.asarray(basis)
+    spin = basis.shape[0]
+    nbasis = basis.shape[-1]
+    if imp_idx is None:
+        imp_idx = list(range(lattice.nimp))
+    imp_idx = np.asarray(imp_idx)
+    env_idx = _env_idx(nbasis, imp_idx, None)
+    dev = get_device()
+    if E1 is None:
+        bk = _BasisK(lattice.R2k_basis(basis))
+        H1_scaled = transform_h1_dev(lattice.hcore_lo_k, bk).cpu().numpy()
+        JK_core = lattice.JK_core if lattice.JK_core is not None else [0.0 for s in range(spin)]
+        for s in range(spin):
+            H1_scaled[s] += 0.5 * JK_core[s]
+            if add_vcor_to_E:
+                v = np.asarray(vcor.get()[s]) * 0.5
+                H1_scaled[s] += sum(basis[s, i].T.dot(v).dot(basis[s, i]) for i in range(basis.shape[1]))
+                H1_scaled[s] -= basis[s, 0].T.dot(v).dot(basis[s, 0])
+        H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
+        H0 = lattice.getH0()
+    else:
+        H1_scaled = (-1.0 / spin) * get_veff(rdm1_emb, ImpHam.H2["ccdd"], hyb=1.0)
+        H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
+        H0 = (E1 + lattice.getH0()).real
+    blocks = _s4_blocks_dev(ImpHam.H2["ccdd"], nbasis)                       # restore 4-fold symmetry (l.2019-2022)
+    H2_dev = torch.stack([b.clone() for b in blocks])
+    H2_dev = get_H2_scaled(H2_dev, imp_idx, env_idx)
+    if compact:
+        H2_scaled = H2_dev.cpu().numpy()
+    else:                                                                    # restore_Ham(ImpHam_dmet, 1) (l.2029-2031)
+        H2_scaled = np.stack([dev.restore_s1(H2_dev[i].contiguous(), nbasis).cpu().numpy()
+                              for i in range(H2_dev.shape[0])])
+    return Integral(nbasis, spin == 1, False, H0, {"cd": H1_scaled}, {"ccdd": H2_scaled})
+
+
+def transformResults(rhoEmb, E, basis, ImpHam, H1e=None, **kwargs):
+    """slater.py:1780-1840: impurity density, fragment energy (non-interacting-bath formula) and electron number
+    from the solver's embedding density matrix -- small host matrices."""
+    rhoEmb = np.asarray(rhoEmb)
+    basis = np.asarray(basis)
+    spin = rhoEmb.shape[0]
+    nscsites = basis.shape[2]
+    nbasis = basis.shape[-1]
+    if "lattice" in kwargs:
+        imp_idx = np.asarray(kwargs.get("imp_idx", range(kwargs["lattice"].nimp)))
+    else:
+        imp_idx = np.asarray(kwargs.get("imp_idx", np.arange(nscsites)))
+    if any(imp_idx >= nscsites):
+        warnings.warn("imp_idx is out of the first cell... imp_idx:\n%s" % imp_idx)
+    nelec = 0.0
+    for s in range(spin):
+        nelec += np.sum(rhoEmb[s, imp_idx, imp_idx])
+    nelec *= (2.0 / spin)
+    rhoImp = rhoEmb[np.ix_(range(spin), imp_idx, imp_idx)]
+    if E is not None:
+        lattice = kwargs["lattice"]
+        last_dmu = kwargs["last_dmu"]
+        imp_idx = np.asarray(kwargs.get("imp_idx", list(range(lattice.nimp))))
+        dmu_idx = kwargs.get("dmu_idx", None)
+        if dmu_idx is None:
+            dmu_idx = list(range(nscsites))
+        env_idx = _env_idx(nbasis, imp_idx, None)
+        E2 = E - np.einsum('spq,sqp', ImpHam.H1["cd"], rhoEmb) * (2.0 / spin) - ImpHam.H0
+        H1_scaled = np.array(ImpHam.H1["cd"], copy=True)
+        dmu_mat = np.zeros((nscsites, nscsites))
+        dmu_mat[dmu_idx, dmu_idx] = -last_dmu
+        for s in range(spin):
+            H1_scaled[s] -= basis[s, 0].T.dot(dmu_mat).dot(basis[s, 0])        # transform_imp
+            if lattice.JK_core is not None:
+                H1_scaled[s] -= 0.5 * lattice.JK_core[s]
+        H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
+        E1 = np.einsum('spq,sqp', H1_scaled, rhoEmb) * (2.0 / spin)
+        Efrag = E1 + E2 + lattice.getH0()
+    else:
+        Efrag = None
+    return rhoImp, Efrag, nelec

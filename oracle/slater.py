@@ -376,3 +376,121 @@ def get_emb_Ham(lattice, basis, vcor, local=True, **kwargs):
 
 
 embHam = get_emb_Ham
+
+
+# ---------------------------------------------------------------------------------------------------------
+# energy side (slater.py:1716-1840, 1957-2032)
+# ---------------------------------------------------------------------------------------------------------
+def get_H1_scaled(H1, imp_idx, env_idx=None):
+    """slater.py:1716-1732."""
+    assert H1.ndim == 3
+    nbasis = H1.shape[-1]
+    if env_idx is None:
+        env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
+    imp_env = np.ix_(imp_idx, env_idx)
+    env_imp = np.ix_(env_idx, imp_idx)
+    env_env = np.ix_(env_idx, env_idx)
+    for s in range(H1.shape[0]):
+        H1[s][imp_env] *= 0.5
+        H1[s][env_imp] *= 0.5
+        H1[s][env_env] = 0.0
+    return H1
+
+
+def get_H2_scaled(H2, imp_idx, env_idx=None):
+    """slater.py:1734-1778."""
+    if H2.ndim == 3:
+        nbasis_pair = H2.shape[-1]
+        nbasis = int(np.sqrt(nbasis_pair * 2))
+        tril_idx = np.tril_indices(nbasis)
+        mask = np.isin(tril_idx, imp_idx)
+        zero = np.logical_not(np.logical_or(*mask))
+        half = np.logical_xor(*mask)
+        one = np.logical_and(*mask)
+        mask_list = (zero, half, one)
+        for s in range(H2.shape[0]):
+            for i, mask_i in enumerate(mask_list):
+                for j, mask_j in enumerate(mask_list):
+                    if i + j == 4:
+                        continue
+                    elif i + j == 0:
+                        H2[s][np.ix_(mask_i, mask_j)] = 0.0
+                    else:
+                        H2[s][np.ix_(mask_i, mask_j)] *= ((i + j) * 0.25)
+    elif H2.ndim == 5:
+        nbasis = H2.shape[-1]
+        if env_idx is None:
+            env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
+        mask_list = (env_idx, imp_idx)
+        for s in range(H2.shape[0]):
+            for i, mi in enumerate(mask_list):
+                for j, mj in enumerate(mask_list):
+                    for k, mk in enumerate(mask_list):
+                        for l, ml in enumerate(mask_list):
+                            H2[s][np.ix_(mi, mj, mk, ml)] *= (i + j + k + l) * 0.25
+    else:
+        raise ValueError("Unknown H2 shape to scale: %s" % (str(H2.shape)))
+    return H2
+
+
+def get_H_dmet(basis, lattice, ImpHam, last_dmu, imp_idx=None, compact=True, **kwargs):
+    """slater.py:1957-2032, default branch (E1, veff not given)."""
+    spin = basis.shape[0]
+    nbasis = basis.shape[-1]
+    if imp_idx is None:
+        imp_idx = list(range(len(lattice.imp_idx)))
+    imp_idx = np.asarray(imp_idx)
+    env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
+    basis_k = lattice.R2k_basis(basis)
+    H1_scaled = transform_h1(lattice.hcore_lo_k, basis_k)
+    JK_core = lattice.JK_core if lattice.JK_core is not None else [0.0 for s in range(spin)]
+    for s in range(spin):
+        H1_scaled[s] += 0.5 * JK_core[s]
+    H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
+    H0 = lattice.getH0()
+    npair = nbasis * (nbasis + 1) // 2
+    H2_scaled = np.empty((spin * (spin + 1) // 2, npair, npair))
+    for s in range(spin * (spin + 1) // 2):
+        H2_scaled[s] = lib.restore(4, ImpHam.H2["ccdd"][s], nbasis)
+    H2_scaled = get_H2_scaled(H2_scaled, imp_idx, env_idx)
+    if not compact:
+        H2_scaled = np.stack([lib.restore(1, H2_scaled[s], nbasis) for s in range(H2_scaled.shape[0])])
+    return Integral(nbasis, spin == 1, False, H0, {"cd": H1_scaled}, {"ccdd": H2_scaled})
+
+
+def transformResults(rhoEmb, E, basis, ImpHam, H1e=None, **kwargs):
+    """slater.py:1780-1840."""
+    spin = rhoEmb.shape[0]
+    nscsites = basis.shape[2]
+    nbasis = basis.shape[-1]
+    if "lattice" in kwargs:
+        imp_idx = np.asarray(kwargs.get("imp_idx", range(len(kwargs["lattice"].imp_idx))))
+    else:
+        imp_idx = np.asarray(kwargs.get("imp_idx", np.arange(nscsites)))
+    nelec = 0.0
+    for s in range(spin):
+        nelec += np.sum(rhoEmb[s, imp_idx, imp_idx])
+    nelec *= (2.0 / spin)
+    rhoImp = rhoEmb[np.ix_(range(spin), imp_idx, imp_idx)]
+    if E is not None:
+        lattice = kwargs["lattice"]
+        last_dmu = kwargs["last_dmu"]
+        imp_idx = np.asarray(kwargs.get("imp_idx", list(range(len(lattice.imp_idx)))))
+        dmu_idx = kwargs.get("dmu_idx", None)
+        if dmu_idx is None:
+            dmu_idx = list(range(nscsites))
+        env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
+        E2 = E - np.einsum('spq,sqp', ImpHam.H1["cd"], rhoEmb) * (2.0 / spin) - ImpHam.H0
+        H1_scaled = np.array(ImpHam.H1["cd"], copy=True)
+        dmu_mat = np.zeros((nscsites, nscsites))
+        dmu_mat[dmu_idx, dmu_idx] = -last_dmu
+        for s in range(spin):
+            H1_scaled[s] -= transform_imp(basis[s], lattice, dmu_mat)
+            if lattice.JK_core is not None:
+                H1_scaled[s] -= 0.5 * lattice.JK_core[s]
+        H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
+        E1 = np.einsum('spq,sqp', H1_scaled, rhoEmb) * (2.0 / spin)
+        Efrag = E1 + E2 + lattice.getH0()
+    else:
+        Efrag = None
+    return rhoImp, Efrag, nelec

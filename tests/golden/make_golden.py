@@ -130,7 +130,19 @@ def gen_embham():
         rho = Lat.rdm1_lo_R * (0.5 if spin == 1 else 1.0)
         basis = ref_slater.get_emb_basis(Lat, rho)
         Ham, _ = ref_slater.get_emb_Ham(Lat, basis, None)
-        save(name, kmesh=np.array(kmesh), nao=nao, naux=naux, nval=nval, spin=spin, sym=sym, gdf_seed=gdf.seed,
+        # energy side: scaled DMET Hamiltonian and result transformation (slater.py:1780-1840, 1957-2032)
+        Hd = ref_slater.get_H_dmet(basis, Lat, Ham, 0.0)
+        Hd1 = ref_slater.get_H_dmet(basis, Lat, Ham, 0.0, compact=False) if sym == 1 else None
+        rng = np.random.default_rng(5)
+        nb = basis.shape[-1]
+        rho_emb = rng.standard_normal((spin, nb, nb))
+        rho_emb = rho_emb + rho_emb.transpose(0, 2, 1)
+        rhoImp, Efrag, nelec = ref_slater.transformResults(rho_emb, -3.25, basis, Ham, lattice=Lat, last_dmu=0.1)
+        extra = dict(Hd_H1=Hd.H1["cd"], Hd_H2=Hd.H2["ccdd"], Hd_H0=Hd.H0, rho_emb=rho_emb, rhoImp=rhoImp,
+                     Efrag=Efrag, nelec=nelec)
+        if Hd1 is not None:
+            extra["Hd_H2_s1"] = Hd1.H2["ccdd"]
+        save(name, **extra, kmesh=np.array(kmesh), nao=nao, naux=naux, nval=nval, spin=spin, sym=sym, gdf_seed=gdf.seed,
              gdf_scale=gdf.scale, C_ao_lo=C, hcore=hcore, ovlp=ovlp, vhf=vhf, rdm1=rdm1,
              hcore_lo_k=Lat.hcore_lo_k, rdm1_lo_k=Lat.rdm1_lo_k, rdm1_lo_R=Lat.rdm1_lo_R, vhf_lo_k=Lat.vhf_lo_k,
              rho=rho, basis=basis, H1=Ham.H1["cd"], H2=Ham.H2["ccdd"], ovlp_emb=Ham.ovlp, JK_core=Lat.JK_core,

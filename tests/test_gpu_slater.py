@@ -103,3 +103,21 @@ def test_transform_helpers(dev):
     assert np.abs(slater.get_veff(d, e) - osl.get_veff(d, e)).max() < 1e-11
     u = rng.standard_normal((3, 6, 6))
     assert np.array_equal(slater.unit2emb(u, 5), osl.unit2emb(u, 5))
+
+
+def test_h2_scaling_kernels(dev):
+    """get_H1_scaled / get_H2_scaled (slater.py:1716-1778) against the oracle for s4 and s1 layouts"""
+    from libdmet_preview_b200 import slater
+    from oracle import slater as osl, pyscf_lib as olib
+    rng = np.random.default_rng(8)
+    n, imp = 7, [0, 1, 2, 5]
+    x = rng.standard_normal((3, 28, 28))
+    a, b = x.copy(), x.copy()
+    assert np.abs(slater.get_H2_scaled(a, imp) - osl.get_H2_scaled(b, imp)).max() < 1e-15
+    y = rng.standard_normal((1, n, n, n, n))
+    a, b = y.copy(), y.copy()
+    assert np.abs(slater.get_H2_scaled(a, imp) - osl.get_H2_scaled(b, imp)).max() < 1e-15
+    h = rng.standard_normal((2, n, n))
+    assert np.array_equal(slater.get_H1_scaled(h.copy(), imp), osl.get_H1_scaled(h.copy(), imp))
+    with pytest.raises(ValueError):
+        slater.get_H2_scaled(rng.standard_normal((4, 4)), imp)
