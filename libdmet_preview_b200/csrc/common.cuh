@@ -88,7 +88,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col)   (SASS: DMMA.8x8x4)
 //   lane = 4*g + t :  a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    // volatile: keeps the MMAs in program order with the (volatile) fragment loads and barrier operations
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }

@@ -111,7 +111,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t sub = (uint32_t)((t & 1) * 8);
     const uint32_t ch = (uint32_t)(t >> 1);     // chunk of k = 4*kk + t is 2*kk + (t>>1)
 
-    int stage = 0;
+    // A stage is handed back to the producer one iteration late, right after the wait for the NEXT stage: the
+    // wait loop is a control-flow boundary behind all MMAs of the previous stage, so every fragment load of that
+    // stage has returned its data (the MMAs that consume them have issued) before TMA may overwrite the buffer.
+    // Releasing directly after the last fragment loads is not safe: the arrive does not wait for LDS in flight.
+    int stage = 0, prev_stage = -1;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int tm, tn;
@@ -124,6 +128,10 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
         for (int kt = 0; kt < ktiles; ++kt) {
             mbar_wait(bar_base + 8 * stage, phase);
+            if (prev_stage >= 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8 * (T::STAGES + prev_stage));
+            }
             const uint32_t sbase = smem_base + stage * T::STAGE_BYTES;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -138,8 +146,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int i = 0; i < T::FA; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_base + 8 * (T::STAGES + stage));
+            prev_stage = stage;
             if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
 
@@ -151,6 +158,17 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int r = tm * T::BM + wm * T::FA * 8 + i * 8 + pg;
             if (r >= args.M) continue;
             double* crow = args.C + (long long)r * args.ldc;
+            // accumulate mode: all old values of the row first (16 independent loads), then the stores
+            double old[T::FB][2];
+            if (args.accumulate) {
+#pragma unroll
+                for (int j = 0; j < T::FB; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = tn * T::BN + wn * T::FB * 8 + j * 8 + (e ? pc1 : pc0);
+                        old[j][e] = c < args.N ? crow[c] : 0.0;
+                    }
+            }
 #pragma unroll
             for (int j = 0; j < T::FB; ++j) {
                 const int cbase = tn * T::BN + wn * T::FB * 8 + j * 8;
@@ -159,7 +177,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int c = cbase + (e ? pc1 : pc0);
                     if (c >= args.N) continue;
                     double v = args.alpha * acc[i][j][e];
-                    if (args.accumulate) v += crow[c];
+                    if (args.accumulate) v += old[j][e];
                     crow[c] = v;
                 }
             }

@@ -126,7 +126,11 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t a_c0 = (uint32_t)((t ^ pg) * 16);       // k-step 0 ; k-step 1 is a_c0 ^ 64
     const uint32_t b_off = (uint32_t)(T::A_BYTES + (wn * FB * 8 + g) * 64 + t * 16);
 
-    int stage = 0;
+    // A stage is handed back to the producer one iteration late, right after the wait for the NEXT stage: the
+    // wait loop is a control-flow boundary behind all MMAs of the previous stage, so every fragment load of that
+    // stage has returned its data (the MMAs that consume them have issued) before TMA may overwrite the buffer.
+    // Releasing directly after the last fragment loads is not safe: the arrive does not wait for LDS in flight.
+    int stage = 0, prev_stage = -1;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_batch;
@@ -149,6 +153,10 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t mB = segs[s].conjB;
             for (int kt = 0; kt < ktiles; ++kt) {
                 mbar_wait(bar_base + 8 * stage, phase);
+                if (prev_stage >= 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_base + 8 * (T::STAGES + prev_stage));
+                }
                 const uint32_t sbase = smem_base + stage * T::STAGE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
@@ -177,34 +185,52 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_base + 8 * (T::STAGES + stage));
+                prev_stage = stage;
                 if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
             }
         }
 
         // ---------------- epilogue: registers -> global ----------------
+        // accumulate mode reads the old values of a whole chunk first (independent loads in flight together) and
+        // only then stores: a load/store chain per element would expose one DRAM round trip per element.
         double2* Cb = args.C + (args.c_off ? args.c_off[b] : 0ll);
         const double alpha = args.alpha;
+        constexpr int JB = FB > 23 ? 1 : (FB > 20 ? 2 : 4);   // the widest tiles have no registers to spare
+        constexpr bool kBatch = FB <= 23;
 #pragma unroll
         for (int i = 0; i < FA; ++i) {
             const int r = tm * T::BM + wm * FA * 8 + i * 8 + pg;
             if (r >= args.M) continue;
             const long long roff = (long long)(r / args.rdiv) * args.s_outer + (long long)(r % args.rdiv) * args.s_inner;
 #pragma unroll
-            for (int j = 0; j < FB; ++j) {
-                const int c = tn * T::BN + wn * FB * 8 + j * 8 + 2 * t;
+            for (int j0 = 0; j0 < FB; j0 += JB) {
+                double2 old[JB][2];
+                if (kBatch && args.accumulate) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    if (c + e >= args.N) continue;
-                    double2* p = Cb + roff + (long long)(c + e) * args.s_col;
-                    double2 v = make_double2(alpha * cr[i][j][e], alpha * ci[i][j][e]);
-                    if (args.accumulate) {
-                        const double2 o = *p;
-                        v.x += o.x;
-                        v.y += o.y;
+                    for (int jj = 0; jj < JB; ++jj)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = tn * T::BN + wn * FB * 8 + (j0 + jj) * 8 + 2 * t + e;
+                            old[jj][e] = (j0 + jj < FB && c < args.N) ? Cb[roff + (long long)c * args.s_col]
+                                                                      : make_double2(0.0, 0.0);
+                        }
+                }
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    if (j0 + jj >= FB) continue;
+                    const int j = j0 + jj;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = tn * T::BN + wn * FB * 8 + j * 8 + 2 * t + e;
+                        if (c >= args.N) continue;
+                        double2 v = make_double2(alpha * cr[i][j][e], alpha * ci[i][j][e]);
+                        if (args.accumulate) {
+                            const double2 o = kBatch ? old[jj][e] : Cb[roff + (long long)c * args.s_col];
+                            v.x += o.x;
+                            v.y += o.y;
+                        }
+                        Cb[roff + (long long)c * args.s_col] = v;
                     }
-                    *p = v;
                 }
             }
         }

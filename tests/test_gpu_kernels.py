@@ -135,3 +135,36 @@ def test_error_reporting(dev):
         dev.zgemm_tn(A, A, [[5, 0, 0, 0]], dev.empty((4, 4), torch.complex128))     # slice out of range
     with pytest.raises(LdmError):
         dev.dgemm_tn(dev.empty((4, 3)), dev.empty((4, 3)), dev.empty((4, 4)))       # odd leading dimension
+
+
+def test_gemm_pipeline_many_tiles_per_cta(dev):
+    """Regression for the shared-memory stage hand-over: with many tiles per persistent CTA the consumers used to
+    release a stage while its last fragment loads were still in flight (random rows of a tile corrupted, run to run).
+    Sizes give ~12 (dgemm) and ~20 (zgemm) tiles per CTA; results must be exact and repeatable."""
+    rng = np.random.default_rng(11)
+    M, K = 5500, 1000
+    X = rng.standard_normal((M, K))
+    ref = 2.0 * (X @ X.T)
+    Xd = dev.to_device(X, torch.float64)
+    tm = np.arange(M) // 128
+    mask = tm[:, None] >= tm[None, :]
+    first = None
+    for rep in range(3):
+        E = dev.zeros((M, M))
+        dev.dgemm_tn(Xd, Xd, E, alpha=2.0, accumulate=True, lower_only=True)
+        got = E.cpu().numpy()
+        assert np.abs((got - ref) * mask).max() < 1e-9
+        first = got if first is None else first
+        assert np.array_equal(got, first)
+    A = _z(rng, 1, 200000, 64)
+    B = _z(rng, 1, 150, 64)
+    Ad, Bd = dev.to_device(A, torch.complex128), dev.to_device(B, torch.complex128)
+    refz = A[0] @ B[0].T
+    first = None
+    for rep in range(3):
+        C = dev.zeros((200000, 150), torch.complex128)
+        dev.zgemm_tn(Ad, Bd, [[0, 0, 0, 0]], C, accumulate=True)
+        got = C.cpu().numpy()
+        assert np.abs(got - refz).max() < 1e-10
+        first = got if first is None else first
+        assert np.array_equal(got, first)
