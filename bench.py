@@ -401,7 +401,7 @@ def run_ours(args):
         return
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:       # reported at N=1 only (rank 0's host cores are otherwise shared)
         c = cpu_sample(kmesh, nao, naux, neo)
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         cpu = {"value": c["tflops"], "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": c["sample"],
