@@ -4,8 +4,6 @@ extract_stripe, orbital partition, and `set_Ham` from explicit mean-field matric
 the seven k2R transforms running on the GPU.  A real libdmet `Lattice` works with `slater.embHam` as well -- only
 attributes are read.
 """
-import itertools as it
-
 import numpy as np
 
 from . import fourier, make_basis
@@ -102,103 +100,87 @@ class Lattice(object):
 
     # ---- stripe <-> full (lattice.py:304-351) ----
     def expand(self, A, dense=False):
+        """stripe ((spin,) ncells, n, n) -> full translation-invariant matrix: block (i + j, j) = A[i]; all-zero
+        stripes are skipped unless `dense` (same result, the reference's shortcut)"""
         assert A.shape[-3] == self.ncells
-        nsc = A.shape[-1]
-        nsites = nsc * self.ncells
-        lead = A.shape[:-3]
-        A4 = A.reshape((-1, self.ncells, nsc, nsc))
-        big = np.zeros((A4.shape[0], nsites, nsites), dtype=A.dtype)
-        if dense:
-            rows = range(self.ncells)
-        else:
-            rows = [i for i in range(self.ncells) if not np.allclose(A4[:, i], 0.0)]
-        for i, j in it.product(rows, range(self.ncells)):
-            idx = self.add(i, j)
-            big[:, idx * nsc:(idx + 1) * nsc, j * nsc:(j + 1) * nsc] = A4[:, i]
-        return big.reshape(lead + (nsites, nsites))
+        n = A.shape[-1]
+        stripes = A.reshape((-1, self.ncells, n, n))
+        full = np.zeros((stripes.shape[0], self.ncells * n, self.ncells * n), dtype=A.dtype)
+        target = np.asarray([[self.add(i, j) for j in range(self.ncells)] for i in range(self.ncells)])
+        for i in range(self.ncells):
+            if not dense and np.allclose(stripes[:, i], 0.0):
+                continue
+            for j in range(self.ncells):
+                r = target[i, j]
+                full[:, r * n:(r + 1) * n, j * n:(j + 1) * n] = stripes[:, i]
+        return full.reshape(A.shape[:-3] + full.shape[1:])
 
     def extract_stripe(self, A):
-        ncells = self.ncells
-        nsc = A.shape[-1] // ncells
-        if A.ndim == 2:
-            return A.reshape((ncells, nsc, ncells, nsc))[:, :, 0]
-        elif A.ndim == 3:
-            return A.reshape((A.shape[0], ncells, nsc, ncells, nsc))[:, :, :, 0]
-        raise ValueError("unknown shape of A, %s" % (A.shape,))
+        """first block column of a full matrix"""
+        if A.ndim not in (2, 3):
+            raise ValueError("unknown shape of A, %s" % (A.shape,))
+        n = A.shape[-1] // self.ncells
+        return A.reshape(A.shape[:-2] + (self.ncells, n, self.ncells, n))[..., :, :, 0, :]
 
     # ---- Hamiltonian (lattice.py:416-515, 591-673) ----
+    _H1_NAMES = ("hcore", "fock", "fock_hf", "veff", "vhf")      # transformed with C^dagger . C and given a spin axis
+
     def set_Ham(self, kmf, df, C_ao_lo, eri_symmetry=4, ovlp=None, hcore=None, rdm1=None, fock=None, veff=None,
                 vhf=None, vj=None, vk=None, vxc=None, use_hcore_as_emb_ham=False, H0=0.0, hcore_hf_add=None):
-        """Same argument list as the reference.  Without PySCF `kmf` is None and ovlp, hcore, rdm1 and vhf (or
-        vj and vk: vhf = vj - vk/2 restricted, vj[0]+vj[1]-vk unrestricted) must be given as
+        """Same argument list as the reference.  Without PySCF pass kmf=None together with ovlp, hcore, rdm1 and
+        vhf (or vj and vk: vhf = vj - vk/2 restricted, vj[0] + vj[1] - vk unrestricted) as
         ((spin,) nkpts, nao, nao) arrays."""
-        self.kmf = kmf
-        self.df = df
+        self.kmf, self.df = kmf, df
         self.C_ao_lo = np.asarray(C_ao_lo)
-        if kmf is not None:
+        if kmf is not None:                               # pull what was not supplied from the mean-field object
             ovlp = kmf.get_ovlp() if ovlp is None else ovlp
             hcore = kmf.get_hcore() if hcore is None else hcore
             rdm1 = kmf.make_rdm1() if rdm1 is None else rdm1
-            if (vj is None or vk is None) and vhf is None:
+            if vhf is None and (vj is None or vk is None):
                 vj, vk = kmf.get_jk(dm_kpts=rdm1)
-        if ovlp is None or hcore is None or rdm1 is None:
-            raise ValueError("set_Ham: ovlp, hcore and rdm1 are required when no mean-field object is given")
-        ovlp, hcore, rdm1 = np.asarray(ovlp), np.asarray(hcore), np.asarray(rdm1)
+        missing = [n for n, v in (("ovlp", ovlp), ("hcore", hcore), ("rdm1", rdm1)) if v is None]
+        if missing:
+            raise ValueError("set_Ham: %s required when no mean-field object is given" % ", ".join(missing))
         if vhf is None:
             if vj is None or vk is None:
                 raise ValueError("set_Ham: vhf (or vj and vk) is required when no mean-field object is given")
             vj, vk = np.asarray(vj), np.asarray(vk)
-            vhf = vj - vk * 0.5 if vk.ndim == 3 else vj[0] + vj[1] - vk      # pbc_helper.get_veff, HF
-        vhf = np.asarray(vhf)
-        if veff is None:
-            veff = vhf
-        if fock is None:
-            fock = hcore + veff
-        fock_hf = hcore + vhf
-        if hcore_hf_add is not None:
-            fock_hf = fock_hf + hcore_hf_add
-        self.ovlp_ao_k, self.hcore_ao_k, self.rdm1_ao_k = ovlp, hcore, rdm1
-        self.fock_ao_k, self.fock_hf_ao_k = np.asarray(fock), np.asarray(fock_hf)
+            vhf = vj - 0.5 * vk if vk.ndim == 3 else vj[0] + vj[1] - vk
+        self.ovlp_ao_k, self.hcore_ao_k, self.rdm1_ao_k = (np.asarray(x) for x in (ovlp, hcore, rdm1))
+        self.vhf_ao_k = np.asarray(vhf)
+        self.veff_ao_k = self.vhf_ao_k if veff is None else np.asarray(veff)
+        self.fock_ao_k = self.hcore_ao_k + self.veff_ao_k if fock is None else np.asarray(fock)
+        self.fock_hf_ao_k = self.hcore_ao_k + self.vhf_ao_k
         self.hcore_hf_add = hcore_hf_add
-        self.veff_ao_k, self.vhf_ao_k = np.asarray(veff), vhf
+        if hcore_hf_add is not None:
+            self.fock_hf_ao_k = self.fock_hf_ao_k + hcore_hf_add
         if vxc is not None:
             self.vxc_ao_k = np.asarray(vxc)
-        if self.C_ao_lo.ndim == 3:
-            self.spin, self.restricted = 1, True
-        else:
-            self.spin = self.C_ao_lo.shape[0]
-            self.restricted = (self.spin == 1)
+        self.spin = 1 if self.C_ao_lo.ndim == 3 else self.C_ao_lo.shape[0]
+        self.restricted = (self.spin == 1)
+        if eri_symmetry not in (1, 4, 8) or (eri_symmetry == 8 and not self.restricted):
+            raise AssertionError("eri_symmetry must be 1, 4 or (restricted only) 8")
         self.eri_symmetry = eri_symmetry
-        assert self.eri_symmetry in [1, 4, 8]
-        if not self.restricted:
-            assert self.eri_symmetry != 8
         self.transform_obj_to_lo()
         self.H0 = H0
         self.has_Ham = True
         self.use_hcore_as_emb_ham = use_hcore_as_emb_ham
 
     def transform_obj_to_lo(self):
-        """lattice.py:591-673 (non-GHF): six transform_h1_to_lo + transform_rdm1_to_lo, then seven k2R."""
+        """AO -> LO for hcore, ovlp, fock, fock_hf, veff, vhf (C^dagger h C) and rdm1 (C^-1 D C^-dagger), then the
+        seven k -> R transforms; all on the device (lattice.py:591-673, non-GHF)."""
         C = self.C_ao_lo
         if C.shape[-2] != self.hcore_ao_k.shape[-1]:
             raise NotImplementedError("generalised (GHF) coefficient layout is outside the hot path")
-        t = make_basis.transform_h1_to_lo
-        self.hcore_lo_k = add_spin_dim(t(self.hcore_ao_k, C), self.spin)
-        self.ovlp_lo_k = t(self.ovlp_ao_k, C)
-        self.fock_lo_k = add_spin_dim(t(self.fock_ao_k, C), self.spin)
-        self.fock_hf_lo_k = add_spin_dim(t(self.fock_hf_ao_k, C), self.spin)
-        self.veff_lo_k = add_spin_dim(t(self.veff_ao_k, C), self.spin)
-        self.vhf_lo_k = add_spin_dim(t(self.vhf_ao_k, C), self.spin)
+        for name in self._H1_NAMES:
+            lo_k = make_basis.transform_h1_to_lo(getattr(self, name + "_ao_k"), C)
+            setattr(self, name + "_lo_k", add_spin_dim(lo_k, self.spin))
+        self.ovlp_lo_k = make_basis.transform_h1_to_lo(self.ovlp_ao_k, C)
         self.rdm1_lo_k = add_spin_dim(make_basis.transform_rdm1_to_lo(self.rdm1_ao_k, C, self.ovlp_ao_k), self.spin)
-        self.hcore_lo_R = self.k2R(self.hcore_lo_k)
-        self.ovlp_lo_R = self.k2R(self.ovlp_lo_k)
-        self.fock_lo_R = self.k2R(self.fock_lo_k)
-        self.fock_hf_lo_R = self.k2R(self.fock_hf_lo_k)
-        self.veff_lo_R = self.k2R(self.veff_lo_k)
-        self.vhf_lo_R = self.k2R(self.vhf_lo_k)
-        self.rdm1_lo_R = self.k2R(self.rdm1_lo_k)
+        for name in self._H1_NAMES + ("ovlp", "rdm1"):
+            setattr(self, name + "_lo_R", self.k2R(getattr(self, name + "_lo_k")))
         if self.vxc_ao_k is not None:
-            self.vxc_lo_k = add_spin_dim(t(self.vxc_ao_k, C), self.spin)
+            self.vxc_lo_k = add_spin_dim(make_basis.transform_h1_to_lo(self.vxc_ao_k, C), self.spin)
             self.vxc_lo_R = self.k2R(self.vxc_lo_k)
 
     def update_lo(self, C_ao_lo):

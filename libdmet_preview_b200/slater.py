@@ -58,55 +58,54 @@ embBasis = get_emb_basis
 
 
 def _get_emb_basis_svd(lattice, rdm1, **kwargs):
-    """slater.py:117-220: bath = left singular vectors of rdm1[env, imp]."""
-    imp_idx = list(kwargs.get("imp_idx", lattice.imp_idx))
-    val_idx = list(kwargs.get("val_idx", lattice.val_idx))
-    valence_bath = kwargs.get("valence_bath", True)
-    orth = kwargs.get("orth", True)
-    tol_bath = kwargs.get("tol_bath", 1e-9)
-    nbath = kwargs.get("nbath", None)
-    if kwargs.get("localize_bath", None) is not None:
+    """slater.py:117-220.  The bath orbitals are the left singular vectors of the (environment x bath-generating
+    impurity orbitals) block of the density matrix with singular value >= tol_bath (or the first `nbath`).  With a
+    valence bath only the valence orbitals generate bath states; rows of the bath on the virtual impurity orbitals
+    are then zeroed and the bath is Loewdin re-orthonormalised (`orth`).  Result: (spin, ncells, nlo, nimp + nbath),
+    identity on the impurity rows, bath on the environment rows."""
+    opt = dict(imp_idx=lattice.imp_idx, val_idx=lattice.val_idx, valence_bath=True, orth=True, tol_bath=1e-9,
+               nbath=None, localize_bath=None)
+    opt.update({k: v for k, v in kwargs.items() if k in opt})
+    if opt["localize_bath"] is not None:
         raise NotImplementedError("bath localisation is only defined for model Hamiltonians in the reference")
-
+    imp_idx, val_idx = list(opt["imp_idx"]), list(opt["val_idx"])
     ncells, nlo = int(lattice.ncells), int(lattice.nscsites)
-    imp_idx_bath = val_idx if valence_bath else imp_idx
-    in_bath = np.zeros(ncells * nlo, dtype=bool)
-    in_bath[imp_idx_bath] = True
-    in_imp = np.zeros(ncells * nlo, dtype=bool)
-    in_imp[imp_idx] = True
-    env_idx = np.where(~in_bath)[0]
-    virt_mask = in_imp[env_idx]
+    ntot = ncells * nlo
+    gen_idx = val_idx if opt["valence_bath"] else imp_idx        # orbitals whose entanglement defines the bath
+    is_gen = np.zeros(ntot, dtype=bool)
+    is_gen[gen_idx] = True
+    is_imp = np.zeros(ntot, dtype=bool)
+    is_imp[imp_idx] = True
+    env_idx = np.flatnonzero(~is_gen)
     nimp = len(imp_idx)
 
     rdm1 = np.asarray(rdm1)
-    if rdm1.ndim == 3:
-        rdm1 = rdm1[np.newaxis]
+    rdm1 = rdm1[None] if rdm1.ndim == 3 else rdm1
     assert rdm1.shape[-3:] == (ncells, nlo, nlo)
     spin = rdm1.shape[0]
-
-    if np.max(imp_idx_bath) >= nlo - 1:      # (sic) l.167: also taken for the last orbital of cell 0
-        rdm1_env_imp = lattice.expand(rdm1)[:, env_idx][:, :, imp_idx_bath]
-        nbath_final = len(imp_idx_bath)
+    # the reference takes the expanded-matrix route as soon as the LAST orbital of cell 0 generates bath states
+    # (">= nlo - 1", slater.py:167); the route only changes the cap on the number of bath orbitals
+    if max(gen_idx) >= nlo - 1:
+        coupling = lattice.expand(rdm1)[:, env_idx][:, :, gen_idx]
+        nbath_cap = len(gen_idx)
     else:
-        rdm1_env_imp = rdm1.reshape(spin, ncells * nlo, nlo)[:, env_idx][:, :, imp_idx_bath]
-        nbath_final = nlo
-    basis = np.zeros((spin, ncells * nlo, nimp * 2))
+        coupling = rdm1.reshape(spin, ntot, nlo)[:, env_idx][:, :, gen_idx]
+        nbath_cap = nlo
 
+    basis = np.zeros((spin, ntot, 2 * nimp))
     for s in range(spin):
-        u, sigma, vt = la.svd(rdm1_env_imp[s], full_matrices=False)
-        nbath_s = int((sigma >= tol_bath).sum()) if nbath is None else nbath
-        B = u[:, :nbath_s]
-        if np.sum(np.abs(sigma[:nbath_s]) < tol_bath) > 0:
+        u, sigma, _ = la.svd(coupling[s], full_matrices=False)          # host LAPACK, as in the reference
+        nb = int(np.count_nonzero(sigma >= opt["tol_bath"])) if opt["nbath"] is None else int(opt["nbath"])
+        if np.any(np.abs(sigma[:nb]) < opt["tol_bath"]):
             warnings.warn("Zero singular value exists, \nthis may cause numerical instability.")
-        if nbath_s > 0 and orth:
-            B[virt_mask] = 0.0
-            B = vec_lowdin(B)
+        bath = u[:, :nb]
+        if nb > 0 and opt["orth"]:
+            bath[is_imp[env_idx]] = 0.0
+            bath = vec_lowdin(bath)
         basis[s, imp_idx, :nimp] = np.eye(nimp)
-        basis[s, env_idx, nimp:nimp + nbath_s] = B
-        nbath_final = min(nbath_final, nbath_s)
-
-    basis = basis[:, :, :nimp + nbath_final].reshape(spin, ncells, nlo, nimp + nbath_final)
-    return basis
+        basis[s, env_idx, nimp:nimp + nb] = bath
+        nbath_cap = min(nbath_cap, nb)
+    return basis[:, :, :nimp + nbath_cap].reshape(spin, ncells, nlo, nimp + nbath_cap)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -241,19 +240,15 @@ def get_veff(rdm1, eri, hyb=1.0):
 
 
 def unit2emb(H2_unit, neo):
-    """slater_helper.py:494-517 (ndarray branch): zero-pad the impurity-block ERI to the embedding space."""
+    """slater_helper.py:494-517 (ndarray branch): the impurity-cell ERI zero-padded to `neo` embedding orbitals in
+    the same s1 / s4 / s8 layout."""
     H2_unit = np.asarray(H2_unit)
-    spin_pair = H2_unit.shape[0]
     npair = neo * (neo + 1) // 2
-    if H2_unit.ndim == 5:
-        H2_emb = np.zeros((spin_pair, neo, neo, neo, neo))
-    elif H2_unit.ndim == 3:
-        H2_emb = np.zeros((spin_pair, npair, npair))
-    elif H2_unit.ndim == 2:
-        H2_emb = np.zeros((spin_pair, npair * (npair + 1) // 2))
-    else:
+    tail = {5: (neo,) * 4, 3: (npair, npair), 2: (npair * (npair + 1) // 2,)}.get(H2_unit.ndim)
+    if tail is None:
         raise ValueError
-    H2_emb[tuple(map(slice, H2_unit.shape))] = H2_unit
+    H2_emb = np.zeros((H2_unit.shape[0],) + tail)
+    H2_emb[tuple(slice(0, n) for n in H2_unit.shape)] = H2_unit
     return H2_emb
 
 
@@ -364,21 +359,17 @@ embHam = get_emb_Ham
 # ---------------------------------------------------------------------------------------------------------
 def _env_idx(nbasis, imp_idx, env_idx):
     if env_idx is None:
-        imp = set(int(i) for i in imp_idx)
-        env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp], dtype=int)
+        env_idx = np.setdiff1d(np.arange(nbasis), np.asarray(imp_idx, dtype=int))
     return np.asarray(env_idx, dtype=int)
 
 
 def get_H1_scaled(H1, imp_idx, env_idx=None):
-    """slater.py:1716-1732 (in place): imp-env blocks halved, env-env block zeroed."""
+    """slater.py:1716-1732 (in place): every element is weighted by (number of impurity indices) / 2 --
+    impurity-environment blocks halved, environment-environment block zeroed."""
     assert H1.ndim == 3
-    nbasis = H1.shape[-1]
-    imp_idx = np.asarray(imp_idx, dtype=int)
-    env_idx = _env_idx(nbasis, imp_idx, env_idx)
-    for s in range(H1.shape[0]):
-        H1[s][np.ix_(imp_idx, env_idx)] *= 0.5
-        H1[s][np.ix_(env_idx, imp_idx)] *= 0.5
-        H1[s][np.ix_(env_idx, env_idx)] = 0.0
+    member = np.zeros(H1.shape[-1])
+    member[np.asarray(imp_idx, dtype=int)] = 1.0
+    H1 *= 0.5 * (member[:, None] + member[None, :])
     return H1
 
 
@@ -455,43 +446,32 @@ def get_H_dmet(basis, lattice, ImpHam, last_dmu, imp_idx=None, dmu_idx=None, add
 
 
 def transformResults(rhoEmb, E, basis, ImpHam, H1e=None, **kwargs):
-    """slater.py:1780-1840: impurity density, fragment energy (non-interacting-bath formula) and electron number
-    from the solver's embedding density matrix -- small host matrices."""
-    rhoEmb = np.asarray(rhoEmb)
-    basis = np.asarray(basis)
-    spin = rhoEmb.shape[0]
-    nscsites = basis.shape[2]
-    nbasis = basis.shape[-1]
-    if "lattice" in kwargs:
-        imp_idx = np.asarray(kwargs.get("imp_idx", range(kwargs["lattice"].nimp)))
-    else:
-        imp_idx = np.asarray(kwargs.get("imp_idx", np.arange(nscsites)))
-    if any(imp_idx >= nscsites):
+    """slater.py:1780-1840: impurity block of the solver's density matrix, fragment energy and electron number
+    (small host matrices).  The two-body part of the solver energy, E2 = E - <H1> - H0, is kept; the one-body part is
+    re-evaluated with the chemical-potential shift and half of JK_core removed and the impurity weights applied."""
+    rhoEmb, basis = np.asarray(rhoEmb), np.asarray(basis)
+    spin, nscsites, nbasis = rhoEmb.shape[0], basis.shape[2], basis.shape[-1]
+    lattice = kwargs.get("lattice", None)
+    default_imp = range(lattice.nimp) if lattice is not None else np.arange(nscsites)
+    imp_idx = np.asarray(kwargs.get("imp_idx", default_imp))
+    if np.any(imp_idx >= nscsites):
         warnings.warn("imp_idx is out of the first cell... imp_idx:\n%s" % imp_idx)
-    nelec = 0.0
+    per_spin = 2.0 / spin
+    nelec = per_spin * float(sum(rhoEmb[s, imp_idx, imp_idx].sum() for s in range(spin)))
+    rhoImp = rhoEmb[:, imp_idx][:, :, imp_idx]
+    if E is None:
+        return rhoImp, None, nelec
+    dmu_idx = kwargs.get("dmu_idx", None)
+    dmu_idx = list(range(nscsites)) if dmu_idx is None else dmu_idx
+    H1 = ImpHam.H1["cd"]
+    E2 = E - per_spin * np.einsum("spq,sqp", H1, rhoEmb) - ImpHam.H0
+    shift = np.zeros((nscsites, nscsites))
+    shift[dmu_idx, dmu_idx] = -kwargs["last_dmu"]
+    H1_scaled = np.array(H1, copy=True)
     for s in range(spin):
-        nelec += np.sum(rhoEmb[s, imp_idx, imp_idx])
-    nelec *= (2.0 / spin)
-    rhoImp = rhoEmb[np.ix_(range(spin), imp_idx, imp_idx)]
-    if E is not None:
-        lattice = kwargs["lattice"]
-        last_dmu = kwargs["last_dmu"]
-        imp_idx = np.asarray(kwargs.get("imp_idx", list(range(lattice.nimp))))
-        dmu_idx = kwargs.get("dmu_idx", None)
-        if dmu_idx is None:
-            dmu_idx = list(range(nscsites))
-        env_idx = _env_idx(nbasis, imp_idx, None)
-        E2 = E - np.einsum('spq,sqp', ImpHam.H1["cd"], rhoEmb) * (2.0 / spin) - ImpHam.H0
-        H1_scaled = np.array(ImpHam.H1["cd"], copy=True)
-        dmu_mat = np.zeros((nscsites, nscsites))
-        dmu_mat[dmu_idx, dmu_idx] = -last_dmu
-        for s in range(spin):
-            H1_scaled[s] -= basis[s, 0].T.dot(dmu_mat).dot(basis[s, 0])        # transform_imp
-            if lattice.JK_core is not None:
-                H1_scaled[s] -= 0.5 * lattice.JK_core[s]
-        H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
-        E1 = np.einsum('spq,sqp', H1_scaled, rhoEmb) * (2.0 / spin)
-        Efrag = E1 + E2 + lattice.getH0()
-    else:
-        Efrag = None
-    return rhoImp, Efrag, nelec
+        H1_scaled[s] -= basis[s, 0].T.dot(shift).dot(basis[s, 0])          # chemical potential acts on cell 0
+        if lattice.JK_core is not None:
+            H1_scaled[s] -= 0.5 * lattice.JK_core[s]
+    H1_scaled = get_H1_scaled(H1_scaled, imp_idx)
+    E1 = per_spin * np.einsum("spq,sqp", H1_scaled, rhoEmb)
+    return rhoImp, E1 + E2 + lattice.getH0(), nelec

@@ -1,6 +1,11 @@
-"""Oracle: lattice Fourier transforms and k-point helpers.  Restates libdmet/system/fourier.py:39-177 and
-libdmet/system/lattice.py:44-56,304-351.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py)."""
-import itertools as it
+"""Oracle: lattice Fourier transforms and k-point helpers.
+
+Behaviour restated from libdmet/system/fourier.py:39-65 (cell vectors, fftfreq-ordered scaled k-points,
+round_to_FBZ), :73-81 (kpt_member), :112-121 (R2k phase), :129-177 (R2k / k2R / FFTtoK / FFTtoT: scipy fftn / ifftn
+over the mesh axes, no normalisation R->k, 1/Nk k->R, k2R keeps the real part) and from libdmet/system/lattice.py:
+44-56 (cell grid, phases), 192-207 (cell index arithmetic), 304-351 (expand / extract_stripe), 399-411.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""
 import numpy as np
 from scipy import fft as scifft
 
@@ -11,120 +16,109 @@ IMAG_DISCARD_TOL = 1e-7  # libdmet/settings.py:4
 
 
 def max_abs(x):
-    """libdmet/utils/misc.py:34-41."""
+    """largest magnitude of an array (libdmet/utils/misc.py:34-41)"""
     x = np.asarray(x)
-    if x.size == 0:
-        return 0.0
-    if np.iscomplexobj(x):
-        return np.abs(x).max()
-    return max(np.max(x), abs(np.min(x)))
+    return float(np.abs(x).max()) if x.size else 0.0
 
 
 def get_R_vec_rel(kmesh):
-    """Integer cell positions, C order (fourier.py:39-44 before the multiplication by lattice vectors)."""
-    return lib.cartesian_prod([np.arange(x) for x in kmesh])
+    """integer cell positions in C order (fourier.py:39-44 before multiplying by the lattice vectors)"""
+    return lib.cartesian_prod([np.arange(n) for n in kmesh])
 
 
 def make_kpts_scaled(kmesh):
-    """fourier.py:46-53."""
-    ks_each_axis = [scifft.fftfreq(kmesh[d], 1.0) for d in range(len(kmesh))]
-    return lib.cartesian_prod(ks_each_axis)
+    """scaled k-points in numpy.fft order (fourier.py:46-53)"""
+    return lib.cartesian_prod([scifft.fftfreq(int(n), 1.0) for n in kmesh])
 
 
 def round_to_FBZ(kpts, tol=1e-10, wrap_around=True):
-    """fourier.py:55-65."""
-    kpts_round = kpts - np.floor(kpts)
+    """fold fractional k-points into [-0.5, 0.5) (or [0, 1) without wrap-around)   (fourier.py:55-65)"""
+    folded = np.asarray(kpts, dtype=float) - np.floor(kpts)
     if wrap_around:
-        kpts_round[kpts_round > (0.5 - tol)] -= 1.0
-    else:
-        kpts_round[kpts_round > (1.0 - tol)] = 0.0
-    return kpts_round
+        return np.where(folded > 0.5 - tol, folded - 1.0, folded)
+    return np.where(folded > 1.0 - tol, 0.0, folded)
 
 
 def kpt_member(kpt, kpts, tol=KPT_DIFF_TOL):
-    """fourier.py:73-81."""
-    kpts = np.reshape(kpts, (len(kpts), kpt.size))
-    dk = kpts - kpt.ravel()
-    dk = np.linalg.norm(dk - np.round(dk), axis=-1)
-    return np.where(dk < tol)[0]
+    """indices of kpts equal to kpt modulo reciprocal lattice vectors (fourier.py:73-81)"""
+    delta = np.asarray(kpts).reshape(len(kpts), -1) - np.ravel(kpt)
+    dist = np.linalg.norm(delta - np.round(delta), axis=1)
+    return np.flatnonzero(dist < tol)
 
 
 def get_phase_R2k_scaled(kmesh, kpts_scaled):
-    """exp(-i R.k), shape (ncells, nkpts) (fourier.py:112-121) written with scaled k-points and integer cell
-    vectors: R_abs . k_abs = 2 pi R_rel . k_scaled."""
-    R_rel = get_R_vec_rel(kmesh)
-    return np.exp(-2.0j * np.pi * np.einsum("Ru,ku->Rk", R_rel, np.asarray(kpts_scaled)))
+    """exp(-i R.k), shape (ncells, nkpts) (fourier.py:112-121); R.k = 2 pi R_rel . k_scaled"""
+    return np.exp(-2.0j * np.pi * np.dot(get_R_vec_rel(kmesh), np.asarray(kpts_scaled).T))
+
+
+def _mesh_view(A, kmesh):
+    return A.reshape(tuple(kmesh) + A.shape[-2:]), tuple(range(len(kmesh)))
 
 
 def FFTtoK(A, kmesh):
-    """fourier.py:160-166."""
-    return scifft.fftn(A.reshape(tuple(kmesh) + A.shape[-2:]),
-                       axes=range(len(kmesh)), workers=-1).reshape(A.shape)
+    """cells -> k-points, unnormalised (fourier.py:160-166)"""
+    view, axes = _mesh_view(A, kmesh)
+    return scifft.fftn(view, axes=axes).reshape(A.shape)
 
 
 def FFTtoT(B, kmesh, tol=IMAG_DISCARD_TOL, warn=None):
-    """fourier.py:168-177 (the warning is returned through `warn` if a list is given)."""
-    A = scifft.ifftn(B.reshape(tuple(kmesh) + B.shape[-2:]),
-                     axes=range(len(kmesh)), workers=-1).reshape(B.shape)
-    if max_abs(A.imag) > tol and warn is not None:
-        warn.append(max_abs(A.imag))
+    """k-points -> cells with 1/Nk, real part; the imaginary-part warning of fourier.py:174-175 is appended to
+    `warn` when a list is passed (fourier.py:168-177)"""
+    view, axes = _mesh_view(B, kmesh)
+    A = scifft.ifftn(view, axes=axes).reshape(B.shape)
+    worst = max_abs(A.imag)
+    if warn is not None and worst > tol:
+        warn.append(worst)
     return A.real
 
 
+def _per_spin(fn, x, what):
+    if x.ndim == 3:
+        return fn(x)
+    if x.ndim == 4:
+        return np.stack([fn(xs) for xs in x])
+    raise ValueError("unknown shape of %s: %s" % (what, str(x.shape)))
+
+
 def R2k(dm_R, kmesh):
-    """fourier.py:129-142."""
-    if dm_R.ndim == 3:
-        dm_k = FFTtoK(dm_R, kmesh)
-    elif dm_R.ndim == 4:
-        dm_k = np.zeros_like(dm_R, dtype=np.complex128)
-        for s in range(dm_R.shape[0]):
-            dm_k[s] = FFTtoK(dm_R[s], kmesh)
-    else:
-        raise ValueError("unknown shape of dm_R: %s" % str(dm_R.shape))
-    return dm_k
+    """fourier.py:129-142"""
+    return _per_spin(lambda a: FFTtoK(a, kmesh), dm_R, "dm_R")
 
 
 def k2R(dm_k, kmesh, tol=IMAG_DISCARD_TOL, warn=None):
-    """fourier.py:144-158."""
-    if dm_k.ndim == 3:
-        dm_R = FFTtoT(dm_k, kmesh, tol=tol, warn=warn)
-    elif dm_k.ndim == 4:
-        dm_R = np.zeros_like(dm_k)
-        for s in range(dm_R.shape[0]):
-            dm_R[s] = FFTtoT(dm_k[s], kmesh, tol=tol, warn=warn)
-    else:
-        raise ValueError("unknown shape of dm_k: %s" % str(dm_k.shape))
-    return dm_R.real
+    """fourier.py:144-158"""
+    return _per_spin(lambda b: FFTtoT(b, kmesh, tol=tol, warn=warn), dm_k, "dm_k").real
 
 
 class StripeLattice(object):
-    """The part of libdmet/system/lattice.py:31-56,192-231,304-351,399-411 the path reads: cell grid, cell
-    index arithmetic, expand/extract_stripe and the k2R/R2k method wrappers."""
+    """The parts of the reference's Lattice the path reads: cell grid and index arithmetic, phases, k2R / R2k
+    wrappers, expand / extract_stripe (lattice.py:31-56, 192-231, 304-351, 399-411)."""
 
     def __init__(self, kmesh, nscsites):
-        self.kmesh = list(kmesh)
-        self.csize = np.asarray(kmesh)
-        self.ncells = int(np.prod(self.csize))
-        self.nkpts = self.ncells
+        self.kmesh = [int(n) for n in kmesh]
+        self.csize = np.asarray(self.kmesh)
+        self.ncells = self.nkpts = int(np.prod(self.csize))
         self.nscsites = self.nao = int(nscsites)
-        self.cells = get_R_vec_rel(kmesh)
-        self.celldict = dict(zip(map(tuple, self.cells), range(self.ncells)))
-        self.kpts_scaled = make_kpts_scaled(kmesh)
-        self.phase_R2k = get_phase_R2k_scaled(kmesh, self.kpts_scaled)
+        self.cells = get_R_vec_rel(self.kmesh)
+        self.celldict = {tuple(c): i for i, c in enumerate(self.cells)}
+        self.kpts_scaled = make_kpts_scaled(self.kmesh)
+        self.phase_R2k = get_phase_R2k_scaled(self.kmesh, self.kpts_scaled)
         self.phase_k2R = self.phase_R2k.conj().T / self.nkpts
 
+    # cell index arithmetic
     def cell_idx2pos(self, idx):
         return self.cells[idx % self.ncells]
 
     def cell_pos2idx(self, pos):
-        return self.celldict[tuple(pos % self.csize)]
+        return self.celldict[tuple(np.mod(pos, self.csize))]
 
     def add(self, i, j):
-        return self.cell_pos2idx(self.cell_idx2pos(i) + self.cell_idx2pos(j))
+        return self.cell_pos2idx(self.cells[i] + self.cells[j])
 
     def subtract(self, i, j):
-        return self.cell_pos2idx(self.cell_idx2pos(i) - self.cell_idx2pos(j))
+        return self.cell_pos2idx(self.cells[i] - self.cells[j])
 
+    # Fourier wrappers
     def k2R(self, A, tol=IMAG_DISCARD_TOL):
         return k2R(A, self.kmesh, tol=tol)
 
@@ -135,36 +129,25 @@ class StripeLattice(object):
     R2k_basis = R2k
 
     def expand(self, A, dense=False):
-        """lattice.py:304-337."""
+        """stripe (.., ncells, n, n) -> full translation-invariant (.., ncells*n, ncells*n): block (i+j, j) = A[i].
+        Without `dense`, all-zero stripes are skipped like the reference does (lattice.py:304-337)."""
         assert A.shape[-3] == self.ncells
-        nscsites = A.shape[-1]
-        nsites = A.shape[-1] * A.shape[-3]
-        if A.ndim == 3:
-            bigA = np.zeros((nsites, nsites), dtype=A.dtype)
-            rng = range(self.ncells) if dense else \
-                [j for j in range(self.ncells) if not np.allclose(A[j], 0.0)]
-            for i, j in it.product(rng, range(self.ncells)):
-                idx = self.add(i, j)
-                bigA[idx*nscsites:(idx+1)*nscsites, j*nscsites:(j+1)*nscsites] = A[i]
-        elif A.ndim == 4:
-            spin = A.shape[0]
-            bigA = np.zeros((spin, nsites, nsites), dtype=A.dtype)
-            rng = range(self.ncells) if dense else \
-                [j for j in range(self.ncells) if not np.allclose(A[:, j], 0.0)]
-            for i, j in it.product(rng, range(self.ncells)):
-                idx = self.add(i, j)
-                bigA[:, idx*nscsites:(idx+1)*nscsites, j*nscsites:(j+1)*nscsites] = A[:, i]
-        else:
-            raise ValueError("unknown shape of A, %s" % (A.shape,))
-        return bigA
+        n = A.shape[-1]
+        lead = A.shape[:-3]
+        stripes = A.reshape((-1, self.ncells, n, n))
+        full = np.zeros((stripes.shape[0], self.ncells * n, self.ncells * n), dtype=A.dtype)
+        for i in range(self.ncells):
+            if not dense and np.allclose(stripes[:, i], 0.0):
+                continue
+            for j in range(self.ncells):
+                r = self.add(i, j)
+                full[:, r * n:(r + 1) * n, j * n:(j + 1) * n] = stripes[:, i]
+        return full.reshape(lead + full.shape[1:])
 
     def extract_stripe(self, A):
-        """lattice.py:339-351."""
-        ncells = self.ncells
-        nscsites = A.shape[-1] // ncells
-        if A.ndim == 2:
-            return A.reshape((ncells, nscsites, ncells, nscsites))[:, :, 0]
-        elif A.ndim == 3:
-            spin = A.shape[0]
-            return A.reshape((spin, ncells, nscsites, ncells, nscsites))[:, :, :, 0]
-        raise ValueError("unknown shape of A, %s" % (A.shape,))
+        """first block column of a full matrix (lattice.py:339-351)"""
+        n = A.shape[-1] // self.ncells
+        if A.ndim not in (2, 3):
+            raise ValueError("unknown shape of A, %s" % (A.shape,))
+        blocks = A.reshape(A.shape[:-2] + (self.ncells, n, self.ncells, n))
+        return blocks[..., :, :, 0, :]

@@ -1,302 +1,234 @@
-"""Oracle: embedding basis and embedding Hamiltonian (Slater-determinant DMET).
+"""Oracle: embedding basis, embedding Hamiltonian and the energy-side helpers of Slater-determinant DMET.
 
-Restates libdmet/routine/slater.py:98-220 (get_emb_basis, SVD), 320-370 (get_emb_Ham), 438-476 (ab-initio branch of
-__embHam2e), 478-523 (get_veff, HF branch), 525-547 + 559-560 + 590-605 + 639-643 (__embHam1e, interacting bath,
-HF), 690-712; libdmet/routine/slater_helper.py:37-50,73-80,102-103,494-517; libdmet/solver/scf.py:255-352;
-libdmet/lo/lowdin.py:83-136; libdmet/system/integral.py:61-105,883-928.
+Behaviour restated (own numpy code) from
+  libdmet/routine/slater.py          98-220 get_emb_basis (SVD bath), 320-370 get_emb_Ham, 438-476 ab-initio branch of
+                                     __embHam2e, 478-523 get_veff (HF), 525-605 + 639-643 __embHam1e (interacting bath,
+                                     HF), 690-712 transform_h1 / foldRho_k, 1716-1778 get_H1_scaled / get_H2_scaled,
+                                     1780-1840 transformResults, 1957-2032 get_H_dmet (default branch)
+  libdmet/routine/slater_helper.py   37-50 transform_trans_inv_k, 73-80, 102-103, 494-517 unit2emb
+  libdmet/solver/scf.py              255-352 _get_jk / _get_veff
+  libdmet/lo/lowdin.py               83-136 Loewdin orthogonalisation
+  libdmet/system/integral.py         61-105 Integral, 883-928 get_eri_format
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 `lattice` is duck-typed: .ncells .nscsites .imp_idx .val_idx .expand() .R2k_basis() .df .cell .C_ao_lo
-.eri_symmetry .is_model .hcore_lo_k .vhf_lo_k .ovlp_lo_k .fock_lo_k .rdm1_lo_k .rdm1_lo_R .getH0() .JK_core
+.eri_symmetry .is_model .hcore_lo_k .vhf_lo_k .ovlp_lo_k .rdm1_lo_k .rdm1_lo_R .getH0() .JK_core
 """
 import numpy as np
 import scipy.linalg as la
 
 from . import pyscf_lib as lib
 from .fourier import max_abs, IMAG_DISCARD_TOL
-from .make_basis import mdot, add_spin_dim
+from .make_basis import add_spin_dim
 from . import eri_transform
 
 
 # ---------------------------------------------------------------------------------------------------------
-# libdmet/lo/lowdin.py:83-136
+# small linear-algebra helpers
 # ---------------------------------------------------------------------------------------------------------
-def _lowdin(s, tol=1e-14):
-    e, v = la.eigh(s)
-    idx = e > tol
-    return np.dot(v[:, idx] / np.sqrt(e[idx]), v[:, idx].conj().T)
+def _inv_sqrt(s, tol=1e-14):
+    """S^(-1/2) on the span of eigenvalues > tol (lowdin.py:83-92)"""
+    w, v = la.eigh(s)
+    keep = w > tol
+    return (v[:, keep] / np.sqrt(w[keep])) @ v[:, keep].conj().T
 
 
-def _vec_lowdin(c, s=1, f=None):
-    if f is None:
-        return np.dot(c, _lowdin(mdot(c.conj().T, s, c)))
-    return np.dot(c * f, _lowdin(mdot(c.conj().T, s, c)))
-
-
-def vec_lowdin(C, S, f=None):
-    """lowdin.py:103-136 (only the S.ndim == 2 branches are reachable from get_emb_basis)."""
-    S = np.asarray(S)
-    assert S.ndim == 2
-    if C.ndim == 2:
-        return _vec_lowdin(C, S, f)
-    C_orth = np.zeros_like(C)
-    for s in range(C.shape[0]):
-        C_orth[s] = _vec_lowdin(C[s], S, f if f is None else f[s])
-    return C_orth
+def vec_lowdin(C, S=None):
+    """symmetric orthonormalisation C (C^dagger S C)^(-1/2) of a set of vectors (lowdin.py:94-136, fixed metric)"""
+    C = np.asarray(C)
+    if C.ndim == 3:
+        return np.stack([vec_lowdin(c, S) for c in C])
+    metric = C.conj().T @ C if S is None else C.conj().T @ S @ C
+    return C @ _inv_sqrt(metric)
 
 
 def check_span_same_space(a, b, ovlp=None, tol=1e-8):
-    """Whether the columns of a and b span the same space (what the reference's own test compares baths
-    with, libdmet/routine/test/test_slater.py:46-54): the projector of one must reproduce the other."""
-    a = np.asarray(a)
-    b = np.asarray(b)
-    if ovlp is None:
-        ovlp = np.eye(a.shape[0])
+    """do the columns of a and b span the same space?  (the comparison the reference's own bath test makes,
+    libdmet/routine/test/test_slater.py:46-54: orbitals are only defined up to rotations among themselves)"""
+    a, b = np.asarray(a), np.asarray(b)
     if a.shape != b.shape:
         return False
-    sa = mdot(a.conj().T, ovlp, a)
-    pa = mdot(a, la.inv(sa), a.conj().T, ovlp)
-    return max_abs(pa.dot(b) - b) < tol
+    S = np.eye(a.shape[0]) if ovlp is None else ovlp
+    proj = a @ la.inv(a.conj().T @ S @ a) @ a.conj().T @ S
+    return max_abs(proj @ b - b) < tol
 
 
 # ---------------------------------------------------------------------------------------------------------
 # get_emb_basis
 # ---------------------------------------------------------------------------------------------------------
 def get_emb_basis(lattice, rho=None, local=True, kind='svd', **kwargs):
-    """slater.py:98-115."""
-    if rho is None:
-        rho = lattice.rdm1_lo_R
+    """dispatcher (slater.py:98-115); only the local SVD construction is restated"""
+    rho = lattice.rdm1_lo_R if rho is None else rho
     assert local, "oracle restates the local branch only"
-    if kind == 'svd':
-        return _get_emb_basis_svd(lattice, np.asarray(rho).real, **kwargs)
-    raise ValueError("get_emb_basis: Unknown kind %s" % kind)
+    if kind != 'svd':
+        raise ValueError("get_emb_basis: Unknown kind %s" % kind)
+    return _get_emb_basis_svd(lattice, np.asarray(rho).real, **kwargs)
 
 
-def _get_emb_basis_svd(lattice, rdm1, **kwargs):
-    """slater.py:117-220."""
-    imp_idx = kwargs.get("imp_idx", lattice.imp_idx)
-    val_idx = kwargs.get("val_idx", lattice.val_idx)
-    valence_bath = kwargs.get("valence_bath", True)
-    orth = kwargs.get("orth", True)
-    tol_bath = kwargs.get("tol_bath", 1e-9)
-    nbath = kwargs.get("nbath", None)
-
-    ncells = lattice.ncells
-    nlo = lattice.nscsites
-    imp_idx_bath = val_idx if valence_bath else imp_idx
-    env_idx = []
-    virt_mask = []
-    for i in range(ncells * nlo):
-        if i not in imp_idx_bath:
-            env_idx.append(i)
-            virt_mask.append(i in imp_idx)
+def _get_emb_basis_svd(lattice, rdm1, imp_idx=None, val_idx=None, valence_bath=True, orth=True, tol_bath=1e-9,
+                       nbath=None, **unused):
+    """Bath orbitals = left singular vectors of the environment x impurity block of the density matrix
+    (slater.py:117-220).  With a valence bath only the valence orbitals generate bath states; the virtual impurity
+    rows of the bath are then zeroed and the bath re-orthonormalised.  Output (spin, ncells, nlo, nimp + nbath) with
+    the identity on the impurity rows."""
+    imp_idx = list(lattice.imp_idx if imp_idx is None else imp_idx)
+    val_idx = list(lattice.val_idx if val_idx is None else val_idx)
+    ncells, nlo = lattice.ncells, lattice.nscsites
+    ntot = ncells * nlo
+    generators = val_idx if valence_bath else imp_idx
+    env = np.setdiff1d(np.arange(ntot), generators)            # sorted, like the reference's scan
+    env_is_imp = np.isin(env, imp_idx)
     nimp = len(imp_idx)
 
     rdm1 = np.asarray(rdm1)
-    if rdm1.ndim == 3:
-        rdm1 = rdm1[np.newaxis]
-    assert rdm1.shape[-3:] == (ncells, nlo, nlo)
+    rdm1 = rdm1[None] if rdm1.ndim == 3 else rdm1
+    assert rdm1.shape[1:] == (ncells, nlo, nlo)
     spin = rdm1.shape[0]
-
-    if np.max(imp_idx_bath) >= nlo - 1:
-        rdm1_env_imp = lattice.expand(rdm1)[:, env_idx][:, :, imp_idx_bath]
-        nbath_final = len(imp_idx_bath)
+    # (sic) the reference switches to the expanded matrix already when the LAST orbital of cell 0 generates bath
+    # states (`>= nlo - 1`, slater.py:167); it only changes the cap on the number of bath orbitals
+    if max(generators) >= nlo - 1:
+        coupling = lattice.expand(rdm1)[:, env][:, :, generators]
+        cap = len(generators)
     else:
-        rdm1_env_imp = rdm1.reshape(spin, ncells * nlo, nlo)[:, env_idx][:, :, imp_idx_bath]
-        nbath_final = nlo
-    basis = np.zeros((spin, ncells * nlo, nimp * 2))
-
+        coupling = rdm1.reshape(spin, ntot, nlo)[:, env][:, :, generators]
+        cap = nlo
+    out = np.zeros((spin, ntot, 2 * nimp))
     for s in range(spin):
-        u, sigma, vt = la.svd(rdm1_env_imp[s], full_matrices=False)
-        if nbath is None:
-            nbath_s = (sigma >= tol_bath).sum()
-        else:
-            nbath_s = nbath
-        B = u[:, :nbath_s]
-        if nbath_s > 0:
-            if orth:
-                B[virt_mask] = 0.0
-                B = vec_lowdin(B, np.eye(B.shape[0]))
-        basis[s, imp_idx, :nimp] = np.eye(nimp)
-        basis[s, env_idx, nimp:nimp + nbath_s] = B
-        nbath_final = min(nbath_final, nbath_s)
-
-    basis = basis[:, :, :nimp + nbath_final].reshape(spin, ncells, nlo, nimp + nbath_final)
-    return basis
+        u, sigma, _ = la.svd(coupling[s], full_matrices=False)
+        keep = int(np.count_nonzero(sigma >= tol_bath)) if nbath is None else nbath
+        bath = u[:, :keep]
+        if keep > 0 and orth:
+            bath[env_is_imp] = 0.0
+            bath = vec_lowdin(bath)
+        out[s, imp_idx, :nimp] = np.eye(nimp)
+        out[s, env, nimp:nimp + keep] = bath
+        cap = min(cap, keep)
+    return out[:, :, :nimp + cap].reshape(spin, ncells, nlo, nimp + cap)
 
 
 embBasis = get_emb_basis
 
 
 # ---------------------------------------------------------------------------------------------------------
-# libdmet/system/integral.py
+# Integral container and ERI layout detection
 # ---------------------------------------------------------------------------------------------------------
 class Integral(object):
-    """integral.py:61-105."""
+    """what embHam returns: norb, restricted, bogoliubov, H0, H1 {"cd"}, H2 {"ccdd"}, ovlp (integral.py:61-105)"""
 
     def __init__(self, norb, restricted, bogoliubov, H0, H1, H2, ovlp=None):
-        self.norb = norb
-        self.restricted = restricted
-        self.bogoliubov = bogoliubov
-        self.H0 = H0
-        if isinstance(H1, np.ndarray):
-            H1 = {"cd": H1}
-        if isinstance(H2, np.ndarray):
-            H2 = {"ccdd": H2}
-        for key in H1:
-            assert H1[key] is None or (H1[key].ndim == 3 and H1[key].shape[-1] == self.norb)
-        self.H1 = H1
-        for key in H2:
-            if H2[key] is not None:
-                assert H2[key].ndim in (5, 3, 2)
-        self.H2 = H2
-        self.ovlp = np.eye(self.norb) if ovlp is None else ovlp
+        self.norb, self.restricted, self.bogoliubov, self.H0 = norb, restricted, bogoliubov, H0
+        self.H1 = {"cd": H1} if isinstance(H1, np.ndarray) else H1
+        self.H2 = {"ccdd": H2} if isinstance(H2, np.ndarray) else H2
+        for v in self.H1.values():
+            assert v is None or (v.ndim == 3 and v.shape[-1] == norb)
+        for v in self.H2.values():
+            assert v is None or v.ndim in (5, 3, 2)
+        self.ovlp = np.eye(norb) if ovlp is None else ovlp
 
 
 def get_eri_format(eri, nao):
-    """integral.py:883-928."""
+    """('s1' | 's4' | 's8', spin_dim in {0, 1, 3}) from the array rank and size (integral.py:883-928)"""
     eri = np.asarray(eri)
-    nao_pair = nao * (nao + 1) // 2
-    s1_size = nao ** 4
-    s4_size = nao_pair * nao_pair
-    s8_size = nao_pair * (nao_pair + 1) // 2
+    npair = nao * (nao + 1) // 2
+    size = {'s1': nao ** 4, 's4': npair * npair, 's8': npair * (npair + 1) // 2}
     if eri.ndim == 5:
-        eri_format, spin_dim = 's1', eri.size // s1_size
-    elif eri.ndim == 4 and eri.size == s1_size:
-        eri_format, spin_dim = 's1', 0
+        fmt, spin_dim = 's1', eri.size // size['s1']
+    elif eri.ndim == 4 and eri.size == size['s1']:
+        fmt, spin_dim = 's1', 0
     elif eri.ndim == 3:
-        eri_format, spin_dim = 's4', eri.size // s4_size
-    elif eri.ndim == 2 and eri.size == s4_size:
-        eri_format, spin_dim = 's4', 0
-    elif eri.ndim == 2 and eri.size == s8_size:
-        eri_format, spin_dim = 's8', 1
-    elif eri.ndim == 1 and eri.size == s8_size:
-        eri_format, spin_dim = 's8', 0
+        fmt, spin_dim = 's4', eri.size // size['s4']
+    elif eri.ndim == 2 and eri.size == size['s4']:
+        fmt, spin_dim = 's4', 0
+    elif eri.ndim == 2 and eri.size == size['s8']:
+        fmt, spin_dim = 's8', 1
+    elif eri.ndim == 1 and eri.size == size['s8']:
+        fmt, spin_dim = 's8', 0
     else:
         raise ValueError("Unknown ERI shape %s, nao %s" % (str(eri.shape), nao))
-    assert spin_dim in [0, 1, 3]
-    return eri_format, spin_dim
+    assert spin_dim in (0, 1, 3)
+    return fmt, spin_dim
 
 
 # ---------------------------------------------------------------------------------------------------------
-# libdmet/solver/scf.py:255-352
+# J/K and the HF effective potential in the embedding space (solver/scf.py:255-352)
 # ---------------------------------------------------------------------------------------------------------
 def _get_jk(dm, eri, with_j=True, with_k=True):
-    dm = np.asarray(dm, dtype=np.double)
-    if dm.ndim == 2:
-        dm = dm[np.newaxis]
-    spin = dm.shape[0]
-    nao = dm.shape[-1]
-    eri = np.asarray(eri, dtype=np.double)
-    eri_format, spin_dim = get_eri_format(eri, nao)
+    """PySCF convention J_ij = (ij|kl) D_kl, K_jk = (ij|kl) D_il.  One ERI block: J, K per density matrix.  Three blocks
+    (aa, bb, ab as embHam orders them): vj = ((J_a[D_a], J_b[D_b]), (J_a[D_b], J_b[D_a])), vk = (K_a, K_b)."""
+    dm = np.asarray(dm, dtype=float)
+    dm = dm[None] if dm.ndim == 2 else dm
+    n = dm.shape[-1]
+    eri = np.asarray(eri, dtype=float)
+    fmt, spin_dim = get_eri_format(eri, n)
     if spin_dim == 0:
-        eri = eri[None]
-        spin_dim = 1
-    if spin == 1 or spin_dim == 1:
-        if eri_format == 's1':
-            eri = lib.restore(8, eri[0], nao)
-        else:
-            eri = eri[0]
-        vj, vk = lib.dot_eri_dm(eri, dm, hermi=1, with_j=with_j, with_k=with_k)
-    elif spin_dim == 3:
-        assert dm.shape[0] == 2
-        eri_aa = lib.restore(4, eri[0], nao)
-        vj00, vk00 = lib.dot_eri_dm(eri_aa, dm[0], hermi=1, with_j=with_j, with_k=with_k)
-        eri_bb = lib.restore(4, eri[1], nao)
-        vj11, vk11 = lib.dot_eri_dm(eri_bb, dm[1], hermi=1, with_j=with_j, with_k=with_k)
-        eri_ab = lib.restore(4, eri[2], nao)
-        vj01 = lib.dot_eri_dm(eri_ab, dm[1], hermi=1, with_j=with_j, with_k=False)[0]
-        vj10 = lib.dot_eri_dm(eri_ab.T, dm[0], hermi=1, with_j=with_j, with_k=False)[0]
-        vj = np.asarray(((vj00, vj11), (vj01, vj10)))
-        vk = np.asarray((vk00, vk11))
-    else:
+        eri, spin_dim = eri[None], 1
+    if dm.shape[0] == 1 or spin_dim == 1:
+        block = lib.restore(8, eri[0], n) if fmt == 's1' else eri[0]
+        return lib.dot_eri_dm(block, dm, hermi=1, with_j=with_j, with_k=with_k)
+    if spin_dim != 3:
         raise ValueError
-    return vj, vk
+    assert dm.shape[0] == 2
+    aa, bb, ab = (lib.restore(4, eri[i], n) for i in range(3))
+    vj_aa, vk_aa = lib.dot_eri_dm(aa, dm[0], hermi=1, with_j=with_j, with_k=with_k)
+    vj_bb, vk_bb = lib.dot_eri_dm(bb, dm[1], hermi=1, with_j=with_j, with_k=with_k)
+    vj_ab = lib.dot_eri_dm(ab, dm[1], hermi=1, with_j=with_j, with_k=False)[0]       # alpha feels beta density
+    vj_ba = lib.dot_eri_dm(ab.T, dm[0], hermi=1, with_j=with_j, with_k=False)[0]     # beta feels alpha density
+    return np.asarray(((vj_aa, vj_bb), (vj_ab, vj_ba))), np.asarray((vk_aa, vk_bb))
 
 
 def _get_veff(dm, eri):
-    dm = np.asarray(dm, dtype=np.double)
-    if dm.ndim == 2:
-        dm = dm[np.newaxis]
-    spin = dm.shape[0]
+    """restricted (spin-traced dm): J - K/2; unrestricted: J[a] + J[b] - K per spin (scf.py:334-352)"""
+    dm = np.asarray(dm, dtype=float)
+    dm = dm[None] if dm.ndim == 2 else dm
     vj, vk = _get_jk(dm, eri)
-    if spin == 1:
-        veff = vj - vk * 0.5
-    else:
-        veff = vj[0] + vj[1] - vk
-    return veff
+    return vj - 0.5 * vk if dm.shape[0] == 1 else vj[0] + vj[1] - vk
 
 
 def get_veff(rdm1, eri, hyb=1.0):
-    """slater.py:478-523, HF branch (hyb == 1.0, non-GHF)."""
-    rdm1 = np.asarray(rdm1)
-    if rdm1.ndim == 2:
-        rdm1 = rdm1[None]
+    """slater.py:478-523, HF branch"""
     assert hyb == 1.0
-    return _get_veff(rdm1, eri)
+    rdm1 = np.asarray(rdm1)
+    return _get_veff(rdm1[None] if rdm1.ndim == 2 else rdm1, eri)
 
 
 # ---------------------------------------------------------------------------------------------------------
-# libdmet/routine/slater_helper.py
+# one-body transforms into the embedding space
 # ---------------------------------------------------------------------------------------------------------
 def transform_trans_inv_k(basis_k, H_k, warn=None):
-    """slater_helper.py:37-50."""
-    nkpts, nlo, nbasis = basis_k.shape
-    res = np.zeros((nbasis, nbasis), dtype=np.complex128)
-    for k in range(nkpts):
-        res += mdot(basis_k[k].conj().T, H_k[k], basis_k[k])
-    if max_abs(res.imag) > IMAG_DISCARD_TOL and warn is not None:
-        warn.append(max_abs(res.imag))
-    return res.real / float(nkpts)
+    """Re[ sum_k B_k^dagger H_k B_k ] / nkpts; the imaginary-part warning (> 1e-7) goes to `warn`
+    (slater_helper.py:37-50)"""
+    total = np.einsum("kpm,kpq,kqn->mn", np.conj(basis_k), H_k, basis_k)
+    if warn is not None and max_abs(total.imag) > IMAG_DISCARD_TOL:
+        warn.append(max_abs(total.imag))
+    return total.real / float(len(basis_k))
 
 
 def transform_local(basis, lattice, H):
-    """slater_helper.py:73-80."""
-    res = np.zeros((basis.shape[-1],) * 2)
-    for i in range(lattice.ncells):
-        res += mdot(basis[i].T, H, basis[i])
-    return res
+    """sum over cells of B_R^T H B_R (slater_helper.py:73-80)"""
+    return np.einsum("Rpm,pq,Rqn->mn", basis, H, basis)
 
 
 def transform_imp(basis, lattice, H):
-    """slater_helper.py:102-103."""
-    return mdot(basis[0].T, H, basis[0])
-
-
-def init_H2(norb, symmetry, spin_dim):
-    npair = norb * (norb + 1) // 2
-    if symmetry == 1:
-        return np.zeros((spin_dim, norb, norb, norb, norb))
-    if symmetry == 4:
-        return np.zeros((spin_dim, npair, npair))
-    return np.zeros((spin_dim, npair * (npair + 1) // 2))
+    """impurity-cell term B_0^T H B_0 (slater_helper.py:102-103)"""
+    return basis[0].T @ H @ basis[0]
 
 
 def unit2emb(H2_unit, neo):
-    """slater_helper.py:494-517 (ndarray branch)."""
-    spin_pair = H2_unit.shape[0]
-    if H2_unit.ndim == 5:
-        H2_emb = init_H2(neo, 1, spin_pair)
-    elif H2_unit.ndim == 3:
-        H2_emb = init_H2(neo, 4, spin_pair)
-    elif H2_unit.ndim == 2:
-        H2_emb = init_H2(neo, 8, spin_pair)
-    else:
+    """zero-pad the impurity-cell ERI to neo embedding orbitals, same symmetry layout (slater_helper.py:494-517)"""
+    H2_unit = np.asarray(H2_unit)
+    npair = neo * (neo + 1) // 2
+    tail = {5: (neo,) * 4, 3: (npair, npair), 2: (npair * (npair + 1) // 2,)}.get(H2_unit.ndim)
+    if tail is None:
         raise ValueError
-    fill_idx = tuple(map(slice, H2_unit.shape))
-    H2_emb[fill_idx] = H2_unit
-    return H2_emb
+    out = np.zeros((H2_unit.shape[0],) + tail)
+    out[tuple(slice(0, n) for n in H2_unit.shape)] = H2_unit
+    return out
 
 
 def transform_h1(H1_k, basis_k):
-    """slater.py:690-697."""
-    spin = basis_k.shape[0]
-    nbasis = basis_k.shape[-1]
-    H1_k = add_spin_dim(H1_k, spin, non_spin_dim=3)
-    H1 = np.empty((spin, nbasis, nbasis))
-    for s in range(spin):
-        H1[s] = transform_trans_inv_k(basis_k[s], H1_k[s])
-    return H1
+    """per-spin transform_trans_inv_k with spin broadcasting of H1_k (slater.py:690-697)"""
+    H1_k = add_spin_dim(H1_k, basis_k.shape[0], non_spin_dim=3)
+    return np.stack([transform_trans_inv_k(basis_k[s], H1_k[s]) for s in range(basis_k.shape[0])])
 
 
 foldRho_k = transform_h1   # slater.py:712
@@ -306,191 +238,133 @@ foldRho_k = transform_h1   # slater.py:712
 # get_emb_Ham
 # ---------------------------------------------------------------------------------------------------------
 def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwargs):
-    """slater.py:372-476, ab-initio branch (438-472)."""
-    nbasis = basis.shape[-1]
-    eri_symmetry = lattice.eri_symmetry
-    max_memory = kwargs.get("max_memory", None)
+    """two-body part, ab-initio branch (slater.py:438-476): interacting bath -> get_emb_eri, otherwise the unit ERI
+    zero-padded; unrestricted blocks reordered aa, ab, bb -> aa, bb, ab"""
     assert not lattice.is_model
-    cell = lattice.cell
-    mydf = lattice.df
-    C_ao_lo = lattice.C_ao_lo
-    kscaled_center = kwargs.get("kscaled_center", None)
-    t_reversal_symm = kwargs.get("t_reversal_symm", True)
+    common = dict(C_ao_lo=lattice.C_ao_lo, kscaled_center=kwargs.get("kscaled_center", None),
+                  symmetry=lattice.eri_symmetry, max_memory=kwargs.get("max_memory", None),
+                  t_reversal_symm=kwargs.get("t_reversal_symm", True))
     if int_bath:
-        H2 = eri_transform.get_emb_eri(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, kscaled_center=kscaled_center,
-                                       symmetry=eri_symmetry, max_memory=max_memory,
-                                       t_reversal_symm=t_reversal_symm)
-        if last_aabb and isinstance(H2, np.ndarray) and H2.shape[0] == 3:
-            H2 = H2[[0, 2, 1]]
+        H2 = eri_transform.get_emb_eri(lattice.cell, lattice.df, basis=basis, **common)
     else:
-        H2 = eri_transform.get_unit_eri(cell, mydf, C_ao_lo=C_ao_lo, kscaled_center=kscaled_center,
-                                        symmetry=eri_symmetry, max_memory=max_memory,
-                                        t_reversal_symm=t_reversal_symm)
-        if last_aabb and isinstance(H2, np.ndarray) and H2.shape[0] == 3:
-            H2 = H2[[0, 2, 1]]
-        H2 = unit2emb(H2, nbasis)
-    return H2
+        H2 = eri_transform.get_unit_eri(lattice.cell, lattice.df, **common)
+    if last_aabb and H2.shape[0] == 3:
+        H2 = H2[[0, 2, 1]]
+    return H2 if int_bath else unit2emb(H2, basis.shape[-1])
 
 
 def _embHam1e(lattice, basis, vcor, H2_emb, int_bath=True, add_vcor=False, **kwargs):
-    """slater.py:525-688, interacting-bath Hartree-Fock branch (590-605, 639-643)."""
+    """one-body part, interacting bath + Hartree-Fock (slater.py:525-547, 559-560, 590-605, 639-643):
+    H1 = T[hcore + vhf] - veff_emb[folded density], JK_core = H1 - T[hcore] stored on the lattice"""
     assert int_bath, "oracle restates the interacting-bath branch only"
-    spin = basis.shape[0]
     basis_k = lattice.R2k_basis(basis)
-    hcore_k = lattice.hcore_lo_k
-    ovlp_k = lattice.ovlp_lo_k
-    hcore_emb = transform_h1(hcore_k, basis_k)
-    ovlp_emb = transform_h1(ovlp_k, basis_k)
-    if ovlp_emb.ndim == 3 and ovlp_emb.shape[0] == 1:
+    hcore_emb = transform_h1(lattice.hcore_lo_k, basis_k)
+    ovlp_emb = transform_h1(lattice.ovlp_lo_k, basis_k)
+    if ovlp_emb.shape[0] == 1:
         ovlp_emb = ovlp_emb[0]
     rdm1_emb = foldRho_k(lattice.rdm1_lo_k, basis_k)
-    fock_k = lattice.hcore_lo_k + lattice.vhf_lo_k
-    H1 = transform_h1(fock_k, basis_k)
-    JK_emb = get_veff(rdm1_emb, H2_emb)
-    H1 -= JK_emb
+    H1 = transform_h1(lattice.hcore_lo_k + lattice.vhf_lo_k, basis_k) - get_veff(rdm1_emb, H2_emb)
     lattice.JK_core = H1 - hcore_emb
     if add_vcor:
-        for s in range(spin):
-            H1[s] += transform_local(basis[s], lattice, vcor.get()[s])
+        for s in range(basis.shape[0]):
+            v = vcor.get()[s]
+            H1[s] += transform_local(basis[s], lattice, v)
             if not kwargs.get("fitting", False):
-                H1[s] -= transform_imp(basis[s], lattice, vcor.get()[s])
+                H1[s] -= transform_imp(basis[s], lattice, v)
     return H1, ovlp_emb
 
 
 def get_emb_Ham(lattice, basis, vcor, local=True, **kwargs):
-    """slater.py:320-370."""
+    """embedding Hamiltonian as an Integral, plus the deprecated None (slater.py:320-370)"""
     basis = np.asarray(basis)
-    spin = basis.shape[0]
-    nbasis = basis.shape[-1]
-    H2_given = kwargs.get("H2_given", None)
-    if H2_given is None:
+    H2 = kwargs.get("H2_given", None)
+    if H2 is None:
         H2 = _embHam2e(lattice, basis, vcor, local, **kwargs)
-    else:
-        H2 = H2_given
     H1, ovlp_emb = _embHam1e(lattice, basis, vcor, H2, **kwargs)
-    H0 = lattice.getH0()
-    if isinstance(H2, np.ndarray):
-        H2 = {"ccdd": H2}
-    ImpHam = Integral(nbasis, spin == 1, False, H0, {"cd": H1}, H2, ovlp=ovlp_emb)
-    return ImpHam, None
+    nbasis = basis.shape[-1]
+    return Integral(nbasis, basis.shape[0] == 1, False, lattice.getH0(), {"cd": H1}, {"ccdd": H2},
+                    ovlp=ovlp_emb), None
 
 
 embHam = get_emb_Ham
 
 
 # ---------------------------------------------------------------------------------------------------------
-# energy side (slater.py:1716-1840, 1957-2032)
+# energy side
 # ---------------------------------------------------------------------------------------------------------
+def _complement(nbasis, imp_idx):
+    return np.setdiff1d(np.arange(nbasis), np.asarray(imp_idx, dtype=int))
+
+
 def get_H1_scaled(H1, imp_idx, env_idx=None):
-    """slater.py:1716-1732."""
+    """in place: weight = (number of impurity indices) / 2 (slater.py:1716-1732)"""
     assert H1.ndim == 3
-    nbasis = H1.shape[-1]
-    if env_idx is None:
-        env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
-    imp_env = np.ix_(imp_idx, env_idx)
-    env_imp = np.ix_(env_idx, imp_idx)
-    env_env = np.ix_(env_idx, env_idx)
-    for s in range(H1.shape[0]):
-        H1[s][imp_env] *= 0.5
-        H1[s][env_imp] *= 0.5
-        H1[s][env_env] = 0.0
+    member = np.zeros(H1.shape[-1])
+    member[np.asarray(imp_idx, dtype=int)] = 1.0
+    H1 *= 0.5 * (member[:, None] + member[None, :])
     return H1
 
 
 def get_H2_scaled(H2, imp_idx, env_idx=None):
-    """slater.py:1734-1778."""
+    """in place: weight = (number of impurity indices among the four) / 4, s4 (3-d) or s1 (5-d) layout
+    (slater.py:1734-1778)"""
     if H2.ndim == 3:
-        nbasis_pair = H2.shape[-1]
-        nbasis = int(np.sqrt(nbasis_pair * 2))
-        tril_idx = np.tril_indices(nbasis)
-        mask = np.isin(tril_idx, imp_idx)
-        zero = np.logical_not(np.logical_or(*mask))
-        half = np.logical_xor(*mask)
-        one = np.logical_and(*mask)
-        mask_list = (zero, half, one)
-        for s in range(H2.shape[0]):
-            for i, mask_i in enumerate(mask_list):
-                for j, mask_j in enumerate(mask_list):
-                    if i + j == 4:
-                        continue
-                    elif i + j == 0:
-                        H2[s][np.ix_(mask_i, mask_j)] = 0.0
-                    else:
-                        H2[s][np.ix_(mask_i, mask_j)] *= ((i + j) * 0.25)
+        n = int(np.sqrt(H2.shape[-1] * 2))
+        member = np.zeros(n)
+        member[np.asarray(imp_idx, dtype=int)] = 1.0
+        r, c = np.tril_indices(n)
+        wpair = member[r] + member[c]
+        H2 *= 0.25 * (wpair[:, None] + wpair[None, :])
     elif H2.ndim == 5:
-        nbasis = H2.shape[-1]
-        if env_idx is None:
-            env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
-        mask_list = (env_idx, imp_idx)
-        for s in range(H2.shape[0]):
-            for i, mi in enumerate(mask_list):
-                for j, mj in enumerate(mask_list):
-                    for k, mk in enumerate(mask_list):
-                        for l, ml in enumerate(mask_list):
-                            H2[s][np.ix_(mi, mj, mk, ml)] *= (i + j + k + l) * 0.25
+        member = np.zeros(H2.shape[-1])
+        member[np.asarray(imp_idx, dtype=int)] = 1.0
+        m = member
+        H2 *= 0.25 * (m[:, None, None, None] + m[None, :, None, None] + m[None, None, :, None] + m[None, None, None, :])
     else:
         raise ValueError("Unknown H2 shape to scale: %s" % (str(H2.shape)))
     return H2
 
 
 def get_H_dmet(basis, lattice, ImpHam, last_dmu, imp_idx=None, compact=True, **kwargs):
-    """slater.py:1957-2032, default branch (E1, veff not given)."""
-    spin = basis.shape[0]
-    nbasis = basis.shape[-1]
-    if imp_idx is None:
-        imp_idx = list(range(len(lattice.imp_idx)))
-    imp_idx = np.asarray(imp_idx)
-    env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
-    basis_k = lattice.R2k_basis(basis)
-    H1_scaled = transform_h1(lattice.hcore_lo_k, basis_k)
-    JK_core = lattice.JK_core if lattice.JK_core is not None else [0.0 for s in range(spin)]
-    for s in range(spin):
-        H1_scaled[s] += 0.5 * JK_core[s]
-    H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
-    H0 = lattice.getH0()
-    npair = nbasis * (nbasis + 1) // 2
-    H2_scaled = np.empty((spin * (spin + 1) // 2, npair, npair))
-    for s in range(spin * (spin + 1) // 2):
-        H2_scaled[s] = lib.restore(4, ImpHam.H2["ccdd"][s], nbasis)
-    H2_scaled = get_H2_scaled(H2_scaled, imp_idx, env_idx)
+    """DMET Hamiltonian weighted by impurity-index counts, default branch (slater.py:1957-2032):
+    H1 = scaled( T[hcore] + JK_core / 2 ), H2 = scaled( s4 ERI ), H0 = lattice H0"""
+    spin, nbasis = basis.shape[0], basis.shape[-1]
+    imp_idx = np.arange(len(lattice.imp_idx)) if imp_idx is None else np.asarray(imp_idx)
+    H1 = transform_h1(lattice.hcore_lo_k, lattice.R2k_basis(basis))
+    if lattice.JK_core is not None:
+        H1 += 0.5 * np.asarray(lattice.JK_core)
+    H1 = get_H1_scaled(H1, imp_idx)
+    H2 = np.stack([lib.restore(4, blk, nbasis) for blk in ImpHam.H2["ccdd"]]).copy()
+    H2 = get_H2_scaled(H2, imp_idx)
     if not compact:
-        H2_scaled = np.stack([lib.restore(1, H2_scaled[s], nbasis) for s in range(H2_scaled.shape[0])])
-    return Integral(nbasis, spin == 1, False, H0, {"cd": H1_scaled}, {"ccdd": H2_scaled})
+        H2 = np.stack([lib.restore(1, blk, nbasis) for blk in H2])
+    return Integral(nbasis, spin == 1, False, lattice.getH0(), {"cd": H1}, {"ccdd": H2})
 
 
 def transformResults(rhoEmb, E, basis, ImpHam, H1e=None, **kwargs):
-    """slater.py:1780-1840."""
-    spin = rhoEmb.shape[0]
-    nscsites = basis.shape[2]
-    nbasis = basis.shape[-1]
-    if "lattice" in kwargs:
-        imp_idx = np.asarray(kwargs.get("imp_idx", range(len(kwargs["lattice"].imp_idx))))
-    else:
-        imp_idx = np.asarray(kwargs.get("imp_idx", np.arange(nscsites)))
-    nelec = 0.0
+    """impurity density, fragment energy and electron number from the solver's density matrix
+    (slater.py:1780-1840).  E2 = E - <H1> - H0 is the two-body part of the solver energy; the one-body part is
+    re-evaluated with the chemical-potential shift and half of JK_core removed and the impurity weights applied."""
+    spin, nscsites, nbasis = rhoEmb.shape[0], basis.shape[2], basis.shape[-1]
+    lattice = kwargs.get("lattice", None)
+    default_imp = np.arange(len(lattice.imp_idx)) if lattice is not None else np.arange(nscsites)
+    imp_idx = np.asarray(kwargs.get("imp_idx", default_imp))
+    per_spin = 2.0 / spin
+    nelec = per_spin * sum(np.trace(rhoEmb[s][np.ix_(imp_idx, imp_idx)]) for s in range(spin))
+    rhoImp = rhoEmb[:, imp_idx][:, :, imp_idx]
+    if E is None:
+        return rhoImp, None, nelec
+    dmu_idx = kwargs.get("dmu_idx", None)
+    dmu_idx = list(range(nscsites)) if dmu_idx is None else dmu_idx
+    H1 = ImpHam.H1["cd"]
+    E2 = E - per_spin * np.einsum("spq,sqp", H1, rhoEmb) - ImpHam.H0
+    shift = np.zeros((nscsites, nscsites))
+    shift[dmu_idx, dmu_idx] = -kwargs["last_dmu"]
+    H1s = np.array(H1, copy=True)
     for s in range(spin):
-        nelec += np.sum(rhoEmb[s, imp_idx, imp_idx])
-    nelec *= (2.0 / spin)
-    rhoImp = rhoEmb[np.ix_(range(spin), imp_idx, imp_idx)]
-    if E is not None:
-        lattice = kwargs["lattice"]
-        last_dmu = kwargs["last_dmu"]
-        imp_idx = np.asarray(kwargs.get("imp_idx", list(range(len(lattice.imp_idx)))))
-        dmu_idx = kwargs.get("dmu_idx", None)
-        if dmu_idx is None:
-            dmu_idx = list(range(nscsites))
-        env_idx = np.asarray([idx for idx in range(nbasis) if idx not in imp_idx], dtype=int)
-        E2 = E - np.einsum('spq,sqp', ImpHam.H1["cd"], rhoEmb) * (2.0 / spin) - ImpHam.H0
-        H1_scaled = np.array(ImpHam.H1["cd"], copy=True)
-        dmu_mat = np.zeros((nscsites, nscsites))
-        dmu_mat[dmu_idx, dmu_idx] = -last_dmu
-        for s in range(spin):
-            H1_scaled[s] -= transform_imp(basis[s], lattice, dmu_mat)
-            if lattice.JK_core is not None:
-                H1_scaled[s] -= 0.5 * lattice.JK_core[s]
-        H1_scaled = get_H1_scaled(H1_scaled, imp_idx, env_idx)
-        E1 = np.einsum('spq,sqp', H1_scaled, rhoEmb) * (2.0 / spin)
-        Efrag = E1 + E2 + lattice.getH0()
-    else:
-        Efrag = None
-    return rhoImp, Efrag, nelec
+        H1s[s] -= transform_imp(basis[s], lattice, shift)
+        if lattice.JK_core is not None:
+            H1s[s] -= 0.5 * lattice.JK_core[s]
+    H1s = get_H1_scaled(H1s, imp_idx)
+    E1 = per_spin * np.einsum("spq,sqp", H1s, rhoEmb)
+    return rhoImp, E1 + E2 + lattice.getH0(), nelec
