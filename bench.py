@@ -35,6 +35,13 @@ WORKLOADS = {
     "mid": ([2, 2, 4], 200, 1000, 150),
     "small": ([2, 2, 2], 100, 500, 50),          # sweep minimum
     "tiny": ([1, 2, 3], 24, 64, 20),
+    # BASELINE.json configs[4]: synthetic sweep nkpts 8-64, nao 100-300, naux 500-1500, neo 50-200
+    "sweep_222_300_1500_200": ([2, 2, 2], 300, 1500, 200),
+    "sweep_224_200_1000_100": ([2, 2, 4], 200, 1000, 100),
+    "sweep_333_100_500_150": ([3, 3, 3], 100, 500, 150),
+    "sweep_442_200_1000_150": ([4, 4, 2], 200, 1000, 150),
+    "sweep_444_100_500_100": ([4, 4, 4], 100, 500, 100),
+    "sweep_444_300_1500_200": ([4, 4, 4], 300, 1500, 200),
 }
 
 

@@ -352,13 +352,24 @@ __device__ __forceinline__ int tri_idx(int a, int b) { return a >= b ? a * (a + 
 
 __global__ void __launch_bounds__(256)
 restore_s1_kernel(const double* __restrict__ eri4, double* __restrict__ out, int n, long long npair) {
-    const int ij = blockIdx.x;
-    const int i = ij / n, j = ij - i * n;
-    const double* row = eri4 + (long long)tri_idx(i, j) * npair;
-    double* dst = out + (long long)ij * n * n;
+    // one CTA per packed row P = (i >= j): the row is staged in shared memory once and unpacked into the two
+    // (n, n) slabs out[i][j][:][:] and out[j][i][:][:] with coalesced writes
+    extern __shared__ double s1row[];
+    const long long P = blockIdx.x;
+    int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= P) ++i;
+    while ((long long)i * (i + 1) / 2 > P) --i;
+    const int j = (int)(P - (long long)i * (i + 1) / 2);
+    const double* row = eri4 + P * npair;
+    for (long long q = threadIdx.x; q < npair; q += blockDim.x) s1row[q] = row[q];
+    __syncthreads();
+    double* dst_ij = out + ((long long)i * n + j) * n * n;
+    double* dst_ji = out + ((long long)j * n + i) * n * n;
     for (int kl = threadIdx.x; kl < n * n; kl += blockDim.x) {
         const int k = kl / n, l = kl - k * n;
-        dst[kl] = row[tri_idx(k, l)];
+        const double v = s1row[tri_idx(k, l)];
+        dst_ij[kl] = v;
+        if (i != j) dst_ji[kl] = v;
     }
 }
 
@@ -379,10 +390,23 @@ restore_s8_kernel(const double* __restrict__ eri4, double* __restrict__ out, lon
 //    y2[k]      = sum_l M[k][l] D[j][l]   -> contributes to K[i][k]   (i != j)
 // partial rows are written out and reduced in fixed order by jk_reduce_kernel (deterministic, no atomics).
 // ----------------------------------------------------------------------------------------------------------
+// dd[Q = (k >= l)] = D_kl + D_lk (k != l), D_kk : the packed density the J dot product runs against
+__global__ void jk_pack_dm_kernel(const double* __restrict__ D, double* __restrict__ dd, int n) {
+    const long long npair = (long long)n * (n + 1) / 2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npair;
+         q += (long long)gridDim.x * blockDim.x) {
+        int k = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+        while ((long long)(k + 1) * (k + 2) / 2 <= q) ++k;
+        while ((long long)k * (k + 1) / 2 > q) --k;
+        const int l = (int)(q - (long long)k * (k + 1) / 2);
+        dd[q] = k == l ? D[(size_t)k * n + k] : D[(size_t)k * n + l] + D[(size_t)l * n + k];
+    }
+}
+
 __global__ void __launch_bounds__(256)
-jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, double* __restrict__ vj_packed,
-               double* __restrict__ kpart, int n, long long npair, int with_k) {
-    extern __shared__ double srow[];     // [npair] + [2n] D rows + [8] reduction
+jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, const double* __restrict__ dd,
+               double* __restrict__ vj_packed, double* __restrict__ kpart, int n, long long npair, int with_k) {
+    extern __shared__ double srow[];     // [npair] packed row, [n] D[i,:], [n] D[j,:], [8] reduction
     double* dI = srow + npair;
     double* dJ = dI + n;
     double* red = dJ + n;
@@ -392,20 +416,16 @@ jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, do
     while ((long long)i * (i + 1) / 2 > P) --i;
     const int j = (int)(P - (long long)i * (i + 1) / 2);
     const double* row = eri4 + P * npair;
-    for (long long q = threadIdx.x; q < npair; q += blockDim.x) srow[q] = row[q];
+    // stage the row (coalesced) and form the J dot product on the fly
+    double part = 0.0;
+    for (long long q = threadIdx.x; q < npair; q += blockDim.x) {
+        const double v = row[q];
+        srow[q] = v;
+        part = fma(v, dd[q], part);
+    }
     for (int l = threadIdx.x; l < n; l += blockDim.x) {
         dI[l] = D[(size_t)i * n + l];
         dJ[l] = D[(size_t)j * n + l];
-    }
-    __syncthreads();
-    // ---- J ----
-    double part = 0.0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const double* mrow = srow + (size_t)k * (k + 1) / 2;
-        double s = 0.0;
-        for (int l = 0; l < k; ++l) s += mrow[l] * (D[(size_t)k * n + l] + D[(size_t)l * n + k]);
-        s += mrow[k] * D[(size_t)k * n + k];
-        part += s;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -417,13 +437,23 @@ jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, do
         vj_packed[P] = s;
     }
     if (!with_k) return;
-    // ---- K partials ----
+    // K partials: y1[k] = sum_l M[k][l] D[i][l], y2[k] = sum_l M[k][l] D[j][l] with M the symmetric unpacking of the
+    // row.  Thread k walks its own packed row segment (l <= k), then the column below the diagonal (l > k), where
+    // neighbouring threads read neighbouring words.
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         double y1 = 0.0, y2 = 0.0;
-        for (int l = 0; l < n; ++l) {
-            const double m = srow[tri_idx(k, l)];
+        const double* seg = srow + (size_t)k * (k + 1) / 2;
+        for (int l = 0; l <= k; ++l) {
+            const double m = seg[l];
             y1 = fma(m, dI[l], y1);
             y2 = fma(m, dJ[l], y2);
+        }
+        size_t off = (size_t)(k + 1) * (k + 2) / 2 + k;       // element (l = k + 1, k)
+        for (int l = k + 1; l < n; ++l) {
+            const double m = srow[off];
+            y1 = fma(m, dI[l], y1);
+            y2 = fma(m, dJ[l], y2);
+            off += (size_t)l + 1;
         }
         kpart[(P * 2 + 0) * n + k] = y1;
         kpart[(P * 2 + 1) * n + k] = y2;
