@@ -171,10 +171,12 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         ain[i] = xor_hi(y, mA ^ 0x80000000u); // -sa * Ai
                     }
                     const uint32_t b_addr = sbase + b_off + kk * T::B_SLAB;
+                    // software pipeline over the B fragments: fragment j+1 is in flight while the MMAs of j issue
+                    double br, bi, br_n = 0.0, bi_n = 0.0;
+                    lds128(b_addr, br, bi);
 #pragma unroll
                     for (int j = 0; j < FB; ++j) {
-                        double br, bi;
-                        lds128(b_addr + j * 512, br, bi);
+                        if (j + 1 < FB) lds128(b_addr + (j + 1) * 512, br_n, bi_n);
                         bi = xor_hi(bi, mB);                  //  sb * Bi
 #pragma unroll
                         for (int i = 0; i < FA; ++i) {
@@ -183,6 +185,8 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             dmma884(cr[i][j][0], cr[i][j][1], ain[i], bi);
                             dmma884(ci[i][j][0], ci[i][j][1], aip[i], br);
                         }
+                        br = br_n;
+                        bi = bi_n;
                     }
                 }
                 prev_stage = stage;
