@@ -218,6 +218,7 @@ def run_ours(args):
 
     kmesh, nao, naux, neo = WORKLOADS[args.workload]
     F1, F3, B, G = flops(kmesh, nao, naux, neo)
+    args.group, args.kl_group = et.auto_groups(nao, naux, neo, 1, args.group or None, args.kl_group or None)
     gdf = synthetic.SyntheticGDF(kmesh, nao, naux, seed=2026)
     C_ao_lo_h = synthetic.make_C_ao_lo(kmesh, nao, seed=1)
     basis_h = synthetic.make_emb_basis(kmesh, nao, neo, seed=2)
@@ -437,8 +438,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
-    ap.add_argument("--group", type=int, default=4)
-    ap.add_argument("--kl-group", dest="kl_group", type=int, default=4)
+    ap.add_argument("--group", type=int, default=0, help="blocks per stage-1 launch (0 = auto)")
+    ap.add_argument("--kl-group", dest="kl_group", type=int, default=0, help="momenta per stage-3 launch (0 = auto)")
     ap.add_argument("--store-slots", dest="store_slots", type=int, default=0)
     ap.add_argument("--host-pool", dest="host_pool", type=int, default=16)
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=1)

@@ -21,8 +21,24 @@ from . import fourier
 from .make_basis import add_spin_dim
 
 ERI_IMAG_TOL = 1e-6     # eri_transform.py:32
-DEFAULT_GROUP = 4       # (k_i, k_j) blocks per stage-1 launch
-DEFAULT_KL_GROUP = 4    # transfer momenta per stage-3 launch
+DEFAULT_GROUP = None      # (k_i, k_j) blocks per stage-1 launch; None = choose from the block size (auto_groups)
+DEFAULT_KL_GROUP = None   # transfer momenta per stage-3 launch; None = auto
+
+
+def auto_groups(nao, naux, nemb, nspin, group=None, kl_group=None):
+    """How many blocks share a stage-1 launch and how many momenta share a stage-3 launch.  Small blocks are
+    batched until a launch carries ~3e11 flop (about 10 ms) so that tile-wave tails and launch gaps stay below a
+    few percent; the staging buffers (X: group * naux * nemb * nao complex, ring: 2 * group blocks) are capped at
+    ~6 GB.  The target shape (nao 200, naux 1000, neo 150) gets 4 and 4."""
+    if group is None:
+        f_block = 8.0 * naux * nao * nemb * (nao + nemb) * nspin
+        group = int(np.ceil(3.0e11 / f_block))
+        bytes_per_block = 16.0 * naux * nao * (nspin * nemb + 2 * nao)
+        group = max(4, min(group, 32, int(6.0e9 / bytes_per_block)))
+        group = 1 << (max(1, group).bit_length() - 1)          # power of two: units of 32 / 36 blocks split evenly
+    if kl_group is None:
+        kl_group = max(4, min(16, int(np.ceil(4000.0 / (2.0 * naux)))))
+    return int(group), int(kl_group)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -155,6 +171,8 @@ class EriBuild(object):
     def __init__(self, CT, naux, eri, group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, gso=False):
         self.dev = get_device()
         spin, nkpts, nemb, nao = CT.shape
+        group, kl_group = auto_groups(nao, naux, nemb, spin, group, kl_group)
+        self.group, self.kl_group = group, kl_group
         self.CT = CT
         self.eri = eri
         self.shape = (nkpts, nao, naux, nemb, spin)
