@@ -1,0 +1,182 @@
+"""Generalised-spin-orbital (GSO / BCS-type) embedding Hamiltonian -- drop-in for the ab-initio, interacting-bath,
+Hartree-Fock branch of `libdmet.routine.spinless.get_emb_Ham` (`embHam`), spinless.py:433-462, 464-558 (two-body part
+via `get_emb_eri_gso`) and 560-726 (one-body part), with the helpers of spinless_helper.py:31-46 (`separate_basis`),
+349-438 (`transform_trans_inv_k`, `transform_local`, `transform_imp`).
+
+A GSO basis has 2*nao rows per cell (alpha rows, then beta rows).  Lattice quantities come as (3, nkpts, nao, nao)
+stacks (aa, bb, ab); the density matrix is one (nkpts, 2*nao, 2*nao) generalised matrix.  The two-body integrals stay
+on the GPU between the ERI build and the J - K contraction; all contractions run in libldm_b200.so.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from .device import get_device
+from .eri_transform import get_emb_eri_gso, separate_basis
+from .fourier import IMAG_DISCARD_TOL
+from .integral import Integral
+from . import slater
+from .make_basis import sandwich
+
+
+def _zdev(a):
+    return slater._zdev(a)
+
+
+def transform_trans_inv_k_dev(basis_ka, basis_kb, H_k):
+    """Re sum_k [ Ba^dagger H_aa Ba + Bb^dagger H_bb Bb + (Ba^dagger H_ab Bb + h.c.) ] / nkpts  -> (nbasis, nbasis)
+    float64 device tensor (spinless_helper.py:349-381).  H_k: (2 or 3, nkpts, nao, nao)."""
+    dev = get_device()
+    H = _zdev(H_k)
+    assert H.dim() == 4 and H.shape[0] in (2, 3)
+    Ba, Bb = _zdev(basis_ka), _zdev(basis_kb)
+    nk, nao, nb = Ba.shape
+    BaT = dev.ztranspose(Ba)                     # (nk, nbasis, nao): k-contiguous rows
+    BbT = dev.ztranspose(Bb)
+    coef = torch.cat([BaT, BbT]).contiguous()    # slices 0..nk-1 = alpha, nk..2nk-1 = beta
+    H3 = H.reshape(-1, nao, nao)
+    k = np.arange(nk)
+    # aa and bb: batch entry b uses coefficient slice b (left, conjugated, and right) and H slice b
+    terms = sandwich(coef, True, coef, False, H3, h_index=np.concatenate([k, nk + k]),
+                     a_index=np.concatenate([k, nk + k]))
+    res, imag = dev.ksum_real(terms.contiguous(), scale=1.0)
+    worst = imag
+    if H.shape[0] == 3:
+        # ab: Ba^dagger H_ab Bb; its Hermitian conjugate is added on the (real part of the) k-sum
+        VT = dev.empty((nk, nb, nao), torch.complex128)
+        segs = np.zeros((nk, 4), dtype=np.int32)
+        segs[:, 0] = nk + k                       # right factor Bb
+        segs[:, 1] = 2 * nk + k                   # H_ab
+        dev.zgemm_tn(coef, H3, segs, VT, c_off=np.arange(nk, dtype=np.int64) * nb * nao, s_outer=nao, nbatch=nk,
+                     nseg=1)
+        out = dev.empty((nk, nb, nb), torch.complex128)
+        segs2 = np.zeros((nk, 4), dtype=np.int32)
+        segs2[:, 0] = k                           # left factor Ba, conjugated
+        segs2[:, 1] = k
+        segs2[:, 2] = 1
+        dev.zgemm_tn(coef, VT, segs2, out, c_off=np.arange(nk, dtype=np.int64) * nb * nb, s_outer=nb, nbatch=nk,
+                     nseg=1)
+        ab, imag_ab = dev.ksum_real(out, scale=1.0)
+        # Re(T + T^dagger) = Re T + (Re T)^T ; Im(T + T^dagger) is antisymmetric and bounded by 2 max|Im T|
+        res = res + ab + ab.t()
+        worst = worst + 2.0 * imag_ab
+    if worst > IMAG_DISCARD_TOL:
+        warnings.warn("transform_trans_inv_k: has imag part %s" % worst)
+    return res / float(nk)
+
+
+def transform_trans_inv_k(basis_ka, basis_kb, H_k):
+    """spinless_helper.py:349-381, numpy in / numpy out"""
+    return transform_trans_inv_k_dev(basis_ka, basis_kb, H_k).cpu().numpy()
+
+
+def transform_local(basis_Ra, basis_Rb, H):
+    """sum over cells of Ba^T H_aa Ba + Bb^T H_bb Bb (+ Ba^T H_ab Bb + h.c.)   (spinless_helper.py:383-409)"""
+    H = np.asarray(H)
+    assert H.shape[0] in (2, 3)
+    res = np.einsum("Rpm,pq,Rqn->mn", basis_Ra.conj(), H[0], basis_Ra) + \
+        np.einsum("Rpm,pq,Rqn->mn", basis_Rb.conj(), H[1], basis_Rb)
+    if H.shape[0] == 3:
+        ab = np.einsum("Rpm,pq,Rqn->mn", basis_Ra.conj(), H[2], basis_Rb)
+        res = res + ab + ab.conj().T
+    return res
+
+
+def transform_imp(basis_Ra, basis_Rb, H):
+    """the cell-0 term of transform_local (spinless_helper.py:411-438)"""
+    return transform_local(basis_Ra[:1], basis_Rb[:1], H)
+
+
+def foldRho_k(GRho_k, basis_k):
+    """generalised density matrix folded to the embedding space (spinless.py:727-737)"""
+    return slater.transform_trans_inv_k(basis_k, GRho_k)
+
+
+def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwargs):
+    """spinless.py:464-558, ab-initio interacting bath: one GSO ERI block, built in s4 on the device"""
+    if getattr(lattice, "is_model", False):
+        raise NotImplementedError("model Hamiltonians are outside the ab-initio hot path")
+    if not int_bath:
+        raise NotImplementedError("the reference's non-interacting-bath GSO branch feeds a (1, npair, npair) unit ERI "
+                                  "to a 3-block unit2emb (spinless_helper.py:288-313) and cannot run; not mirrored")
+    nb = basis.shape[-1]
+    eri4 = get_emb_eri_gso(lattice.cell, lattice.df, C_ao_lo=lattice.C_ao_lo, basis=basis,
+                           kscaled_center=kwargs.get("kscaled_center", None), symmetry=4,
+                           t_reversal_symm=kwargs.get("t_reversal_symm", True), return_device=True,
+                           **{k: kwargs[k] for k in ("source", "group", "kl_group", "stats") if k in kwargs})
+    dev = get_device()
+    sym = lattice.eri_symmetry
+    if sym == 4:
+        H2 = eri4.cpu().numpy()
+    elif sym == 1:
+        H2 = dev.restore_s1(eri4[0], nb).cpu().numpy()[None]
+    elif sym == 8:
+        H2 = dev.restore_s8(eri4[0], nb).cpu().numpy()[None]
+    else:
+        raise ValueError("unknown eri_symmetry %s" % sym)
+    return H2, [eri4[0]]
+
+
+def _embHam1e(lattice, basis, vcor, mu, H2_emb, eri4_blocks, int_bath=True, add_vcor=False, **kwargs):
+    """spinless.py:560-726, interacting bath, Hartree-Fock: H1 = T[fock_hf] - (J - K)[folded density] - mu N
+    (+ optional local terms); side effect lattice.JK_core.  Returns (H1 (1, nbasis, nbasis), ovlp_emb)."""
+    if not int_bath or kwargs.get("dft", False):
+        raise NotImplementedError("only the interacting-bath Hartree-Fock branch is mirrored")
+    if vcor is not None and hasattr(vcor, "islocal") and not vcor.islocal():
+        raise Exception("nonlocal correlation potential cannot be treated in this routine")
+    basis = np.asarray(basis)
+    nao = int(lattice.nscsites)
+    nb = basis.shape[-1]
+    basis_k = lattice.R2k_basis(basis)
+    basis_Ra, basis_Rb = separate_basis(basis)
+    basis_ka, basis_kb = separate_basis(basis_k)
+    hcore_k = kwargs.get("hcore_custom", None)
+    hcore_k = lattice.getH1(kspace=True) if hcore_k is None else hcore_k
+    hcore_emb = transform_trans_inv_k_dev(basis_ka, basis_kb, hcore_k)
+    ovlp_emb = transform_trans_inv_k_dev(basis_ka, basis_kb, lattice.get_ovlp(kspace=True)).cpu().numpy()
+    bk = slater._BasisK(np.asarray(basis_k)[None])
+    rdm1_emb = slater.transform_trans_inv_k_dev(bk, 0, _zdev(lattice.rdm1_lo_k), 0)     # foldRho_k
+    H1 = transform_trans_inv_k_dev(basis_ka, basis_kb, lattice.fock_hf_lo_k)
+    hcore_add = kwargs.get("hcore_add", None)
+    if hcore_add is not None:
+        H1 = H1 + get_device().to_device(transform_imp(basis_Ra, basis_Rb, hcore_add).real, torch.float64)
+    if eri4_blocks is None:
+        eri4_blocks = slater._s4_blocks_dev(H2_emb, nb)
+    vj, vk = get_device().jk_s4(eri4_blocks[0], rdm1_emb.contiguous())                 # GHF: J - K (scf.py:732-740)
+    H1 = H1 - (vj - vk)
+    lattice.JK_core = (H1 - hcore_emb).cpu().numpy()
+    H1 = H1.cpu().numpy()
+    mu_mat = np.zeros((2, nao, nao))
+    np.fill_diagonal(mu_mat[0], -mu)
+    np.fill_diagonal(mu_mat[1], mu)
+    H1 += transform_local(basis_Ra, basis_Rb, mu_mat).real
+    if add_vcor:
+        H1 += transform_local(basis_Ra, basis_Rb, vcor.get()).real
+        if not kwargs.get("fitting", False):
+            H1 -= transform_imp(basis_Ra, basis_Rb, vcor.get()).real
+        JK_imp = lattice.get_JK_imp()
+        if JK_imp is not None:
+            H1 -= transform_imp(basis_Ra, basis_Rb, JK_imp).real
+    return H1[np.newaxis], ovlp_emb
+
+
+def get_emb_Ham(lattice, basis, vcor, mu, local=True, **kwargs):
+    """spinless.py:433-462.  Returns (Integral, None) with H1 {"cd": (1, n, n)} and H2 {"ccdd": (1, ...)}."""
+    basis = np.asarray(basis)
+    nb = basis.shape[-1]
+    H2_given = kwargs.get("H2_given", None)
+    blocks = None
+    if H2_given is None:
+        if kwargs.get("H2_fname", None) is not None:
+            raise NotImplementedError("loading H2 from HDF5 needs h5py, which this build does not depend on")
+        H2, blocks = _embHam2e(lattice, basis, vcor, local, **kwargs)
+    else:
+        H2 = H2_given
+    kw1 = {k: v for k, v in kwargs.items() if k != "last_aabb"}
+    H1, ovlp = _embHam1e(lattice, basis, vcor, mu, H2, blocks, **kw1)
+    H0 = lattice.getH0() + kwargs.get("H0_add", 0.0)
+    return Integral(nb, True, False, H0, {"cd": H1}, {"ccdd": H2}, ovlp=ovlp), None
+
+
+embHam = get_emb_Ham

@@ -1,0 +1,84 @@
+"""Oracle: generalised-spin-orbital embedding Hamiltonian, ab-initio interacting-bath Hartree-Fock branch.
+
+Behaviour restated (own numpy code) from libdmet/routine/spinless.py:433-462 (get_emb_Ham), 464-558 (two-body part:
+get_emb_eri_gso), 560-726 (one-body part) and libdmet/routine/spinless_helper.py:31-46, 349-438.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""
+import numpy as np
+
+from . import eri_transform
+from .slater import Integral, transform_trans_inv_k as fold_generalised, _get_jk
+
+
+def separate_basis(basis):
+    half = basis.shape[1] // 2
+    return basis[:, :half], basis[:, half:]
+
+
+def transform_trans_inv_k(basis_ka, basis_kb, H_k):
+    """Re sum_k [Ba^+ H_aa Ba + Bb^+ H_bb Bb (+ Ba^+ H_ab Bb + h.c.)] / nkpts   (spinless_helper.py:349-381)"""
+    H_k = np.asarray(H_k)
+    assert H_k.ndim == 4 and H_k.shape[0] in (2, 3)
+    tot = np.einsum("kpm,kpq,kqn->mn", basis_ka.conj(), H_k[0], basis_ka)
+    tot = tot + np.einsum("kpm,kpq,kqn->mn", basis_kb.conj(), H_k[1], basis_kb)
+    if H_k.shape[0] == 3:
+        ab = np.einsum("kpm,kpq,kqn->mn", basis_ka.conj(), H_k[2], basis_kb)
+        tot = tot + ab + ab.conj().T
+    return tot.real / float(len(basis_ka))
+
+
+def transform_local(basis_Ra, basis_Rb, H):
+    """spinless_helper.py:383-409"""
+    H = np.asarray(H)
+    res = np.einsum("Rpm,pq,Rqn->mn", basis_Ra.conj(), H[0], basis_Ra)
+    res = res + np.einsum("Rpm,pq,Rqn->mn", basis_Rb.conj(), H[1], basis_Rb)
+    if H.shape[0] == 3:
+        ab = np.einsum("Rpm,pq,Rqn->mn", basis_Ra.conj(), H[2], basis_Rb)
+        res = res + ab + ab.conj().T
+    return res
+
+
+def transform_imp(basis_Ra, basis_Rb, H):
+    """spinless_helper.py:411-438"""
+    return transform_local(basis_Ra[:1], basis_Rb[:1], H)
+
+
+def get_emb_Ham(lattice, basis, vcor, mu, local=True, int_bath=True, add_vcor=False, **kwargs):
+    """spinless.py:433-726, interacting bath + Hartree-Fock"""
+    assert int_bath and not lattice.is_model
+    basis = np.asarray(basis)
+    nao, nb = lattice.nscsites, basis.shape[-1]
+    H2 = kwargs.get("H2_given", None)
+    if H2 is None:
+        H2 = eri_transform.get_emb_eri_gso(lattice.cell, lattice.df, C_ao_lo=lattice.C_ao_lo, basis=basis,
+                                           kscaled_center=kwargs.get("kscaled_center", None),
+                                           symmetry=lattice.eri_symmetry,
+                                           t_reversal_symm=kwargs.get("t_reversal_symm", True))
+    basis_k = lattice.R2k_basis(basis)
+    Ra, Rb = separate_basis(basis)
+    ka, kb = separate_basis(basis_k)
+    hcore_k = kwargs.get("hcore_custom", None)
+    hcore_emb = transform_trans_inv_k(ka, kb, lattice.getH1(kspace=True) if hcore_k is None else hcore_k)
+    ovlp_emb = transform_trans_inv_k(ka, kb, lattice.get_ovlp(kspace=True))
+    rdm1_emb = fold_generalised(basis_k, lattice.rdm1_lo_k)
+    H1 = transform_trans_inv_k(ka, kb, lattice.fock_hf_lo_k)
+    if kwargs.get("hcore_add", None) is not None:
+        H1 = H1 + transform_imp(Ra, Rb, kwargs["hcore_add"])
+    vj, vk = _get_jk(rdm1_emb, H2)
+    H1 = H1 - (vj[0] - vk[0])
+    lattice.JK_core = H1 - hcore_emb
+    mu_mat = np.zeros((2, nao, nao))
+    np.fill_diagonal(mu_mat[0], -mu)
+    np.fill_diagonal(mu_mat[1], mu)
+    H1 = H1 + transform_local(Ra, Rb, mu_mat)
+    if add_vcor:
+        H1 = H1 + transform_local(Ra, Rb, vcor.get())
+        if not kwargs.get("fitting", False):
+            H1 = H1 - transform_imp(Ra, Rb, vcor.get())
+        if lattice.get_JK_imp() is not None:
+            H1 = H1 - transform_imp(Ra, Rb, lattice.get_JK_imp())
+    H0 = lattice.getH0() + kwargs.get("H0_add", 0.0)
+    return Integral(nb, True, False, H0, {"cd": np.asarray(H1)[None]}, {"ccdd": H2}, ovlp=ovlp_emb), None
+
+
+embHam = get_emb_Ham

@@ -183,7 +183,32 @@ def gen_gso():
         save(name, **out)
 
 
+def gen_gso_embham():
+    """GSO embedding Hamiltonian through the reference's libdmet.routine.spinless.get_emb_Ham (spinless.py:433-726)"""
+    import libdmet.routine.spinless as ref_spinless
+    import libdmet.system.fourier as ref_f
+    from helpers import GSOLattice, gso_basis
+
+    class Vcor(object):
+        def islocal(self):
+            return True
+
+    for name, (kmesh, nao, naux, nemb, sym) in {"gso_embham_113": ([1, 1, 3], 3, 8, 5, 4),
+                                                 "gso_embham_221": ([2, 2, 1], 3, 7, 6, 1)}.items():
+        gdf, C, _ = problem(kmesh, nao, naux, 2, spin=2)
+        gdf.cell = GoldenCell(nao)
+        mydf = ref_gdf(gdf, name)
+        Lat = GSOLattice(gdf, C, ref_f, eri_symmetry=sym)
+        Lat.df = mydf
+        basis = gso_basis(kmesh, nao, nemb)
+        Ham, _ = ref_spinless.get_emb_Ham(Lat, basis, Vcor(), 0.3)
+        save(name, kmesh=np.array(kmesh), nao=nao, naux=naux, nemb=nemb, sym=sym, gdf_seed=gdf.seed,
+             gdf_scale=gdf.scale, C_ao_lo=C, basis=basis, mu=0.3, H1=Ham.H1["cd"], H2=Ham.H2["ccdd"],
+             ovlp=Ham.ovlp, H0=Ham.H0, JK_core=Lat.JK_core)
+
+
 if __name__ == "__main__":
+    gen_gso_embham()
     gen_gso()
     gen_eri()
     gen_fourier_basis()

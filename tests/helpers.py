@@ -67,3 +67,60 @@ def mean_field(kmesh, nao, nocc, spin=1, seed=0):
         vhf = synthetic.make_hermitian_k(kmesh, nao, seed=500 + seed, scale=0.3, spin=spin)
         rdm1 = np.asarray([synthetic.make_rdm1_k(hcore + vhf[s], nocc + (1 - s)) for s in range(spin)])
     return hcore, ovlp, vhf, rdm1
+
+
+class GSOLattice(object):
+    """duck-typed lattice for the generalised-spin-orbital embedding Hamiltonian: (3, nkpts, nao, nao) stacks
+    (aa, bb, ab) for hcore / ovlp / fock_hf and one generalised (nkpts, 2 nao, 2 nao) density matrix, all seeded.
+    `fourier_mod` supplies R2k (oracle.fourier or libdmet_preview_b200.fourier)."""
+
+    def __init__(self, gdf, C_ao_lo, fourier_mod, eri_symmetry=4, seed=0, H0=0.5):
+        self.kmesh = list(gdf.kmesh)
+        self.cell, self.df, self.C_ao_lo = gdf.cell, gdf, np.asarray(C_ao_lo)
+        self.nscsites = self.nao = gdf.nao
+        self.ncells = self.nkpts = len(gdf.kpts_scaled)
+        self.is_model = False
+        self.eri_symmetry = eri_symmetry
+        self.use_hcore_as_emb_ham = False
+        self.JK_core = None
+        self._H0 = H0
+        self._f = fourier_mod
+        nao = gdf.nao
+
+        def stack3(sd, scale):
+            aa = synthetic.make_hermitian_k(self.kmesh, nao, seed=sd, scale=scale)
+            bb = -synthetic.make_hermitian_k(self.kmesh, nao, seed=sd + 1, scale=scale)
+            big = synthetic.make_hermitian_k(self.kmesh, 2 * nao, seed=sd + 2, scale=0.2 * scale)
+            return np.asarray((aa, bb, big[:, :nao, nao:]))
+        self.hcore_lo_k = stack3(600 + seed, 1.0)
+        self.fock_hf_lo_k = self.hcore_lo_k + stack3(610 + seed, 0.3)
+        eye = np.asarray([np.eye(nao, dtype=np.complex128)] * self.nkpts)
+        self.ovlp_lo_k = np.asarray((eye, eye, 0 * eye))
+        self.rdm1_lo_k = synthetic.make_rdm1_k(synthetic.make_hermitian_k(self.kmesh, 2 * nao, seed=620 + seed), nao)
+
+    def R2k_basis(self, basis):
+        return self._f.R2k(basis, self.kmesh)
+
+    def getH1(self, kspace=True):
+        return self.hcore_lo_k
+
+    def getFock(self, kspace=True):
+        return self.fock_hf_lo_k
+
+    def get_ovlp(self, kspace=True):
+        return self.ovlp_lo_k
+
+    def get_JK_imp(self):
+        return None
+
+    getImpJK = get_JK_imp
+
+    def getH0(self):
+        return self._H0
+
+
+def gso_basis(kmesh, nao, nemb, seed=0):
+    """real orthonormal GSO basis (ncells, 2 nao, nemb)"""
+    nk = int(np.prod(kmesh))
+    q, _ = np.linalg.qr(np.random.default_rng(700 + seed).standard_normal((nk * 2 * nao, nemb)))
+    return q.reshape(nk, 2 * nao, nemb)

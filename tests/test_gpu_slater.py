@@ -121,3 +121,29 @@ def test_h2_scaling_kernels(dev):
     assert np.array_equal(slater.get_H1_scaled(h.copy(), imp), osl.get_H1_scaled(h.copy(), imp))
     with pytest.raises(ValueError):
         slater.get_H2_scaled(rng.standard_normal((4, 4)), imp)
+
+
+def test_gso_embham_and_helpers(dev):
+    """spinless helpers and the GSO embedding Hamiltonian at a less trivial size against the oracle"""
+    from helpers import GSOLattice, gso_basis
+    from libdmet_preview_b200 import spinless, fourier
+    from oracle import spinless as osp, fourier as of
+    kmesh, nao, naux, nemb = [2, 1, 3], 5, 13, 9
+    gdf, C, _ = problem(kmesh, nao, naux, 2, spin=2)
+    L1 = GSOLattice(gdf, C, fourier)
+    L2 = GSOLattice(gdf, C, of)
+    basis = gso_basis(kmesh, nao, nemb)
+    bk = of.R2k(basis, kmesh)
+    ka, kb = osp.separate_basis(bk)
+    for H in (L1.hcore_lo_k, L1.hcore_lo_k[:2]):
+        assert np.abs(spinless.transform_trans_inv_k(ka, kb, H) - osp.transform_trans_inv_k(ka, kb, H)).max() < 1e-11
+    Ra, Rb = osp.separate_basis(basis)
+    v = np.random.default_rng(1).standard_normal((3, nao, nao))
+    assert np.abs(spinless.transform_local(Ra, Rb, v) - osp.transform_local(Ra, Rb, v)).max() < 1e-13
+    assert np.abs(spinless.transform_imp(Ra, Rb, v) - osp.transform_imp(Ra, Rb, v)).max() < 1e-13
+    Ham, _ = spinless.embHam(L1, basis, None, -0.2, hcore_add=v)
+    Ref, _ = osp.embHam(L2, basis, None, -0.2, hcore_add=v)
+    assert np.abs(Ham.H2["ccdd"] - Ref.H2["ccdd"]).max() < TOL and np.abs(Ham.H1["cd"] - Ref.H1["cd"]).max() < TOL
+    assert np.abs(L1.JK_core - L2.JK_core).max() < TOL
+    with pytest.raises(NotImplementedError):
+        spinless.embHam(L1, basis, None, 0.0, int_bath=False)
