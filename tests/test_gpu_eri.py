@@ -157,3 +157,38 @@ def test_gso_eri(dev):
         gdf.kmesh, gdf.kpts_scaled))
     via_k = et.get_emb_eri_gso(gdf.cell, gdf, C_ao_lo=C, basis_k=bk, nsplit=2, group=3)
     assert np.abs(via_k - ref).max() < TOL
+
+
+def test_resident_gdf_cache(dev):
+    """a GDF kept resident in HBM across calls (DMET iterations reuse the same tensor): first build fills the store,
+    later builds read it in place; a budget smaller than the tensor falls back to streaming for the rest"""
+    from libdmet_preview_b200 import eri_transform as et
+    from oracle import eri_transform as oe
+    gdf, C, basis = problem([1, 2, 2], 8, 22, 7)
+    ref = oe.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+
+    class HostOnly(object):          # hides the device generator: blocks come from host memory
+        def __init__(self, g):
+            self.g = g
+            self.kpts_scaled, self.kmesh, self.nao, self.naux, self.cell = g.kpts_scaled, g.kmesh, g.nao, g.naux, g.cell
+            self.loads = 0
+
+        def load(self, ki, kj):
+            self.loads += 1
+            return self.g.load(ki, kj)
+
+    for budget in (None, 5 * 22 * 8 * 8 * 16):          # everything resident / only 5 blocks fit
+        host = HostOnly(gdf)
+        res = et.ResidentGDF(host, max_bytes=budget)
+        st1, st2 = {}, {}
+        e1 = et.get_emb_eri(gdf.cell, res, C_ao_lo=C, basis=basis, stats=st1)
+        n1 = host.loads
+        e2 = et.get_emb_eri(gdf.cell, res, C_ao_lo=C, basis=basis * 1.0, stats=st2, nsplit=1)
+        assert np.abs(e1 - ref).max() < TOL and np.abs(e2 - ref).max() < TOL
+        if budget is None:
+            assert host.loads == n1 and st2["h2d_bytes"] == 0          # second build touched no host block
+        else:
+            assert host.loads > n1 and 0 < st2["h2d_bytes"] < st1["h2d_bytes"] + 1
+        res.release()
+    syn = et.ResidentGDF(gdf)
+    assert np.abs(et.get_emb_eri(gdf.cell, syn, C_ao_lo=C, basis=basis) - ref).max() < TOL

@@ -168,3 +168,33 @@ def test_gemm_pipeline_many_tiles_per_cta(dev):
         assert np.abs(got - refz).max() < 1e-10
         first = got if first is None else first
         assert np.array_equal(got, first)
+
+
+def test_eri_pipeline_misuse_is_reported(dev):
+    """error convention of the C ABI: negative status + message, surfaced as LdmError (no crash, no silent result)"""
+    import ctypes as C
+    from libdmet_preview_b200._lib import LdmError, check
+    from libdmet_preview_b200 import eri_transform as et, synthetic
+    gdf = synthetic.SyntheticGDF([1, 1, 2], 4, 6)
+    CT = et.build_CT(gdf, synthetic.make_C_ao_lo([1, 1, 2], 4))
+    eri = dev.zeros((1, 10, 10))
+    with et.EriBuild(CT, gdf.naux, eri, 2, 2) as b:
+        with pytest.raises(LdmError):
+            et.EriBuild(CT, gdf.naux, eri, 2, 2)                 # a second build on the same handle
+        with pytest.raises(LdmError):
+            b.end_kl(1)                                          # transfer momentum without blocks
+        with pytest.raises(LdmError):
+            b.block_store(0, 0, 0, 0)                            # no resident store registered
+        with pytest.raises(LdmError):
+            b.block_synth(0, 7, 0, gdf.keys(0, 0), gdf.scale)    # k index out of range
+        with pytest.raises(LdmError):
+            check(dev.lib.ldm_eri_set_mode(dev.h, 1))            # GSO mode needs two spin flavours
+        b.block_synth(0, 0, 0, gdf.keys(0, 0), gdf.scale)
+        with pytest.raises(LdmError):
+            b.end_kl(3)                                          # weight must be 0, 1 or 2
+        b.end_kl(1)
+        b.finish()
+    with pytest.raises(LdmError):
+        check(dev.lib.ldm_eri_finish(dev.h))                     # no build open
+    msg = dev.lib.ldm_last_error()
+    assert isinstance(msg, bytes) and len(msg) > 0
