@@ -129,6 +129,12 @@ int ldm_synth_block(ldm_handle h, void* stream, void* out_d, int naux, int nao, 
 int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int neo, int nspin, const void* CT_d,
                   double* eri_d, int max_group, int kl_group);
 int ldm_eri_set_store(ldm_handle h, const void* store_d, int nslots);
+/* Optional diagnostic of the path without time reversal (weight-0 units): accumulate
+ * Im(Lambda^dagger Lambda) into imag_d (same shape as eri_d, zeroed by the caller), whose max-abs the reference logs
+ * and warns about above ERI_IMAG_TOL (eri_transform.py:390-395).  Call after ldm_eri_begin.                   */
+int ldm_eri_set_imag(ldm_handle h, double* imag_d);
+/* max |x_i| of a device array -> *out_h (synchronises the stream) */
+int ldm_max_abs(ldm_handle h, void* stream, const double* x_d, int64_t n, double* out_h);
 /* gso = 1 (nspin must be 2): the two "spins" are the alpha / beta halves of generalised spin orbitals and ONE ERI
  * block eri_d (1, npair, npair) is built from Lambda_a - Lambda_b  (reference: get_emb_eri_gso / _Lij_s4_to_eri_gso,
  * eri_transform.py:1104-1284).  Call right after ldm_eri_begin.                                              */

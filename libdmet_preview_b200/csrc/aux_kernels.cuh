@@ -495,6 +495,16 @@ __global__ void scale_s1_kernel(double* __restrict__ E, const int* __restrict__ 
     }
 }
 
+// max |x| of a real array (non-negative doubles order like their bit patterns)
+__global__ void max_abs_kernel(const double* __restrict__ x, long long n, unsigned long long* out) {
+    double m = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
 // unpack a packed symmetric vector to a full (n, n) matrix
 __global__ void unpack_sym_kernel(const double* __restrict__ packed, double* __restrict__ full, int n) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {

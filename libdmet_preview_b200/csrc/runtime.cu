@@ -646,6 +646,9 @@ struct EriPlan {
     long long xt_cols = 0;
     double xt_alpha = 0.0;
     int kl_in_panel = 0;
+    int nauxp = 0;               // column stride of one (re or im) part in the panel: naux rounded up to even
+    double* imag = nullptr;      // optional (spin_pair, npair, npair): Im(Lambda^dagger Lambda) of weight-0 units
+    std::vector<long long> imag_cols;   // panel columns of the weight-0 units waiting in the panel
     CUtensorMap tmRing, tmStore, tmCT, tmXt;
     bool have_store_map = false, have_ring_map = false;
     std::vector<PendingBlock> pending;
@@ -768,6 +771,24 @@ static int flush_panel(ldm_handle h) {
                           K, p->eri + 2 * eri_blk, p->npair, p->xt_alpha, 1, 1);
         if (rc) return rc;
     }
+    // imaginary part of Lambda^dagger Lambda for the units built without time reversal (diagnostic of
+    // eri_transform.py:390-395):  Im[x,y] += Re_x^T Im_y - Im_x^T Re_y  per transfer momentum
+    for (long long col : p->imag_cols) {
+        const int nsp = (p->nspin == 1 || p->gso) ? 1 : 2;
+        int blk = 0;
+        for (int x = 0; x < nsp; ++x)
+            for (int y = x; y < nsp; ++y, ++blk) {
+                const double* RX = p->XT + (size_t)x * xt_spin + col;
+                const double* RY = p->XT + (size_t)y * xt_spin + col;
+                rc = launch_dgemm(h, p->st, RX, p->ldx, RY + p->nauxp, p->ldx, (int)p->npair, (int)p->npair, p->naux,
+                                  p->imag + (size_t)blk * eri_blk, p->npair, 1.0, 1, 0);
+                if (rc) return rc;
+                rc = launch_dgemm(h, p->st, RX + p->nauxp, p->ldx, RY, p->ldx, (int)p->npair, (int)p->npair, p->naux,
+                                  p->imag + (size_t)blk * eri_blk, p->npair, -1.0, 1, 0);
+                if (rc) return rc;
+            }
+    }
+    p->imag_cols.clear();
     rc = plan_timed_end(p, 1);
     if (rc) return rc;
     p->xt_cols = 0;
@@ -792,7 +813,8 @@ int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int 
     p->G = std::max(1, max_group);
     p->klg = std::max(1, kl_group);
     p->npair = (long long)neo * (neo + 1) / 2;
-    p->ldx = ((long long)p->klg * 2 * naux + 15) / 16 * 16;
+    p->nauxp = naux + (naux & 1);
+    p->ldx = ((long long)p->klg * 2 * p->nauxp + 15) / 16 * 16;
     p->CT = static_cast<const double2*>(CT_d);
     p->eri = eri_d;
     p->cfg = &pick_zconfig(neo);
@@ -826,6 +848,33 @@ int ldm_eri_set_mode(ldm_handle h, int gso) {
     LDM_REQUIRE(!gso || h->plan->nspin == 2, "GSO mode needs two spin flavours");
     LDM_REQUIRE(h->plan->pending.empty() && h->plan->xt_cols == 0, "mode must be set before the first block");
     h->plan->gso = gso ? 1 : 0;
+    return 0;
+}
+
+int ldm_eri_set_imag(ldm_handle h, double* imag_d) {
+    LDM_REQUIRE(h && h->plan && imag_d, "arguments");
+    LDM_REQUIRE(h->plan->xt_cols == 0, "must be set before the first ldm_eri_end_kl");
+    h->plan->imag = imag_d;
+    return 0;
+}
+
+int ldm_max_abs(ldm_handle h, void* stream, const double* x_d, int64_t n, double* out_h) {
+    LDM_REQUIRE(h && x_d && out_h && n >= 0, "arguments");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    LDM_CUDA_OK(cudaMemsetAsync(h->imag_d, 0, sizeof(unsigned long long), st));
+    if (n > 0) {
+        max_abs_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(x_d, (long long)n,
+                                                                                               h->imag_d);
+        LDM_CUDA_OK(cudaGetLastError());
+        h->launches++;
+    }
+    unsigned long long bits = 0;
+    LDM_CUDA_OK(cudaMemcpyAsync(&bits, h->imag_d, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    LDM_CUDA_OK(cudaStreamSynchronize(st));
+    double v;
+    std::memcpy(&v, &bits, sizeof(v));
+    *out_h = v;
     return 0;
 }
 
@@ -918,14 +967,25 @@ int ldm_eri_end_kl(ldm_handle h, int weight) {
     if (rc) return rc;
     LDM_REQUIRE(p->sym_init || p->pln_init, "transfer momentum without blocks");
     const double alpha = weight == 2 ? 2.0 : 1.0;
-    const int ncols = (weight == 1 ? 1 : 2) * p->naux;
+    const int ncols = (weight == 1 ? 1 : 2) * p->nauxp;
     if (p->xt_cols > 0 && (p->xt_alpha != alpha || p->xt_cols + ncols > p->ldx || p->kl_in_panel >= p->klg)) {
         rc = flush_panel(h);
         if (rc) return rc;
     }
     p->xt_alpha = alpha;
     const long long col_re = p->xt_cols;
-    const long long col_im = weight == 1 ? -1 : p->xt_cols + p->naux;
+    const long long col_im = weight == 1 ? -1 : p->xt_cols + p->nauxp;
+    if (p->nauxp != p->naux) {      // odd naux: the pad column of each part must not carry stale data
+        for (int s = 0; s < (p->gso ? 1 : p->nspin); ++s)
+            for (int part = 0; part < (weight == 1 ? 1 : 2); ++part) {
+                const long long c0 = p->xt_cols + (long long)part * p->nauxp + p->naux;
+                fill_cols_kernel<<<64, 256, 0, p->st>>>(p->XT + (size_t)s * p->npair * p->ldx, p->npair, p->ldx, c0,
+                                                       c0 + 1);
+                LDM_CUDA_OK(cudaGetLastError());
+                h->launches++;
+            }
+    }
+    if (weight == 0 && p->imag) p->imag_cols.push_back(p->xt_cols);
     const int t = (p->neo + 15) / 16;
     const size_t s_spin = (size_t)p->naux * p->neo * p->neo;
     if (p->gso) {

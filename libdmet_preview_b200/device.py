@@ -196,6 +196,12 @@ class Device(object):
         check(self.lib.ldm_scale_eri(self.h, self.stream, _ptr(eri), n, int(symmetry), _ptr(weights)))
         return eri
 
+    def max_abs(self, x):
+        assert x.dtype == torch.float64 and x.is_contiguous()
+        out = C.c_double(0.0)
+        check(self.lib.ldm_max_abs(self.h, self.stream, _ptr(x), x.numel(), C.byref(out)))
+        return out.value
+
     def synth_block(self, out, naux, nao, keys, scale, aux_offset=0):
         check(self.lib.ldm_synth_block(self.h, self.stream, _ptr(out), naux, nao, int(aux_offset), int(keys[0]),
                                        int(keys[1]), int(keys[2]), int(keys[3]), float(scale)))

@@ -235,7 +235,7 @@ def build_CT(provider, C_ao_lo=None, basis=None, C_ao_eo=None, unit_eri=False):
 class EriBuild(object):
     """One open `ldm_eri_*` build on the process-wide handle (context manager)."""
 
-    def __init__(self, CT, naux, eri, group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, gso=False):
+    def __init__(self, CT, naux, eri, group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, gso=False, imag=None):
         self.dev = get_device()
         spin, nkpts, nemb, nao = CT.shape
         group, kl_group = auto_groups(nao, naux, nemb, spin, group, kl_group)
@@ -248,6 +248,9 @@ class EriBuild(object):
         self.open = True
         if gso:
             check(self.dev.lib.ldm_eri_set_mode(self.dev.h, 1))
+        if imag is not None:
+            self._imag = imag
+            check(self.dev.lib.ldm_eri_set_imag(self.dev.h, _ptr(imag)))
 
     def __enter__(self):
         return self
@@ -362,7 +365,7 @@ def finalize_eri(eri, nemb, symmetry, nspin):
 
 def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL, kscaled_center=None,
                    source="auto", group=DEFAULT_GROUP, kl_group=DEFAULT_KL_GROUP, items=None, schedule=None,
-                   stores=None, store_map=None, stats=None, gso=False):
+                   stores=None, store_map=None, stats=None, gso=False, imag=None):
     """Stages 1-3 on the device.  Returns the (spin_pair, npair, npair) tensor holding the LOWER triangles of the
     symmetric blocks, summed over `items` = [(unit index, l0, l1)] (default: every unit, full aux range).
     stores: {(l0, l1): resident device tensor (nslots, l1-l0, nao, nao)} for source "store"."""
@@ -382,7 +385,7 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
     for (l0, l1) in ranges:                 # one build per distinct aux range (workspaces are sized by it)
         sub = [it for it in items if (it[1], it[2]) == (l0, l1)]
         sub.sort(key=lambda it: (schedule.units[it[0]][1], it[0]))     # equal weights share stage-3 launches
-        with EriBuild(CT, l1 - l0, eri, group, kl_group, gso=gso) as b:
+        with EriBuild(CT, l1 - l0, eri, group, kl_group, gso=gso, imag=imag) as b:
             if stores is not None:
                 b.set_store(stores[(l0, l1)])
             elif isinstance(provider, ResidentGDF) and source in ("auto", "resident"):
@@ -404,6 +407,25 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
     return eri
 
 
+def _imag_buffer(t_reversal_symm, kwargs, spin_pair, nemb):
+    """without time reversal the reference forms the complex Lambda^dagger Lambda, logs max|imag| and warns above
+    ERI_IMAG_TOL before dropping it (eri_transform.py:390-396); `check_imag=False` skips that diagnostic"""
+    if t_reversal_symm or not kwargs.get("check_imag", True):
+        return None
+    npair = nemb * (nemb + 1) // 2
+    return get_device().zeros((spin_pair, npair, npair))
+
+
+def _report_imag(imag, kwargs):
+    if imag is None:
+        return
+    norm = get_device().max_abs(imag)
+    if isinstance(kwargs.get("stats", None), dict):
+        kwargs["stats"]["eri_imag_norm"] = norm
+    if norm > ERI_IMAG_TOL:
+        warnings.warn("ERI has imaginary part > %s (%s)" % (ERI_IMAG_TOL, norm))
+
+
 def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_center=None, symmetry=4,
                          max_memory=None, C_ao_eo=None, kconserv_tol=KPT_DIFF_TOL, unit_eri=False, swap_idx=None,
                          t_reversal_symm=True, incore=True, fout="H2.h5", return_device=False, **kwargs):
@@ -420,10 +442,12 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
     CT = build_CT(provider, C_ao_lo, basis, C_ao_eo, unit_eri)
     spin, nkpts, nemb, nao = CT.shape
     schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
+    imag = _imag_buffer(t_reversal_symm, kwargs, spin * (spin + 1) // 2, nemb)
     eri = emb_eri_device(provider, CT, schedule=schedule,
                          items=work_items(schedule, provider.naux, kwargs.get("nsplit", 1)),
                          source=kwargs.get("source", "auto"), group=kwargs.get("group", DEFAULT_GROUP),
-                         kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None))
+                         kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None), imag=imag)
+    _report_imag(imag, kwargs)
     eri = finalize_eri(eri, nemb, symmetry, spin)
     if return_device:
         return eri
@@ -527,9 +551,12 @@ def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_cen
     CT = build_CT_gso(provider, C_ao_lo, basis, basis_k, unit_eri)
     nemb = CT.shape[2]
     schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
+    imag = _imag_buffer(t_reversal_symm, kwargs, 1, nemb)
     eri = emb_eri_device(provider, CT, schedule=schedule,
                          items=work_items(schedule, provider.naux, kwargs.get("nsplit", 1)),
                          source=kwargs.get("source", "auto"), group=kwargs.get("group", DEFAULT_GROUP),
-                         kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None), gso=True)
+                         kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None), gso=True,
+                         imag=imag)
+    _report_imag(imag, kwargs)
     eri = finalize_eri(eri, nemb, symmetry, 1)
     return eri if return_device else eri.cpu().numpy()

@@ -164,7 +164,7 @@ def _chunk_rows(mydf, max_memory):
 
 def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_center=None, symmetry=4,
                          max_memory=None, C_ao_eo=None, kconserv_tol=KPT_DIFF_TOL, unit_eri=False, swap_idx=None,
-                         t_reversal_symm=True, incore=True, fout="H2.h5", kL_subset=None, restore=True):
+                         t_reversal_symm=True, incore=True, fout="H2.h5", kL_subset=None, restore=True, info=None):
     """eri_transform.py:235-399 (incore).  `kL_subset` / `restore=False` are oracle-only hooks for the multi-rank
     tests (the reference's MPI variant shards the same kL loop, eri_transform_mpi.py:151-157)."""
     assert incore, "oracle restates the incore branch only"
@@ -184,6 +184,8 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
             continue
         Lij_s4 = _accumulate_Lij_s4(mydf, C_ao_emb, kL, kscaled, kconserv_tol, t_reversal_symm, blksize)
         _Lij_s4_to_eri(Lij_s4, eri, weight=weights[kL], t_reversal_symm=t_reversal_symm)
+    if info is not None and not t_reversal_symm:
+        info["eri_imag_norm"] = max_abs(eri.imag)          # what the reference logs / warns about (l.390-395)
     if not restore:
         return eri
     return eri_restore(eri.real, symmetry, nemb)

@@ -192,3 +192,31 @@ def test_resident_gdf_cache(dev):
         res.release()
     syn = et.ResidentGDF(gdf)
     assert np.abs(et.get_emb_eri(gdf.cell, syn, C_ao_lo=C, basis=basis) - ref).max() < TOL
+
+
+def test_imaginary_part_diagnostic(dev):
+    """without time reversal the reference forms the complex Lambda^dagger Lambda, logs max|imag| and warns above 1e-6
+    (eri_transform.py:390-396).  Physical inputs give ~0; coefficients without time-reversal structure do not."""
+    import warnings
+    from libdmet_preview_b200 import eri_transform as et
+    from oracle import eri_transform as oe
+    gdf, C, basis = problem([1, 2, 2], 7, 15, 6, spin=2)          # odd naux exercises the padded panel columns
+    st = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        got = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, t_reversal_symm=False, stats=st)
+    info = {}
+    ref = oe.get_emb_eri_fast_gdf(gdf.cell, gdf, C_ao_lo=C, basis=basis, t_reversal_symm=False, info=info)
+    assert np.abs(got - ref).max() < TOL and st["eri_imag_norm"] < 1e-12 and info["eri_imag_norm"] < 1e-12
+    rng = np.random.default_rng(0)
+    C_bad = rng.standard_normal((2, 4, 7, 5)) + 1j * rng.standard_normal((2, 4, 7, 5))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        got = et.get_emb_eri_fast_gdf(gdf.cell, gdf, C_ao_eo=C_bad, t_reversal_symm=False, stats=st)
+    ref = oe.get_emb_eri_fast_gdf(gdf.cell, gdf, C_ao_eo=C_bad, t_reversal_symm=False, info=info)
+    assert np.abs(got - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
+    assert info["eri_imag_norm"] > 1e-3
+    assert abs(st["eri_imag_norm"] - info["eri_imag_norm"]) < 1e-10 * max(1.0, info["eri_imag_norm"])
+    assert any("imaginary part" in str(x.message) for x in w)
+    quiet = et.get_emb_eri_fast_gdf(gdf.cell, gdf, C_ao_eo=C_bad, t_reversal_symm=False, check_imag=False)
+    assert np.array_equal(quiet, got)
