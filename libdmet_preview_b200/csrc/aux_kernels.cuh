@@ -350,10 +350,12 @@ mirror_lower_kernel(double* __restrict__ E, int n, long long ld) {
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri_idx(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(256)
 restore_s1_kernel(const double* __restrict__ eri4, double* __restrict__ out, int n, long long npair) {
-    // one CTA per packed row P = (i >= j): the row is staged in shared memory once and unpacked into the two
-    // (n, n) slabs out[i][j][:][:] and out[j][i][:][:] with coalesced writes
+    // one CTA per packed row P = (i >= j): the row is staged in shared memory once (STAGED; rows beyond 200 KB are
+    // gathered from global memory / L2 instead) and unpacked into the two (n, n) slabs out[i][j][:][:] and
+    // out[j][i][:][:] with coalesced writes
     extern __shared__ double s1row[];
     const long long P = blockIdx.x;
     int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
@@ -361,13 +363,16 @@ restore_s1_kernel(const double* __restrict__ eri4, double* __restrict__ out, int
     while ((long long)i * (i + 1) / 2 > P) --i;
     const int j = (int)(P - (long long)i * (i + 1) / 2);
     const double* row = eri4 + P * npair;
-    for (long long q = threadIdx.x; q < npair; q += blockDim.x) s1row[q] = row[q];
-    __syncthreads();
+    if (STAGED) {
+        for (long long q = threadIdx.x; q < npair; q += blockDim.x) s1row[q] = row[q];
+        __syncthreads();
+    }
+    const double* src = STAGED ? s1row : row;
     double* dst_ij = out + ((long long)i * n + j) * n * n;
     double* dst_ji = out + ((long long)j * n + i) * n * n;
     for (int kl = threadIdx.x; kl < n * n; kl += blockDim.x) {
         const int k = kl / n, l = kl - k * n;
-        const double v = s1row[tri_idx(k, l)];
+        const double v = src[tri_idx(k, l)];
         dst_ij[kl] = v;
         if (i != j) dst_ji[kl] = v;
     }
@@ -403,11 +408,14 @@ __global__ void jk_pack_dm_kernel(const double* __restrict__ D, double* __restri
     }
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(256)
 jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, const double* __restrict__ dd,
                double* __restrict__ vj_packed, double* __restrict__ kpart, int n, long long npair, int with_k) {
-    extern __shared__ double srow[];     // [npair] packed row, [n] D[i,:], [n] D[j,:], [8] reduction
-    double* dI = srow + npair;
+    // STAGED: the packed row lives in shared memory; otherwise (rows beyond 200 KB) it is re-read from global / L2
+    extern __shared__ double jk_smem[];  // [npair if STAGED] packed row, [n] D[i,:], [n] D[j,:], [8] reduction
+    double* srow = jk_smem;
+    double* dI = jk_smem + (STAGED ? npair : 0);
     double* dJ = dI + n;
     double* red = dJ + n;
     const long long P = blockIdx.x;
@@ -420,9 +428,10 @@ jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, co
     double part = 0.0;
     for (long long q = threadIdx.x; q < npair; q += blockDim.x) {
         const double v = row[q];
-        srow[q] = v;
+        if (STAGED) srow[q] = v;
         part = fma(v, dd[q], part);
     }
+    const double* src = STAGED ? srow : row;
     for (int l = threadIdx.x; l < n; l += blockDim.x) {
         dI[l] = D[(size_t)i * n + l];
         dJ[l] = D[(size_t)j * n + l];
@@ -442,7 +451,7 @@ jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, co
     // neighbouring threads read neighbouring words.
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         double y1 = 0.0, y2 = 0.0;
-        const double* seg = srow + (size_t)k * (k + 1) / 2;
+        const double* seg = src + (size_t)k * (k + 1) / 2;
         for (int l = 0; l <= k; ++l) {
             const double m = seg[l];
             y1 = fma(m, dI[l], y1);
@@ -450,7 +459,7 @@ jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, co
         }
         size_t off = (size_t)(k + 1) * (k + 2) / 2 + k;       // element (l = k + 1, k)
         for (int l = k + 1; l < n; ++l) {
-            const double m = srow[off];
+            const double m = src[off];
             y1 = fma(m, dI[l], y1);
             y2 = fma(m, dJ[l], y2);
             off += (size_t)l + 1;

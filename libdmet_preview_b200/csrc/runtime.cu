@@ -183,12 +183,12 @@ static int ensure_attrs(ldm_handle h) {
         LDM_CUDA_OK(cudaFuncSetAttribute((const void*)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)dgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      DTile::SMEM));
-    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      200 * 1024));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)pack_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      16 * 16 * 17 * 16));
-    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)restore_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     200 * 1024));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)restore_s1_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     h->attrs_set = true;
     return 0;
 }
@@ -536,8 +536,11 @@ int ldm_ksum_real(ldm_handle h, void* stream, const void* in_d, double* out_d, i
 int ldm_restore_s1(ldm_handle h, void* stream, const double* eri4_d, double* out_d, int n) {
     LDM_CUDA_OK(cudaSetDevice(h->device));
     long long npair = (long long)n * (n + 1) / 2;
-    LDM_REQUIRE((size_t)npair * 8 <= 200 * 1024, "neo too large for the shared-memory s4 -> s1 kernel");
-    restore_s1_kernel<<<(unsigned)npair, 256, (size_t)npair * 8, (cudaStream_t)stream>>>(eri4_d, out_d, n, npair);
+    if ((size_t)npair * 8 <= 200 * 1024)
+        restore_s1_kernel<true><<<(unsigned)npair, 256, (size_t)npair * 8, (cudaStream_t)stream>>>(eri4_d, out_d, n,
+                                                                                                 npair);
+    else
+        restore_s1_kernel<false><<<(unsigned)npair, 256, 0, (cudaStream_t)stream>>>(eri4_d, out_d, n, npair);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -558,8 +561,8 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
     LDM_CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     long long npair = (long long)n * (n + 1) / 2;
-    size_t smem = (size_t)(npair + 2 * n + 8) * 8;
-    LDM_REQUIRE(smem <= 200 * 1024, "neo too large for the shared-memory J/K kernel");
+    const bool staged = (size_t)(npair + 2 * n + 8) * 8 <= 200 * 1024;
+    size_t smem = (size_t)((staged ? npair : 0) + 2 * n + 8) * 8;
     size_t need = (size_t)npair * 16 + (size_t)npair * 2 * n * 8;
     if (h->jk_part_bytes < need) {
         if (h->jk_part_d) LDM_CUDA_OK(cudaFree(h->jk_part_d));
@@ -571,8 +574,12 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
     double* kpart = dd + npair;
     jk_pack_dm_kernel<<<(unsigned)std::min<long long>((npair + 255) / 256, 1024), 256, 0, st>>>(dm_d, dd, n);
     LDM_CUDA_OK(cudaGetLastError());
-    jk_rows_kernel<<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair,
-                                                      vk_d != nullptr);
+    if (staged)
+        jk_rows_kernel<true><<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair,
+                                                                vk_d != nullptr);
+    else
+        jk_rows_kernel<false><<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair,
+                                                                 vk_d != nullptr);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
     unpack_sym_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(vj_packed, vj_d, n);

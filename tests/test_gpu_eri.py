@@ -220,3 +220,11 @@ def test_imaginary_part_diagnostic(dev):
     assert any("imaginary part" in str(x.message) for x in w)
     quiet = et.get_emb_eri_fast_gdf(gdf.cell, gdf, C_ao_eo=C_bad, t_reversal_symm=False, check_imag=False)
     assert np.array_equal(quiet, got)
+
+
+@pytest.mark.parametrize("kmesh,nao,naux,neo", [([1, 1, 2], 120, 9, 210), ([1, 1, 1], 1, 1, 1), ([2, 1, 1], 3, 1, 2)])
+def test_extreme_shapes(dev, kmesh, nao, naux, neo):
+    """neo > 200 (two N tiles per GEMM), and degenerate one-orbital / one-auxiliary problems"""
+    gdf, C, basis = problem(kmesh, nao, naux, neo)
+    got, ref = both(gdf, C_ao_lo=C, basis=basis)
+    assert got.shape == ref.shape and np.abs(got - ref).max() < TOL

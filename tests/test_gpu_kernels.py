@@ -198,3 +198,40 @@ def test_eri_pipeline_misuse_is_reported(dev):
         check(dev.lib.ldm_eri_finish(dev.h))                     # no build open
     msg = dev.lib.ldm_last_error()
     assert isinstance(msg, bytes) and len(msg) > 0
+
+
+def test_large_neo_fallbacks(dev):
+    """neo beyond the shared-memory row budget (npair * 8 B > 200 KB, neo > 225): s4 -> s1 and J/K fall back to
+    global-memory gathers; the GEMM splits N over several tiles"""
+    from oracle import pyscf_lib as olib
+    n = 232
+    npair = n * (n + 1) // 2
+    rng = np.random.default_rng(4)
+    e4 = rng.standard_normal((npair, npair))
+    e4d = dev.to_device(e4, torch.float64)
+    d = rng.standard_normal((n, n))
+    d = d + d.T
+    vj, vk = dev.jk_s4(e4d, dev.to_device(d, torch.float64))
+    e1 = dev.restore_s1(e4d, n).cpu().numpy()
+    idx = np.tril_indices(n)
+    tri = np.zeros((n, n), dtype=np.int64)
+    tri[idx] = np.arange(npair)
+    tri[(idx[1], idx[0])] = np.arange(npair)
+    for (i, j, k, l) in [(0, 0, 0, 0), (5, 200, 17, 3), (231, 7, 100, 231), (40, 41, 42, 43)]:
+        assert e1[i, j, k, l] == e4[tri[i, j], tri[k, l]]
+    dp = d + d.T
+    dp[np.diag_indices(n)] *= 0.5
+    rj = np.zeros((n, n))
+    rj[idx] = e4 @ dp[idx]
+    rj[(idx[1], idx[0])] = rj[idx]
+    assert np.abs(vj.cpu().numpy() - rj).max() < 1e-9
+    rk = np.einsum("ijkl,il->jk", e1, d)
+    assert np.abs(vk.cpu().numpy() - rk).max() < 1e-9
+
+
+def test_zgemm_many_n_tiles(dev):
+    rng = np.random.default_rng(6)
+    A, B = _z(rng, 1, 300, 33), _z(rng, 1, 450, 33)
+    out = dev.empty((300, 450), torch.complex128)
+    dev.zgemm_tn(dev.to_device(A, torch.complex128), dev.to_device(B, torch.complex128), [[0, 0, 0, 1]], out)
+    assert np.abs(out.cpu().numpy() - A[0] @ B[0].conj().T).max() < 1e-11
