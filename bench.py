@@ -153,7 +153,7 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     line = {"impl": "reference", "metric": "get_emb_eri_fp64_tflops", "value": val, "unit": "TFLOP/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128 GEMMs)",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(args, kmesh, nao, naux, neo, B, G),
             "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                              "sample": res["sample"] + "; numpy/OpenBLAS zgemm+dgemm, all host threads; the "
@@ -417,7 +417,7 @@ def run_ours(args):
 
     line = {"metric": "get_emb_eri_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128 GEMMs, DMMA)",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (seeded counter-based GDF tensor generated on the device; %d resident blocks per GPU, "
                     "the %d block pieces of this rank's schedule cycle over them)" % (nslots, len(my_blocks)),
             "config": dict(config_dict(args, kmesh, nao, naux, neo, B, G), parallelism="(kL, aux-range) work items sharded x%d, one NCCL reduce of the s4 ERI" % world,
