@@ -312,17 +312,51 @@ def _host_block(provider, ki, kj, l0, l1, naux_full):
     return L[l0:l1]                      # leading-index slice of a C-contiguous block: still contiguous
 
 
-def run_items(build, provider, schedule, items, source="auto", store_map=None):
+class _Prefetcher(object):
+    """Loads GDF blocks from the provider on a background thread, `depth` blocks ahead of the consumer -- the role
+    of `lib.map_with_prefetch` in the reference's `sr_loop` (eri_transform.py:223).  h5py / numpy release the GIL
+    while reading, so disk or page-cache latency overlaps the host->device copy and the kernels."""
+
+    def __init__(self, provider, requests, depth):
+        import queue
+        import threading
+        self.q = queue.Queue(maxsize=max(1, depth))
+        self.err = None
+
+        def work():
+            try:
+                for (ki, kj, l0, l1) in requests:
+                    self.q.put(_host_block(provider, ki, kj, l0, l1, provider.naux))
+            except BaseException as e:          # surfaced in the consumer
+                self.err = e
+                self.q.put(None)
+        self.th = threading.Thread(target=work, daemon=True)
+        self.th.start()
+
+    def next(self):
+        blk = self.q.get()
+        if blk is None and self.err is not None:
+            raise self.err
+        return blk
+
+
+def run_items(build, provider, schedule, items, source="auto", store_map=None, prefetch=2):
     """Feed the (k_i, k_j) blocks of `items` -- (unit index, l0, l1) with one common aux range -- to an open build.
-    source: "host"   provider.load(ki, kj)[l0:l1] -> host array -> H2D inside the call
-            "synth"  provider.keys(ki, kj) -> device generator (SyntheticGDF only)
-            "store"  store_map[(ki, kj, l0)] -> slot of the resident device store registered with build.set_store
-            "auto"   synth if the provider has .keys, else host"""
+    source: "host"      provider.load(ki, kj)[l0:l1] -> host array -> H2D inside the call (blocks are loaded
+                        `prefetch` ahead on a background thread)
+            "synth"     provider.keys(ki, kj) -> device generator (SyntheticGDF only)
+            "store"     store_map[(ki, kj, l0)] -> slot of the resident device store registered with build.set_store
+            "resident"  ResidentGDF: cached blocks in place, the rest streamed
+            "auto"      resident for a ResidentGDF, synth if the provider has .keys, else host"""
     if source == "auto":
         if isinstance(provider, ResidentGDF):
             source = "resident"
         else:
             source = "synth" if hasattr(provider, "keys") and hasattr(provider, "scale") else "host"
+    pre = None
+    if source == "host" and prefetch:
+        reqs = [(ki, kj, l0, l1) for (u, l0, l1) in items for (ki, kj, sym) in schedule.units[u][2]]
+        pre = _Prefetcher(provider, reqs, prefetch)
     for (u, l0, l1) in items:
         kL, weight, blocks = schedule.units[u]
         for (ki, kj, sym) in blocks:
@@ -333,7 +367,8 @@ def run_items(build, provider, schedule, items, source="auto", store_map=None):
                 else:
                     build.block_host(ki, kj, sym, _host_block(provider, ki, kj, l0, l1, provider.naux))
             elif source == "host":
-                build.block_host(ki, kj, sym, _host_block(provider, ki, kj, l0, l1, provider.naux))
+                blk = pre.next() if pre is not None else _host_block(provider, ki, kj, l0, l1, provider.naux)
+                build.block_host(ki, kj, sym, blk)
             elif source == "synth":
                 build.block_synth(ki, kj, sym, provider.keys(ki, kj), provider.scale, l0)
             elif source == "store":

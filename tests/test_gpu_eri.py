@@ -228,3 +228,32 @@ def test_extreme_shapes(dev, kmesh, nao, naux, neo):
     gdf, C, basis = problem(kmesh, nao, naux, neo)
     got, ref = both(gdf, C_ao_lo=C, basis=basis)
     assert got.shape == ref.shape and np.abs(got - ref).max() < TOL
+
+
+def test_host_prefetch_thread(dev):
+    """host blocks are loaded ahead on a background thread (the reference prefetches one chunk ahead,
+    eri_transform.py:223); order and results are unchanged, provider errors surface in the caller"""
+    import time
+    from libdmet_preview_b200 import eri_transform as et
+    gdf, C, basis = problem([1, 2, 2], 6, 12, 5)
+
+    class Slow(object):
+        def __init__(self, g, fail_at=None):
+            self.g, self.calls, self.fail_at = g, [], fail_at
+            self.kpts_scaled, self.kmesh, self.nao, self.naux, self.cell = g.kpts_scaled, g.kmesh, g.nao, g.naux, g.cell
+
+        def load(self, ki, kj):
+            self.calls.append((ki, kj))
+            if self.fail_at is not None and len(self.calls) == self.fail_at:
+                raise IOError("disk went away")
+            time.sleep(0.002)
+            return self.g.load(ki, kj)
+
+    ref = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+    slow = Slow(gdf)
+    got = et.get_emb_eri(gdf.cell, slow, C_ao_lo=C, basis=basis)
+    assert np.array_equal(got, ref) and len(slow.calls) == len(set(slow.calls)) == 10
+    with pytest.raises(IOError):
+        et.get_emb_eri(gdf.cell, Slow(gdf, fail_at=4), C_ao_lo=C, basis=basis)
+    # the handle is usable again after the failed build
+    assert np.array_equal(et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis), ref)
