@@ -35,6 +35,10 @@ WORKLOADS = {
     "mid": ([2, 2, 4], 200, 1000, 150),
     "small": ([2, 2, 2], 100, 500, 50),          # sweep minimum
     "tiny": ([1, 2, 3], 24, 64, 20),
+    # shapes of BASELINE.json configs[0..2] (sizes estimated in SURVEY.md section 8; 5th entry = number of spins)
+    "c1_hchain": ([1, 1, 3], 4, 30, 6),
+    "c2_graphene": ([3, 3, 1], 26, 150, 40),
+    "c3_nio_uhf": ([2, 2, 2], 78, 400, 106, 2),
     # BASELINE.json configs[4]: synthetic sweep nkpts 8-64, nao 100-300, naux 500-1500, neo 50-200
     "sweep_222_300_1500_200": ([2, 2, 2], 300, 1500, 200),
     "sweep_224_200_1000_100": ([2, 2, 4], 200, 1000, 100),
@@ -45,12 +49,18 @@ WORKLOADS = {
 }
 
 
+def workload(name):
+    w = WORKLOADS[name]
+    return (w[0], w[1], w[2], w[3], (w[4] if len(w) > 4 else 1))
+
+
 def flops(kmesh, nao, naux, neo, nspin=1):
     from libdmet_preview_b200.synthetic import trs_block_count
     B, G = trs_block_count(kmesh, True)
     npair = neo * (neo + 1) // 2
     F1 = 8.0 * naux * nao * neo * (nao + neo) * nspin * B
-    F3 = float(naux) * npair * (npair + 1) * G
+    # unrestricted: aa and bb are syrk products, ab a full product (= two syrk halves)
+    F3 = float(naux) * npair * (npair + 1) * G * (1 if nspin == 1 else 4)
     return F1, F3, B, G
 
 
@@ -137,11 +147,11 @@ def cpu_sample(kmesh, nao, naux, neo, nblocks=2, budget_s=25.0):
 
 
 def run_reference(args):
-    kmesh, nao, naux, neo = WORKLOADS[args.workload]
+    kmesh, nao, naux, neo, nspin = workload(args.workload)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    F1, F3, B, G = flops(kmesh, nao, naux, neo)
+    F1, F3, B, G = flops(kmesh, nao, naux, neo)      # the CPU sample times the restricted path
     times = []
     res = None
     for it in range(args.warmup + args.steps):
@@ -164,8 +174,9 @@ def run_reference(args):
 
 
 def config_dict(args, kmesh, nao, naux, neo, B, G):
-    return {"workload": "%s: get_emb_eri GDF restricted s4 time-reversal, kmesh %s nkpts %d nao %d naux %d neo %d "
-                        "(%d (ki,kj) blocks, %d Gram products)" % (args.workload, "x".join(map(str, kmesh)),
+    kind = "restricted" if workload(args.workload)[4] == 1 else "unrestricted"
+    return {"workload": "%s: get_emb_eri GDF %s s4 time-reversal, kmesh %s nkpts %d nao %d naux %d neo %d "
+                        "(%d (ki,kj) blocks, %d Gram products)" % (args.workload, kind, "x".join(map(str, kmesh)),
                                                                   int(np.prod(kmesh)), nao, naux, neo, B, G),
             "kmesh": kmesh, "nao": nao, "naux": naux, "neo": neo, "symmetry": 4, "t_reversal_symm": True}
 
@@ -216,24 +227,24 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = get_device(local_rank)
 
-    kmesh, nao, naux, neo = WORKLOADS[args.workload]
-    F1, F3, B, G = flops(kmesh, nao, naux, neo)
-    args.group, args.kl_group = et.auto_groups(nao, naux, neo, 1, args.group or None, args.kl_group or None)
+    kmesh, nao, naux, neo, nspin = workload(args.workload)
+    F1, F3, B, G = flops(kmesh, nao, naux, neo, nspin)
+    args.group, args.kl_group = et.auto_groups(nao, naux, neo, nspin, args.group or None, args.kl_group or None)
     gdf = synthetic.SyntheticGDF(kmesh, nao, naux, seed=2026)
-    C_ao_lo_h = synthetic.make_C_ao_lo(kmesh, nao, seed=1)
-    basis_h = synthetic.make_emb_basis(kmesh, nao, neo, seed=2)
+    C_ao_lo_h = synthetic.make_C_ao_lo(kmesh, nao, seed=1, spin=(nspin if nspin > 1 else None))
+    basis_h = synthetic.make_emb_basis(kmesh, nao, neo, seed=2, spin=nspin)
     C_ao_lo = dev.to_device(C_ao_lo_h, torch.complex128)
     basis = dev.to_device(basis_h, torch.float64)
     schedule = build_schedule(gdf.kpts_scaled, True)
-    my_items = ldist.rank_items(schedule, nao, naux, neo, 1, world)[rank]
+    my_items = ldist.rank_items(schedule, nao, naux, neo, nspin, world)[rank]
     my_blocks = [(l0, l1, blk) for (u, l0, l1) in my_items for blk in schedule.units[u][2]]
     my_rows = sum(l1 - l0 for (l0, l1, _) in my_blocks)           # GDF rows this rank transforms
 
     # ---- resident store of L blocks (inputs in HBM before the timed region) ----
     free_b, total_b = torch.cuda.mem_get_info()
     npair = neo * (neo + 1) // 2
-    work_b = (args.group * naux * neo * nao * 16 + 2 * naux * neo * neo * 16 +
-              npair * args.kl_group * 2 * naux * 8 + 2 * npair * npair * 8) + (6 << 30)
+    work_b = nspin * (args.group * naux * neo * nao * 16 + 2 * naux * neo * neo * 16 +
+                      npair * args.kl_group * 2 * naux * 8 + 3 * npair * npair * 8) + (6 << 30)
     ranges = sorted({(l0, l1) for (l0, l1, _) in my_blocks})
     budget = free_b - work_b
     stores, store_map, nslots_tot = {}, {}, 0
@@ -273,7 +284,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             t2 = time.perf_counter()
         if rank == 0:
-            eri = et.finalize_eri(eri, neo, 4, 1)
+            eri = et.finalize_eri(eri, neo, 4, nspin)
         if debug:
             torch.cuda.synchronize()
             t3 = time.perf_counter()
@@ -353,7 +364,9 @@ def run_ours(args):
         e2e_call()                                                       # warm-up
         barrier()
         t0 = time.perf_counter()
+        res = None
         for _ in range(n_e2e):
+            del res                      # a DMET loop drops the previous eri too: the pinned result buffer is reused
             res = e2e_call(st)
         barrier()
         t_e2e = (time.perf_counter() - t0) / n_e2e
@@ -375,7 +388,7 @@ def run_ours(args):
 
     # ---- one DMET iteration of this path: get_emb_basis + embHam through the public API (N=1 only) ----
     dmet_iter = None
-    if world == 1 and not args.no_dmet:
+    if world == 1 and not args.no_dmet and nspin == 1:
         from libdmet_preview_b200 import lattice as lat, slater
         torch.cuda.empty_cache()
         nval = neo - nao // 2 if neo > nao // 2 else max(1, neo // 3)       # impurity = nao/2 orbitals + nval bath
@@ -409,7 +422,7 @@ def run_ours(args):
         return
 
     cpu = None
-    if not args.no_cpu and world == 1:       # reported at N=1 only (rank 0's host cores are otherwise shared)
+    if not args.no_cpu and world == 1 and nspin == 1:       # reported at N=1 only (rank 0's host cores are otherwise shared)
         c = cpu_sample(kmesh, nao, naux, neo)
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         cpu = {"value": c["tflops"], "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": c["sample"],
@@ -420,7 +433,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (seeded counter-based GDF tensor generated on the device; %d resident blocks per GPU, "
                     "the %d block pieces of this rank's schedule cycle over them)" % (nslots, len(my_blocks)),
-            "config": dict(config_dict(args, kmesh, nao, naux, neo, B, G), parallelism="(kL, aux-range) work items sharded x%d, one NCCL reduce of the s4 ERI" % world,
+            "config": dict(config_dict(args, kmesh, nao, naux, neo, B, G), nspin=nspin, parallelism="(kL, aux-range) work items sharded x%d, one NCCL reduce of the s4 ERI" % world,
                            l2_policy="inputs larger than L2 (each GDF block %.0f MB, ERI %.0f MB)" %
                            (blk_bytes / 1e6, npair * npair * 8 / 1e6), group=args.group, kl_group=args.kl_group),
             "get_emb_eri_seconds": t_step, "flops_per_step": F1 + F3, "clocks": clk.summary(),

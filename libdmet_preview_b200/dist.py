@@ -77,4 +77,5 @@ def get_emb_eri_sharded(cell, mydf, C_ao_lo=None, basis=None, kscaled_center=Non
     if dist.get_rank(group) != 0 and not all_ranks:
         return None
     eri = et.finalize_eri(eri, nemb, symmetry, nspin)
-    return eri if return_device else eri.cpu().numpy()
+    from .device import get_device
+    return eri if return_device else get_device().to_host(eri)

@@ -486,7 +486,7 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
     eri = finalize_eri(eri, nemb, symmetry, spin)
     if return_device:
         return eri
-    return eri.cpu().numpy()
+    return get_device().to_host(eri)
 
 
 get_emb_eri_fast = get_emb_eri_fast_gdf
@@ -594,4 +594,4 @@ def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_cen
                          imag=imag)
     _report_imag(imag, kwargs)
     eri = finalize_eri(eri, nemb, symmetry, 1)
-    return eri if return_device else eri.cpu().numpy()
+    return eri if return_device else get_device().to_host(eri)

@@ -277,12 +277,12 @@ def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwar
         blocks = [eri4[i] for i in order]
         dev = get_device()
         if eri_symmetry == 4:
-            H2 = torch.stack(blocks).cpu().numpy()
+            H2 = dev.to_host(eri4 if order == list(range(eri4.shape[0])) else torch.stack(blocks))
         elif eri_symmetry == 1:
-            H2 = np.stack([dev.restore_s1(b, nbasis).cpu().numpy() for b in blocks])
+            H2 = np.stack([dev.to_host(dev.restore_s1(b, nbasis)) for b in blocks])
         elif eri_symmetry == 8:
             assert len(blocks) == 1
-            H2 = dev.restore_s8(blocks[0], nbasis).cpu().numpy()[None]
+            H2 = dev.to_host(dev.restore_s8(blocks[0], nbasis))[None]
         else:
             raise ValueError("unknown eri_symmetry %s" % eri_symmetry)
         return H2, blocks

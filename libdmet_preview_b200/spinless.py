@@ -108,11 +108,11 @@ def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwar
     dev = get_device()
     sym = lattice.eri_symmetry
     if sym == 4:
-        H2 = eri4.cpu().numpy()
+        H2 = dev.to_host(eri4)
     elif sym == 1:
-        H2 = dev.restore_s1(eri4[0], nb).cpu().numpy()[None]
+        H2 = dev.to_host(dev.restore_s1(eri4[0], nb))[None]
     elif sym == 8:
-        H2 = dev.restore_s8(eri4[0], nb).cpu().numpy()[None]
+        H2 = dev.to_host(dev.restore_s8(eri4[0], nb))[None]
     else:
         raise ValueError("unknown eri_symmetry %s" % sym)
     return H2, [eri4[0]]

@@ -1,7 +1,7 @@
 #!/bin/bash
 # synthetic get_emb_eri sweep of BASELINE.json configs[4] on one GPU -> gpurun_out/sweep.jsonl
 mkdir -p gpurun_out; : > gpurun_out/sweep.jsonl
-for w in small sweep_222_300_1500_200 sweep_224_200_1000_100 sweep_333_100_500_150 sweep_442_200_1000_150 sweep_444_100_500_100 sweep_444_300_1500_200; do
+for w in c1_hchain c2_graphene c3_nio_uhf small sweep_222_300_1500_200 sweep_224_200_1000_100 sweep_333_100_500_150 sweep_442_200_1000_150 sweep_444_100_500_100 sweep_444_300_1500_200; do
   timeout 300 python bench.py --workload $w --steps 2 --warmup 2 --no-e2e --no-cpu --no-dmet 2>/dev/null | tail -1 >> gpurun_out/sweep.jsonl
 done
 python - <<'PY'
