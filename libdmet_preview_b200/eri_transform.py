@@ -16,7 +16,7 @@ import torch
 
 from ._lib import check
 from .device import get_device, _ptr
-from .schedule import build_schedule, work_items, KPT_DIFF_TOL
+from .schedule import build_schedule, work_items, round_to_FBZ, KPT_DIFF_TOL
 from . import fourier
 from .make_basis import add_spin_dim
 
@@ -595,3 +595,162 @@ def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_cen
     _report_imag(imag, kwargs)
     eri = finalize_eri(eri, nemb, symmetry, 1)
     return eri if return_device else get_device().to_host(eri)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GDF tensor rotated to the LO basis (eri_transform.py:1312-1427)
+# ---------------------------------------------------------------------------------------------------------
+def stored_pairs(provider):
+    """(k_i, k_j) index pairs of a GDF file in file order (j <= i, eri_transform.py:1352-1355 without band
+    k-points); a provider may carry its own list in `.kptij_idx`"""
+    if hasattr(provider, "kptij_idx"):
+        return [tuple(int(x) for x in p) for p in provider.kptij_idx]
+    nk = len(provider.kpts_scaled)
+    return [(i, j) for i in range(nk) for j in range(i + 1)]
+
+
+def get_mask_kptij_lst(cell, kptij_lst, tol=KPT_DIFF_TOL, scaled=False):
+    """time-reversal map over the stored pairs: mask[a] = b when pair b = -pair a (b > a, and mask[b] = -2: filled
+    from a), -1 otherwise (eri_transform.py:1409-1427).  `scaled` skips the cell.get_scaled_kpts conversion."""
+    kptij = np.asarray(kptij_lst, dtype=float)
+    if not scaled:
+        kptij = cell.get_scaled_kpts(kptij)
+    flat = round_to_FBZ(kptij.reshape(len(kptij), -1), tol=tol)
+    mask = np.full(len(flat), -1, dtype=int)
+    for a in range(len(flat)):
+        if mask[a] != -1:
+            continue
+        s = flat[a][None] + flat[a + 1:]
+        hit = np.flatnonzero(np.abs(s - np.round(s)).max(axis=1) < tol) if len(s) else []
+        if len(hit):
+            mask[a], mask[a + 1 + hit[0]] = a + 1 + hit[0], -2
+    return mask
+
+
+def _pack_rows(x):
+    """(naux, n, n) -> (naux, n(n+1)/2) lower triangle, row-major (PySCF pack_tril)"""
+    r, c = np.tril_indices(x.shape[-1])
+    return np.ascontiguousarray(x[:, r, c])
+
+
+class LoGDF(object):
+    """The LO-basis GDF tensor `transform_gdf_to_lo` produces, kept in memory in the layout the reference writes to
+    its HDF5 file: `kptij_idx` (stored pairs) and `j3c[pos]` = real packed (both k-points Gamma), complex packed
+    (k_i == k_j) or full (naux, nlo*nlo).  `.load(ki, kj)` serves (naux, nlo, nlo) blocks the way PySCF's `_load3c`
+    + `sr_loop(compact=False)` do (conj-transpose of the stored pair when only (kj, ki) is there, Hermitian
+    unpacking of packed blocks), so the object is a GDF provider for `get_emb_eri` with C_ao_lo = identity."""
+
+    def __init__(self, provider, nlo, kptij_idx, j3c):
+        self.kpts_scaled = np.asarray(provider.kpts_scaled)
+        self.kmesh = list(getattr(provider, "kmesh", []))
+        self.kpts = getattr(provider, "kpts", None)
+        self.blockdim = getattr(provider, "blockdim", 240)
+        self.naux = int(provider.naux)
+        self.nao = int(nlo)
+        cell = getattr(provider, "cell", None)
+        if cell is not None and int(cell.nao_nr()) != nlo:        # l.1400-1403: nao_nr of the new object is nlo
+            import copy
+            cell = copy.copy(cell)
+            cell.nao_nr = lambda *args: nlo
+        self.cell = cell
+        self.kptij_idx = list(kptij_idx)
+        self.j3c = j3c
+        self._pos = {p: n for n, p in enumerate(self.kptij_idx)}
+        self._cderi = "<memory>"
+
+    def _unpacked(self, pos):
+        x = self.j3c[pos]
+        n = self.nao
+        if x.shape[-1] == n * n:
+            return x.reshape(-1, n, n)
+        out = np.empty((x.shape[0], n, n), dtype=np.complex128)
+        r, c = np.tril_indices(n)
+        out[:, c, r] = x.conj()
+        out[:, r, c] = x
+        return out
+
+    def load(self, ki, kj):
+        if (ki, kj) in self._pos:
+            return np.asarray(self._unpacked(self._pos[(ki, kj)]), dtype=np.complex128)
+        return np.ascontiguousarray(self._unpacked(self._pos[(kj, ki)]).conj().transpose(0, 2, 1))
+
+    def save(self, fname):
+        """write the reference's file layout (`j3c-kptij`, `j3c/<pos>/0`); needs h5py, or a name ending in .npz"""
+        kptij = np.asarray([(self.kpts[i], self.kpts[j]) for i, j in self.kptij_idx]) if self.kpts is not None \
+            else np.asarray([(self.kpts_scaled[i], self.kpts_scaled[j]) for i, j in self.kptij_idx])
+        if fname.endswith(".npz"):
+            np.savez(fname, **{"j3c-kptij": kptij}, **{"j3c/%d/0" % k: v for k, v in self.j3c.items()})
+            return
+        try:
+            import h5py
+        except ImportError:
+            raise RuntimeError("writing %s needs h5py (not installed); pass fname=None or a .npz name" % fname)
+        with h5py.File(fname, "w") as f:
+            f["j3c-kptij"] = kptij
+            for k, v in self.j3c.items():
+                f["j3c/%d/0" % k] = v
+
+
+def transform_gdf_to_lo(mydf, C_ao_lo, fname="gdf_ints_lo.h5", t_reversal_symm=True, **kwargs):
+    """Rotate every stored GDF block to the LO basis, L_lo[L, m, n] = sum_pq conj(C_i[p, m]) L[L, p, q] C_j[q, n],
+    with the reference's storage rules and time-reversal filling (eri_transform.py:1312-1407).  Both half
+    transformations run on the device (two `zgemm_tn` launches per pair).  Returns a `LoGDF` (and writes `fname`
+    unless it is None); with a PySCF GDF the returned object is a new GDF whose `_cderi` is `fname`, as in the
+    reference."""
+    dev = get_device()
+    cell = getattr(mydf, "cell", None)
+    provider = as_provider(cell, mydf)
+    Cz = _to_z(C_ao_lo)
+    assert Cz.dim() == 3
+    nkpts, nao, nlo = Cz.shape
+    assert nkpts == len(provider.kpts_scaled)
+    assert nao == provider.nao
+    naux = provider.naux
+    pairs = stored_pairs(provider)
+    ks = np.asarray(provider.kpts_scaled)
+    if t_reversal_symm:
+        mask = get_mask_kptij_lst(None, [np.concatenate([ks[i], ks[j]]) for i, j in pairs], scaled=True)
+    else:
+        mask = np.full(len(pairs), -1, dtype=int)
+
+    CT = dev.ztranspose(Cz)                                                         # (nk, nlo, nao)
+    synth = hasattr(provider, "keys") and hasattr(provider, "scale") and kwargs.get("source", "auto") != "host"
+    Ld = dev.empty((naux, nao, nao), torch.complex128)
+    XT = dev.empty((naux, nlo, nao), torch.complex128)
+    S = dev.empty((naux, nlo, nlo), torch.complex128)
+    j3c = {}
+    for pos, (i, j) in enumerate(pairs):
+        if mask[pos] == -2:          # filled from its time-reversal partner (l.1372-1373)
+            continue
+        if synth:
+            dev.synth_block(Ld, naux, nao, provider.keys(i, j), provider.scale)
+        else:
+            blk = np.ascontiguousarray(provider.load(i, j), dtype=np.complex128)
+            assert blk.size == naux * nao * nao
+            Ld.copy_(torch.from_numpy(blk.reshape(naux, nao, nao)), non_blocking=False)
+        # XT[L][n][p] = sum_q L[L][p][q] C_j[q][n]
+        dev.zgemm_tn(Ld.reshape(1, naux * nao, nao), CT, [[0, j, 0, 0]], XT, rdiv=nao, s_outer=nlo * nao,
+                     s_inner=1, s_col=nao)
+        # S[L][m][n] = sum_p conj(C_i[p][m]) XT[L][n][p]
+        dev.zgemm_tn(XT.reshape(1, naux * nlo, nao), CT, [[0, i, 0, 1]], S, rdiv=nlo, s_outer=nlo * nlo,
+                     s_inner=1, s_col=nlo)
+        Lij = dev.to_host(S)
+        both_gamma = max(np.abs(ks[i]).max(), np.abs(ks[j]).max()) < KPT_DIFF_TOL
+        if both_gamma:               # l.1386-1388
+            assert np.abs(Lij.imag).max() < ERI_IMAG_TOL
+            stored = _pack_rows(Lij.real)
+        elif i == j:                 # l.1389-1390
+            stored = _pack_rows(Lij)
+        else:
+            stored = Lij.reshape(naux, nlo * nlo).copy()
+        j3c[pos] = stored
+        if mask[pos] != -1:          # l.1395-1396
+            j3c[int(mask[pos])] = stored.conj()
+    out = LoGDF(provider, nlo, pairs, j3c)
+    if fname is not None:
+        out.save(fname)
+        if isinstance(provider, PyscfGDFProvider):
+            mydf_lo = mydf.__class__(out.cell if nlo != nao else mydf.cell, mydf.kpts)
+            mydf_lo._cderi = fname
+            return mydf_lo
+    return out

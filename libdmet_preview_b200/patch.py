@@ -3,7 +3,7 @@
     import libdmet_preview_b200.patch as p; p.install()
 
 rebinds the names the reference's callers actually resolve:
-  * `libdmet.basis_transform.eri_transform.get_emb_eri / get_unit_eri / get_emb_eri_fast_gdf`
+  * `libdmet.basis_transform.eri_transform.get_emb_eri / get_unit_eri / get_emb_eri_fast_gdf / transform_gdf_to_lo`
   * `libdmet.routine.slater.get_emb_eri / get_unit_eri` -- imported BY NAME at module load (slater.py:32-33), so the
     attribute on `slater` must be replaced too
   * `libdmet.system.fourier.k2R / R2k / FFTtoK / FFTtoT` and the copies `libdmet.system.lattice` pulled in with
@@ -48,6 +48,7 @@ def install():
     _swap(r_eri, "get_unit_eri", get_unit_eri)
     _swap(r_eri, "get_emb_eri", get_emb_eri)
     _swap(r_eri, "get_emb_eri_fast_gdf", eri.get_emb_eri_fast_gdf)
+    _swap(r_eri, "transform_gdf_to_lo", eri.transform_gdf_to_lo)
     _swap(r_sl, "get_emb_eri", get_emb_eri)
     _swap(r_sl, "get_unit_eri", get_unit_eri)
     for m in (r_f, r_lat):

@@ -1,7 +1,7 @@
 """Oracle: embedding ERI from Gaussian-density-fitting integrals.
 
 Numpy restatement (own code, same algorithm) of libdmet/basis_transform/eri_transform.py:44-112 (dispatch), 118-157, 195-227
-(sr_loop chunking), 235-399 (get_emb_eri_fast_gdf, incore), 403-434, 436-485, 523-544.
+(sr_loop chunking), 235-399 (get_emb_eri_fast_gdf, incore), 403-434, 436-485, 523-544, 1312-1427 (GDF tensor in the LO basis).
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 `mydf` is any GDF provider with
@@ -255,3 +255,66 @@ def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_cen
         Lij_s4 = _accumulate_Lij_s4(mydf, C_ao_emb, kL, kscaled, kconserv_tol, t_reversal_symm, blksize)
         _Lij_s4_to_eri_gso(Lij_s4, eri, weight=weights[kL], t_reversal_symm=t_reversal_symm)
     return eri_restore(eri.real, symmetry, nemb)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GDF tensor in the LO basis (eri_transform.py:1312-1427)
+# ---------------------------------------------------------------------------------------------------------
+def stored_pairs(mydf):
+    """(k_i, k_j) index pairs a PySCF GDF file holds, in file order: j <= i (eri_transform.py:1352-1355 without
+    band k-points); providers may carry their own list in `.kptij_idx`"""
+    if hasattr(mydf, "kptij_idx"):
+        return [tuple(int(x) for x in p) for p in mydf.kptij_idx]
+    nk = len(mydf.kpts_scaled)
+    return [(i, j) for i in range(nk) for j in range(i + 1)]
+
+
+def get_mask_kptij_lst(kptij_scaled, tol=KPT_DIFF_TOL):
+    """time-reversal partner of every stored pair: mask[a] = b > a when pair b = -pair a (b then gets -2 =
+    "filled from its partner"), -1 for pairs that are their own partner or have none (eri_transform.py:1409-1427)"""
+    flat = round_to_FBZ(np.asarray(kptij_scaled, dtype=float).reshape(len(kptij_scaled), -1), tol=tol)
+    mask = np.full(len(flat), -1, dtype=int)
+    for a in range(len(flat)):
+        if mask[a] != -1:
+            continue
+        for b in range(a + 1, len(flat)):
+            s = flat[a] + flat[b]
+            if max_abs(s - np.round(s)) < tol:
+                mask[a], mask[b] = b, -2
+                break
+    return mask
+
+
+def transform_gdf_to_lo(mydf, C_ao_lo, t_reversal_symm=True, blksize=240):
+    """{pair position: L_lo} in the reference's storage convention (eri_transform.py:1312-1407): for every stored
+    pair, L_lo[L, m, n] = sum_pq conj(C_i[p, m]) L[L, p, q] C_j[q, n]; real lower-triangular packed when both
+    k-points are Gamma, complex packed when k_i == k_j, full (naux, nlo*nlo) otherwise; with time reversal the
+    partner pair receives the complex conjugate."""
+    C = np.asarray(C_ao_lo)
+    nk, nao, nlo = C.shape
+    assert nk == len(mydf.kpts_scaled) and nao == mydf.nao
+    pairs = stored_pairs(mydf)
+    ks = np.asarray(mydf.kpts_scaled)
+    mask = (get_mask_kptij_lst([np.concatenate([ks[i], ks[j]]) for i, j in pairs]) if t_reversal_symm
+            else np.full(len(pairs), -1, dtype=int))
+    out = {}
+    for pos, (i, j) in enumerate(pairs):
+        if mask[pos] == -2:
+            continue
+        Lij = np.zeros((mydf.naux, nlo * nlo), dtype=np.complex128)
+        row = 0
+        for Lpq in sr_loop(mydf, i, j, blksize):
+            Lij[row:row + Lpq.shape[0]] = transform_ao_to_emb(Lpq, C, i, j)[0]
+            row += Lpq.shape[0]
+        both_gamma = max_abs(ks[i]) < KPT_DIFF_TOL and max_abs(ks[j]) < KPT_DIFF_TOL
+        if both_gamma:
+            assert max_abs(Lij.imag) < ERI_IMAG_TOL
+            stored = lib.pack_tril(Lij.real.reshape(-1, nlo, nlo))
+        elif i == j:
+            stored = lib.pack_tril(Lij.reshape(-1, nlo, nlo))
+        else:
+            stored = Lij
+        out[pos] = stored
+        if mask[pos] != -1:
+            out[int(mask[pos])] = stored.conj()
+    return out

@@ -10,6 +10,7 @@ Functions executed from the reference:
     libdmet.basis_transform.make_basis.transform_h1_to_lo / multiply_basis     (make_basis.py:524-558, 923-962)
     libdmet.system.lattice.Lattice(...).set_Ham(...)                           (lattice.py:31-56, 416-515, 591-673)
     libdmet.routine.slater.get_emb_basis / get_emb_Ham                         (slater.py:98-220, 320-370, ...)
+    libdmet.basis_transform.eri_transform.transform_gdf_to_lo                  (eri_transform.py:1312-1427)
 Inputs are the seeded synthetic problems of tests/helpers.py; small inputs are stored next to the outputs.
 """
 import os
@@ -51,6 +52,10 @@ class GoldenCell(synthetic.SyntheticCell):
     def super_cell(self, kmesh):
         big = GoldenCell(self._nao * int(np.prod(kmesh)))
         return big
+
+    def copy(self):
+        import copy
+        return copy.copy(self)
 
 
 def ref_gdf(gdf, key):
@@ -207,7 +212,28 @@ def gen_gso_embham():
              ovlp=Ham.ovlp, H0=Ham.H0, JK_core=Lat.JK_core)
 
 
+def gen_gdf_lo():
+    """GDF tensor rotated to the LO basis through the reference's transform_gdf_to_lo (eri_transform.py:1312-1427);
+    the h5py stub collects what the reference writes to its output file"""
+    for name, (kmesh, nao, nlo, naux) in {"gdf_lo_113": ([1, 1, 3], 4, 4, 6), "gdf_lo_221": ([2, 2, 1], 5, 3, 7)}.items():
+        gdf, _, _ = problem(kmesh, nao, naux, 2)
+        gdf.cell = GoldenCell(nao)
+        mydf = ref_gdf(gdf, name)
+        C = synthetic.make_C_ao_lo(kmesh, nao, nlo, seed=31)
+        out = dict(kmesh=np.array(kmesh), nao=nao, nlo=nlo, naux=naux, gdf_seed=gdf.seed, gdf_scale=gdf.scale, C_ao_lo=C)
+        for tag, trs in (("trs", True), ("plain", False)):
+            ref_eri.transform_gdf_to_lo(mydf, C, fname=name + tag, t_reversal_symm=trs)
+            written = ref_stubs.H5_WRITTEN[name + tag]
+            npair = len(written["j3c-kptij"])
+            assert sorted(k for k in written if k != "j3c-kptij") == sorted("j3c/%d/0" % k for k in range(npair))
+            for k in range(npair):
+                out["%s_%d" % (tag, k)] = written["j3c/%d/0" % k]
+        out["kptij"] = written["j3c-kptij"]
+        save(name, **out)
+
+
 if __name__ == "__main__":
+    gen_gdf_lo()
     gen_gso_embham()
     gen_gso()
     gen_eri()

@@ -25,6 +25,7 @@ _STUB_ROOTS = ("pyscf", "h5py", "matplotlib", "mpi4py", "mpi4pyscf", "block2", "
                "seaborn", "ase", "spglib", "numba_stub")
 
 GDF_REGISTRY = {}     # cderi key -> provider
+H5_WRITTEN = {}       # file name -> {dataset name: array} written through the h5py stub
 
 
 class _PlaceholderMeta(type):
@@ -173,8 +174,15 @@ def _populate(m):
             pass
 
         class File(object):
+            """mode "r": a view of a registered in-memory GDF (only `j3c-kptij` is read through h5py by the reference,
+            the blocks go through `_load3c`); mode "w": datasets land in H5_WRITTEN[fname]"""
+
             def __init__(self, fname, mode="r"):
-                self.prov = GDF_REGISTRY[fname]
+                self.mode = mode
+                if mode == "w":
+                    self.out = H5_WRITTEN[fname] = {}
+                else:
+                    self.prov = GDF_REGISTRY[fname]
 
             def __enter__(self):
                 return self
@@ -182,14 +190,21 @@ def _populate(m):
             def __exit__(self, *a):
                 return False
 
+            def close(self):
+                pass
+
             def __getitem__(self, key):
-                if key == "j3c-kptij":
-                    n = len(self.prov.kpts_scaled)
-                    return np.empty((n * (n + 1) // 2, 2, 3))
+                if key == "j3c-kptij":      # absolute k-point pairs, j <= i (PySCF's file order)
+                    k = np.asarray(self.prov.kpts)
+                    n = len(k)
+                    return np.asarray([(k[i], k[j]) for i in range(n) for j in range(i + 1)])
                 raise KeyError(key)
 
+            def __setitem__(self, key, value):
+                self.out[key] = np.array(value)
+
             def __contains__(self, key):
-                return False
+                return self.mode != "w" and key == "j3c-kptij"
         m.File, m.Group = File, Group
     elif name == "pyscf.pbc.tools":
         def super_cell(cell, kmesh):

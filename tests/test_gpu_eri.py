@@ -257,3 +257,37 @@ def test_host_prefetch_thread(dev):
         et.get_emb_eri(gdf.cell, Slow(gdf, fail_at=4), C_ao_lo=C, basis=basis)
     # the handle is usable again after the failed build
     assert np.array_equal(et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis), ref)
+
+
+@pytest.mark.parametrize("nlo", [6, 4])
+def test_gdf_in_lo_basis_gives_the_same_eri(dev, nlo, tmp_path):
+    """transform_gdf_to_lo (eri_transform.py:1312-1407): oracle parity, the reference's own check that the
+    time-reversal filling changes nothing (test_transform_gdf.py:104-108), and the defining property -- the
+    embedding ERI from the LO-basis tensor with identity C equals the one from the AO tensor with C_ao_lo"""
+    from libdmet_preview_b200 import eri_transform as et, synthetic
+    from oracle import eri_transform as oe
+    kmesh, nao, naux, neo = [2, 1, 3], 6, 13, 5
+    gdf, _, _ = problem(kmesh, nao, naux, neo)
+    C = synthetic.make_C_ao_lo(kmesh, nao, nlo, seed=5)
+    basis = synthetic.make_emb_basis(kmesh, nlo, neo, seed=6)
+    lo = et.transform_gdf_to_lo(gdf, C, fname=None)
+    lo_plain = et.transform_gdf_to_lo(gdf, C, fname=None, t_reversal_symm=False)
+    ref = oe.transform_gdf_to_lo(gdf, C)
+    assert sorted(lo.j3c) == sorted(ref) == sorted(lo_plain.j3c)
+    for k in ref:
+        assert lo.j3c[k].shape == ref[k].shape and lo.j3c[k].dtype == ref[k].dtype
+        assert np.abs(lo.j3c[k] - ref[k]).max() < TOL
+        assert np.abs(lo.j3c[k] - lo_plain.j3c[k]).max() < TOL
+    assert lo.nao == nlo and lo.cell.nao_nr() == nlo and gdf.cell.nao_nr() == nao
+    eye = np.tile(np.eye(nlo, dtype=np.complex128), (len(gdf.kpts_scaled), 1, 1))
+    a = et.get_emb_eri(lo.cell, lo, C_ao_lo=eye, basis=basis)
+    b = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+    assert np.abs(a - b).max() < TOL
+    # file round trip in the reference's dataset naming
+    f = str(tmp_path / "gdf_lo.npz")
+    lo.save(f)
+    z = np.load(f)
+    assert z["j3c-kptij"].shape == (len(lo.kptij_idx), 2, 3)
+    assert all(np.array_equal(z["j3c/%d/0" % k], v) for k, v in lo.j3c.items())
+    with pytest.raises(RuntimeError):
+        lo.save(str(tmp_path / "gdf_lo.h5"))            # h5py is not installed in this image
