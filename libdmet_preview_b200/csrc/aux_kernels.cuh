@@ -469,13 +469,222 @@ jk_rows_kernel(const double* __restrict__ eri4, const double* __restrict__ D, co
     }
 }
 
+// Streaming variant for n <= 32 * NCH (<= 256): nothing is staged.  Warp w owns the rows k = w, w + 8, ... of the
+// symmetric matrix M packed in eri4[P][:]; lane reads the words l = lane + 32 c <= k of the row segment straight from
+// global memory (each word is used once).  A word M[k][l] feeds the row sum y[k] += M[k][l] d[l] (warp reduction) and,
+// for l < k, the column sum y[l] += M[k][l] d[k], which lives in the lane's registers for all rows of the warp.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+jk_rows_seg_kernel(const double* __restrict__ eri4, const double* __restrict__ D, const double* __restrict__ dd,
+                   double* __restrict__ vj_packed, double* __restrict__ kpart, int n, long long npair, int with_k) {
+    constexpr int NP = NCH * 32;
+    __shared__ double sDI[NP], sDJ[NP];
+    __shared__ double sRow[2][NP];
+    __shared__ double sCol[8][2][NP];
+    __shared__ double sJ[8];
+    const long long P = blockIdx.x;
+    int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= P) ++i;
+    while ((long long)i * (i + 1) / 2 > P) --i;
+    const int j = (int)(P - (long long)i * (i + 1) / 2);
+    for (int l = threadIdx.x; l < NP; l += blockDim.x) {
+        sDI[l] = l < n ? D[(size_t)i * n + l] : 0.0;
+        sDJ[l] = l < n ? D[(size_t)j * n + l] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double dIl[NCH], dJl[NCH], c1[NCH], c2[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        dIl[c] = sDI[lane + 32 * c];
+        dJl[c] = sDJ[lane + 32 * c];
+        c1[c] = 0.0;
+        c2[c] = 0.0;
+    }
+    const double* row = eri4 + P * npair;
+    double jacc = 0.0;
+    for (int k = w; k < n; k += 8) {
+        const size_t base = (size_t)k * (k + 1) / 2;
+        const double* seg = row + base;
+        const double* dseg = dd + base;
+        double m[NCH], g[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int l = lane + 32 * c;
+            const bool in = l <= k;
+            m[c] = in ? seg[l] : 0.0;
+            g[c] = in ? dseg[l] : 0.0;
+        }
+        const double dik = sDI[k], djk = sDJ[k];
+        double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            jacc = fma(m[c], g[c], jacc);
+            if (with_k) {
+                r1 = fma(m[c], dIl[c], r1);
+                r2 = fma(m[c], dJl[c], r2);
+                const double mc = (lane + 32 * c < k) ? m[c] : 0.0;      // the diagonal word enters once
+                c1[c] = fma(mc, dik, c1[c]);
+                c2[c] = fma(mc, djk, c2[c]);
+            }
+        }
+        if (with_k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+                r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+            }
+            if (lane == 0) {
+                sRow[0][k] = r1;
+                sRow[1][k] = r2;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) jacc += __shfl_xor_sync(0xffffffffu, jacc, o);
+    if (lane == 0) sJ[w] = jacc;
+    if (with_k) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            sCol[w][0][lane + 32 * c] = c1[c];
+            sCol[w][1][lane + 32 * c] = c2[c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sj = 0.0;
+        for (int x = 0; x < 8; ++x) sj += sJ[x];
+        vj_packed[P] = sj;
+    }
+    if (!with_k) return;
+    for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) {
+        const int v = t >= n, k = t - v * n;
+        double y = sRow[v][k];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) y += sCol[x][v][k];
+        kpart[(P * 2 + v) * n + k] = y;
+    }
+}
+
+// Bulk-copy variant (n <= NP, row fits in shared memory): one thread brings the whole packed row in with
+// cp.async.bulk -- a single transaction in flight while the SM's other resident CTA computes.  J is a flat dot product
+// against dd (streamed from L2).  K: thread k of group g walks row k of the symmetric matrix M over its half of the
+// l range -- M[k][l] sits at k(k+1)/2 + l for l <= k and at l(l+1)/2 + k beyond the diagonal, both bank-conflict free
+// across consecutive k -- so y[k] needs no cross-thread reduction; (D[i][l], D[j][l]) is one broadcast 16-byte load.
+// Rows start on 8-byte boundaries only, so the copy covers the enclosing 16-byte aligned range; a tail that would
+// cross the end of the tensor is fetched with plain loads.
+template <int NP>
+__global__ void __launch_bounds__(2 * NP)
+jk_rows_bulk_kernel(const double* __restrict__ eri4, const double* __restrict__ D, const double* __restrict__ dd,
+                    double* __restrict__ vj_packed, double* __restrict__ kpart, int n, long long npair, int with_k) {
+    extern __shared__ __align__(16) double jkb_row[];          // npair + 2 words
+    __shared__ double2 sD[NP];                                 // (D[i][l], D[j][l])
+    __shared__ double sY[2][2][NP];
+    __shared__ double sJ[2 * NP / 32];
+    __shared__ __align__(8) unsigned long long bar_store;
+    const long long P = blockIdx.x;
+    const long long off = P * npair;
+    const long long a0 = off & ~1LL;
+    const int head = (int)(off - a0);
+    long long cnt = ((long long)head + npair + 1) & ~1LL;
+    if (a0 + cnt > npair * npair) cnt -= 2;                     // stay inside the tensor; the tail comes below
+    const uint32_t bar = smem_u32(&bar_store);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)(cnt * 8));
+        const uint32_t dst = smem_u32(jkb_row);
+        for (long long c = 0; c < cnt; c += 4096)
+            bulk_load_1d(dst + (uint32_t)(c * 8), eri4 + a0 + c, (uint32_t)(min(4096LL, cnt - c) * 8), bar);
+    }
+    int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= P) ++i;
+    while ((long long)i * (i + 1) / 2 > P) --i;
+    const int j = (int)(P - (long long)i * (i + 1) / 2);
+    for (int l = threadIdx.x; l < NP; l += blockDim.x)
+        sD[l] = l < n ? make_double2(D[(size_t)i * n + l], D[(size_t)j * n + l]) : make_double2(0.0, 0.0);
+    double* srow = jkb_row + head;
+    for (long long q = cnt - head + threadIdx.x; q < npair; q += blockDim.x) srow[q] = eri4[off + q];
+    __syncthreads();                                            // barrier initialised, tail and D rows in place
+    mbar_wait(bar, 0);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double jacc = 0.0, jacc2 = 0.0;
+    {
+        long long q = threadIdx.x;
+        for (; q + blockDim.x < npair; q += 2 * blockDim.x) {
+            jacc = fma(srow[q], dd[q], jacc);
+            jacc2 = fma(srow[q + blockDim.x], dd[q + blockDim.x], jacc2);
+        }
+        if (q < npair) jacc = fma(srow[q], dd[q], jacc);
+        jacc += jacc2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) jacc += __shfl_xor_sync(0xffffffffu, jacc, o);
+    if (lane == 0) sJ[w] = jacc;
+    if (with_k) {
+        const int g = threadIdx.x >= NP, k = threadIdx.x - g * NP;
+        const int half = (n + 1) >> 1;
+        const int l0 = g * half, l1 = min(n, l0 + half);
+        double y1 = 0.0, y2 = 0.0, z1 = 0.0, z2 = 0.0;
+        if (k < n) {
+            int offA = k * (k + 1) / 2 + l0;                    // M[k][l], l <= k
+            int offB = l0 * (l0 + 1) / 2 + k;                   // M[l][k], l > k
+            int l = l0;
+            for (; l + 1 < l1; l += 2) {
+                const double m0 = srow[l <= k ? offA : offB];
+                const double m1 = srow[l + 1 <= k ? offA + 1 : offB + l + 1];
+                const double2 d0 = sD[l], d1 = sD[l + 1];
+                y1 = fma(m0, d0.x, y1);
+                y2 = fma(m0, d0.y, y2);
+                z1 = fma(m1, d1.x, z1);
+                z2 = fma(m1, d1.y, z2);
+                offA += 2;
+                offB += 2 * l + 3;
+            }
+            if (l < l1) {
+                const double m0 = srow[l <= k ? offA : offB];
+                const double2 d0 = sD[l];
+                y1 = fma(m0, d0.x, y1);
+                y2 = fma(m0, d0.y, y2);
+            }
+        }
+        sY[g][0][k] = y1 + z1;
+        sY[g][1][k] = y2 + z2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sj = 0.0;
+        for (int x = 0; x < 2 * NP / 32; ++x) sj += sJ[x];
+        vj_packed[P] = sj;
+    }
+    if (!with_k) return;
+    for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) {
+        const int v = t >= n, k = t - v * n;
+        kpart[(P * 2 + v) * n + k] = sY[0][v][k] + sY[1][v][k];
+    }
+}
+
+// K[a][k] = sum_{i >= a} y1(P(i, a))[k] + sum_{j < a} y2(P(a, j))[k], terms dealt to the 8 warps and summed in a
+// fixed order (deterministic)
 __global__ void __launch_bounds__(256)
 jk_reduce_kernel(const double* __restrict__ kpart, double* __restrict__ vk, int n) {
+    extern __shared__ double jkr_smem[];          // [8][n]
     const int a = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = lane; k < n; k += 32) {
+        double s = 0.0;
+        for (int t = w; t < n; t += 8) {
+            const long long src = t >= a ? ((long long)t * (t + 1) / 2 + a) * 2 + 0
+                                         : ((long long)a * (a + 1) / 2 + t) * 2 + 1;
+            s += kpart[src * n + k];
+        }
+        jkr_smem[(size_t)w * n + k] = s;
+    }
+    __syncthreads();
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         double s = 0.0;
-        for (int i = a; i < n; ++i) s += kpart[(((long long)i * (i + 1) / 2 + a) * 2 + 0) * n + k];
-        for (int j = 0; j < a; ++j) s += kpart[(((long long)a * (a + 1) / 2 + j) * 2 + 1) * n + k];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) s += jkr_smem[(size_t)x * n + k];
         vk[(size_t)a * n + k] = s;
     }
 }

@@ -185,6 +185,16 @@ static int ensure_attrs(ldm_handle h) {
                                      DTile::SMEM));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      200 * 1024));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_bulk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     210 * 1024));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_bulk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     210 * 1024));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_bulk_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     210 * 1024));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_bulk_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     210 * 1024));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)pack_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      16 * 16 * 17 * 16));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)restore_s1_kernel<true>,
@@ -558,6 +568,7 @@ int ldm_restore_s8(ldm_handle h, void* stream, const double* eri4_d, double* out
 int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm_d, double* vj_d, double* vk_d,
               int n) {
     LDM_REQUIRE(h && eri4_d && dm_d && vj_d, "null pointer");
+    LDM_REQUIRE(n > 0 && n <= 3200, "orbital count out of range");
     LDM_CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     long long npair = (long long)n * (n + 1) / 2;
@@ -574,19 +585,37 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
     double* kpart = dd + npair;
     jk_pack_dm_kernel<<<(unsigned)std::min<long long>((npair + 255) / 256, 1024), 256, 0, st>>>(dm_d, dd, n);
     LDM_CUDA_OK(cudaGetLastError());
-    if (staged)
-        jk_rows_kernel<true><<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair,
-                                                                vk_d != nullptr);
+    const int wk = vk_d != nullptr;
+    const size_t rowb = (size_t)(npair + 2) * 8;      // bulk-copy variant: the packed row in shared memory
+#define LDM_JK_LAUNCH(NCH)                                                                                         \
+    do {                                                                                                           \
+        if (n > 16 && rowb + 16 * 1024 <= 227 * 1024)                                                              \
+            jk_rows_bulk_kernel<32 * NCH><<<(unsigned)npair, 64 * NCH, rowb, st>>>(eri4_d, dm_d, dd, vj_packed,   \
+                                                                                   kpart, n, npair, wk);           \
+        else                                                                                                       \
+            jk_rows_seg_kernel<NCH><<<(unsigned)npair, 256, 0, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair, \
+                                                                     wk);                                          \
+    } while (0)
+    if (n <= 64)
+        LDM_JK_LAUNCH(2);
+    else if (n <= 128)
+        LDM_JK_LAUNCH(4);
+    else if (n <= 160)
+        LDM_JK_LAUNCH(5);
+    else if (n <= 256)
+        LDM_JK_LAUNCH(8);
+#undef LDM_JK_LAUNCH
+    else if (staged)
+        jk_rows_kernel<true><<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair, wk);
     else
-        jk_rows_kernel<false><<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair,
-                                                                 vk_d != nullptr);
+        jk_rows_kernel<false><<<(unsigned)npair, 256, smem, st>>>(eri4_d, dm_d, dd, vj_packed, kpart, n, npair, wk);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
     unpack_sym_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(vj_packed, vj_d, n);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches += 2;
     if (vk_d) {
-        jk_reduce_kernel<<<n, 256, 0, st>>>(kpart, vk_d, n);
+        jk_reduce_kernel<<<n, 256, (size_t)8 * n * 8, st>>>(kpart, vk_d, n);
         LDM_CUDA_OK(cudaGetLastError());
         h->launches++;
     }

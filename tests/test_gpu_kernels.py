@@ -119,6 +119,37 @@ def test_restore_and_jk(dev, n):
     assert np.abs(vj2.cpu().numpy() - olib.dot_eri_dm(eab, d, with_k=False)[0]).max() < 1e-11 * max(1, np.abs(rj).max())
 
 
+@pytest.mark.parametrize("n", [32, 33, 64, 65, 97, 129, 161])
+def test_jk_streaming_variants(dev, n):
+    """every register-tile width of the streaming J/K kernel (n <= 64, 128, 160, 256), non-symmetric density, against
+    the defining sums evaluated row by row on the host (scf.py:269-271: J_ij = sum_kl (ij|kl) D_kl,
+    K_jk = sum_il (ij|kl) D_il)"""
+    rng = np.random.default_rng(n)
+    npair = n * (n + 1) // 2
+    x = rng.standard_normal((npair, npair))
+    e4 = x + x.T
+    d = rng.standard_normal((n, n))
+    vj, vk = dev.jk_s4(dev.to_device(e4, torch.float64), dev.to_device(d, torch.float64))
+    r, c = np.tril_indices(n)
+    dd = np.where(r == c, d[r, c], d[r, c] + d[c, r])
+    rj = np.zeros((n, n))
+    rj[r, c] = e4 @ dd
+    rj[c, r] = rj[r, c]
+    rk = np.zeros((n, n))
+    M = np.zeros((n, n))
+    for P in range(npair):
+        i, j = r[P], c[P]
+        M[r, c] = e4[P]
+        M[c, r] = e4[P]
+        rk[j] += M @ d[i]
+        if i != j:
+            rk[i] += M @ d[j]
+    assert np.abs(vj.cpu().numpy() - rj).max() < 1e-11 * np.abs(rj).max()
+    assert np.abs(vk.cpu().numpy() - rk).max() < 1e-11 * np.abs(rk).max()
+    again = dev.jk_s4(dev.to_device(e4, torch.float64), dev.to_device(d, torch.float64))
+    assert torch.equal(again[0], vj) and torch.equal(again[1], vk)          # fixed summation order
+
+
 def test_synth_block_bit_exact(dev):
     from libdmet_preview_b200 import synthetic
     g = synthetic.SyntheticGDF([2, 1, 3], 9, 14, seed=77)
