@@ -78,7 +78,38 @@ class ClockSampler(object):
         self.stop = False
         self.th = threading.Thread(target=self.run, daemon=True)
 
+    def _nvml(self):
+        """in-process NVML sampling (no fork per sample, nothing that stalls the driver for milliseconds)"""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                 else nv.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                         getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mask = int(get_reasons(h)) if get_reasons else 0
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            self.samples.append([str(sm), str(mx), str(pw)] + ["Active" if mask & b else "Not Active" for _, b in bits])
+            time.sleep(0.05)
+
     def run(self):
+        try:
+            self._nvml()
+            return
+        except Exception:
+            pass
         while not self.stop:
             try:
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
