@@ -366,9 +366,15 @@ def run_ours(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
+    m3 = os.environ.get("LDM_ZGEMM_3M", "1") != "0"
     roofline = {"bound": "tensor", "kernel": "zgemm_tn_kernel (stage 1: both half transformations)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
                 "traffic": traffic,
+                "complex_product": "3M" if m3 else "4M",
+                "executed_tflops": (ach * (0.75 if m3 else 1.0)) if ach else None,
+                "note": ("achieved counts ALGORITHMIC flops (8 per complex multiply-add); the kernel evaluates complex "
+                         "products with three real multiplications, so the tensor pipe executes 0.75 of them and "
+                         "frac can exceed 1") if m3 else None,
                 "peak_source": "cuBLAS DGEMM 8192^3 sustained 4 s on this pool's B200 (tools/probe_peaks.py -> "
                                "profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json carries no FP64 figure",
                 "share_of_step": zg_ms * 1e-3 / (t_step * args.steps),

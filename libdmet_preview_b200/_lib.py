@@ -20,6 +20,7 @@ SIGNATURES = {
     "ldm_last_error": (C.c_char_p, []),
     "ldm_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "ldm_destroy": (C.c_int, [vp]),
+    "ldm_set_option": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     "ldm_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "ldm_host_free": (C.c_int, [vp]),
     "ldm_dev_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),

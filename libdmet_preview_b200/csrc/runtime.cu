@@ -74,18 +74,19 @@ int encode_tmap_f64_3d(CUtensorMap* map, const void* base, uint64_t dim0, uint64
 struct ZConfig {
     int BM, BN, threads, smem;
     void (*kernel)(const CUtensorMap, const CUtensorMap, const ZGemmArgs);
+    bool m3;
 };
 
-template <int WM, int WN, int FA, int FB>
+template <int WM, int WN, int FA, int FB, bool M3 = false>
 static ZConfig make_zconfig() {
     using T = ZTile<WM, WN, FA, FB>;
-    return ZConfig{T::BM, T::BN, T::THREADS, T::SMEM, zgemm_tn_kernel<WM, WN, FA, FB>};
+    return ZConfig{T::BM, T::BN, T::THREADS, T::SMEM, zgemm_tn_kernel<WM, WN, FA, FB, M3>, M3};
 }
 
-template <int FB>
+template <int FB, bool M3 = false>
 static void add_wide(std::vector<ZConfig>& v) {
-    v.push_back(make_zconfig<8, 1, 1, FB>());
-    if constexpr (FB > 1) add_wide<FB - 1>(v);
+    v.push_back(make_zconfig<8, 1, 1, FB, M3>());
+    if constexpr (FB > 1) add_wide<FB - 1, M3>(v);
 }
 
 // Tile family.  First the register-blocked 32x(8*FB) warp tiles (least shared-memory traffic), then the "wide"
@@ -99,24 +100,35 @@ static const std::vector<ZConfig>& zconfigs() {
             make_zconfig<2, 4, 4, 3>(), make_zconfig<4, 2, 4, 3>(), make_zconfig<8, 1, 4, 3>(),
         };
         add_wide<25>(c);
+        // 3-multiplication family (three accumulator sets): 64 x (8*FB) wide tiles up to FB = 13, preceded by the
+        // register-blocked 64x80 / 64x96 / 64x64 tiles with two row fragments per warp
+        c.push_back(make_zconfig<4, 2, 2, 5, true>());
+        c.push_back(make_zconfig<4, 2, 2, 6, true>());
+        c.push_back(make_zconfig<4, 2, 2, 4, true>());
+        add_wide<13, true>(c);
         return c;
     }();
     return v;
 }
 
-static const ZConfig& pick_zconfig(int N) {
+static const ZConfig& pick_zconfig(int N, bool m3) {
     const auto& v = zconfigs();
     if (const char* f = getenv("LDM_FORCE_ZCFG")) {       // development aid: force a tile configuration
         int idx = atoi(f);
         if (idx >= 0 && idx < (int)v.size()) return v[idx];
     }
-    int best = 0;
-    long best_pad = -1;
+    // cost of a configuration: padded N, inflated by a per-tile overhead that shrinks with the tile width (a 64x8
+    // tile pads N = 150 to 152 but spends its time in fragment loads and epilogues); ties: the earlier (more
+    // register-blocked) entry wins
+    int best = -1;
+    double best_cost = 0.0;
     for (size_t i = 0; i < v.size(); ++i) {
-        long pad = (long)((N + v[i].BN - 1) / v[i].BN) * v[i].BN;
-        if (best_pad < 0 || pad < best_pad) {              // ties: the earlier (more register-blocked) entry wins
+        if (v[i].m3 != m3) continue;
+        const double pad = (double)((N + v[i].BN - 1) / v[i].BN) * v[i].BN;
+        const double cost = pad * (1.0 + 24.0 / v[i].BN);
+        if (best < 0 || cost < best_cost) {
             best = (int)i;
-            best_pad = pad;
+            best_cost = cost;
         }
     }
     return v[best];
@@ -146,6 +158,7 @@ struct ldm_context {
     size_t jk_part_bytes = 0;
     EriPlan* plan = nullptr;
     bool attrs_set = false;
+    bool zgemm_3m = true;        // complex products with three real multiplications (see zgemm_tn.cuh)
     // grow-only workspace pool of the ERI pipeline (X, S_sym, S_pln, panel, ring): cudaMalloc/cudaFree of GB-sized
     // buffers costs tens of ms per build and cudaFree synchronises the device, so they are kept across builds
     void* ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -247,6 +260,7 @@ int ldm_create(int device, ldm_handle* out) {
     ldm_context* h = new ldm_context();
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("LDM_ZGEMM_3M")) h->zgemm_3m = atoi(e) != 0;
     LDM_CUDA_OK(cudaMalloc(&h->imag_d, sizeof(unsigned long long)));
     *out = h;
     return ensure_attrs(h);
@@ -265,6 +279,17 @@ int ldm_destroy(ldm_handle h) {
     if (h->jk_part_d) cudaFree(h->jk_part_d);
     delete h;
     return 0;
+}
+
+int ldm_set_option(ldm_handle h, const char* name, int value, int* old_value) {
+    LDM_REQUIRE(h && name, "null pointer");
+    if (std::strcmp(name, "zgemm_3m") == 0) {
+        if (old_value) *old_value = h->zgemm_3m ? 1 : 0;
+        h->zgemm_3m = value != 0;
+        return 0;
+    }
+    set_error(std::string("unknown option: ") + name);
+    return -2;
 }
 
 int ldm_host_alloc(size_t bytes, void** out_h) {
@@ -370,7 +395,7 @@ int ldm_zgemm_tn(ldm_handle h, void* stream, const void* A_d, int za_count, cons
     LDM_REQUIRE(h && A_d && B_d && C_d && segs_h, "null pointer");
     LDM_REQUIRE(M > 0 && N > 0 && K > 0 && nseg > 0 && nbatch > 0, "shape");
     LDM_CUDA_OK(cudaSetDevice(h->device));
-    const ZConfig& cfg = pick_zconfig(N);
+    const ZConfig& cfg = pick_zconfig(N, h->zgemm_3m);
     CUtensorMap tmA, tmB;
     int rc = encode_tmap_f64_3d(&tmA, A_d, 2ull * K, (uint64_t)M, (uint64_t)za_count, 16ull * K, 16ull * K * M, 16,
                                 cfg.BM, true);
@@ -853,7 +878,7 @@ int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int 
     p->ldx = ((long long)p->klg * 2 * p->nauxp + 15) / 16 * 16;
     p->CT = static_cast<const double2*>(CT_d);
     p->eri = eri_d;
-    p->cfg = &pick_zconfig(neo);
+    p->cfg = &pick_zconfig(neo, h->zgemm_3m);
     p->launches0 = h->launches;
     const size_t xt_slice = (size_t)naux * neo * nao;
     const size_t s_elems = (size_t)nspin * naux * neo * neo;

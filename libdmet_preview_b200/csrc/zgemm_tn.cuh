@@ -20,6 +20,13 @@
 //   A: MMA row g of a fragment reads tile row perm(g) = (g>>1)|((g&1)<<2), so the two rows a quarter-warp
 //      touches differ in bit 2 and the swizzle sends them to disjoint bank groups;
 //   B: rows 2q, 2q+1 of a 64-byte slab are one 128-byte line.
+//
+// M3 = true selects the 3-multiplication form of the complex product (Karatsuba / "3M"):
+//   P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi);   Re = P1 - P2,  Im = P3 - P1 - P2
+// i.e. three real DMMAs per complex fragment pair instead of four, for one extra DADD per loaded fragment and a
+// third accumulator set (so the 3M tiles are narrower: FB <= 13).  The kernel is DMMA-bound, so this is a 4/3
+// reduction of the executed tensor work; the result differs from the 4-multiplication form by rounding only
+// (normwise bound of the same order, |error| ~ 1e-15 relative to |A||B| here against the 1e-10 parity bar).
 #pragma once
 #include "common.cuh"
 
@@ -59,7 +66,7 @@ struct ZTile {
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 2 * STAGES * 8;
 };
 
-template <int WM, int WN, int FA, int FB>
+template <int WM, int WN, int FA, int FB, bool M3>
 __global__ void __launch_bounds__((WM * WN + 4) * 32, 1)
 zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ZGemmArgs args) {
@@ -139,13 +146,15 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int tn = rem - tm * args.tiles_n;
         const ZSeg* segs = args.segs + (size_t)b * args.nseg;
 
-        double cr[FA][FB][2], ci[FA][FB][2];
+        // 4M: cr = Re, ci = Im.   3M: cr = P1, ci = P2, cs = P3.
+        double cr[FA][FB][2], ci[FA][FB][2], cs[M3 ? FA : 1][M3 ? FB : 1][2];
 #pragma unroll
         for (int i = 0; i < FA; ++i)
 #pragma unroll
             for (int j = 0; j < FB; ++j) {
                 cr[i][j][0] = cr[i][j][1] = 0.0;
                 ci[i][j][0] = ci[i][j][1] = 0.0;
+                if constexpr (M3) cs[i][j][0] = cs[i][j][1] = 0.0;
             }
 
         for (int s = 0; s < args.nseg; ++s) {
@@ -168,7 +177,8 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         lds128(a_addr + i * 1024, x, y);
                         ar[i] = x;
                         aip[i] = xor_hi(y, mA);               //  sa * Ai
-                        ain[i] = xor_hi(y, mA ^ 0x80000000u); // -sa * Ai
+                        if constexpr (M3) ain[i] = x + aip[i];            // Ar + sa * Ai
+                        else ain[i] = xor_hi(y, mA ^ 0x80000000u);        // -sa * Ai
                     }
                     const uint32_t b_addr = sbase + b_off + kk * T::B_SLAB;
                     // software pipeline over the B fragments: fragment j+1 is in flight while the MMAs of j issue
@@ -178,12 +188,25 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int j = 0; j < FB; ++j) {
                         if (j + 1 < FB) lds128(b_addr + (j + 1) * 512, br_n, bi_n);
                         bi = xor_hi(bi, mB);                  //  sb * Bi
+                        if constexpr (M3) {
+                            // the products that need no operand sum go first: the DADD below has the length of
+                            // 2 FA MMAs to complete before its first consumer issues
 #pragma unroll
-                        for (int i = 0; i < FA; ++i) {
-                            dmma884(cr[i][j][0], cr[i][j][1], ar[i], br);
-                            dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi);
-                            dmma884(cr[i][j][0], cr[i][j][1], ain[i], bi);
-                            dmma884(ci[i][j][0], ci[i][j][1], aip[i], br);
+                            for (int i = 0; i < FA; ++i) {
+                                dmma884(cr[i][j][0], cr[i][j][1], ar[i], br);
+                                dmma884(ci[i][j][0], ci[i][j][1], aip[i], bi);
+                            }
+                            const double bs = br + bi;
+#pragma unroll
+                            for (int i = 0; i < FA; ++i) dmma884(cs[i][j][0], cs[i][j][1], ain[i], bs);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < FA; ++i) {
+                                dmma884(cr[i][j][0], cr[i][j][1], ar[i], br);
+                                dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi);
+                                dmma884(cr[i][j][0], cr[i][j][1], ain[i], bi);
+                                dmma884(ci[i][j][0], ci[i][j][1], aip[i], br);
+                            }
                         }
                         br = br_n;
                         bi = bi_n;
@@ -227,7 +250,12 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int e = 0; e < 2; ++e) {
                         const int c = tn * T::BN + wn * FB * 8 + j * 8 + 2 * t + e;
                         if (c >= args.N) continue;
-                        double2 v = make_double2(alpha * cr[i][j][e], alpha * ci[i][j][e]);
+                        double2 v;
+                        if constexpr (M3)
+                            v = make_double2(alpha * (cr[i][j][e] - ci[i][j][e]),
+                                             alpha * (cs[i][j][e] - cr[i][j][e] - ci[i][j][e]));
+                        else
+                            v = make_double2(alpha * cr[i][j][e], alpha * ci[i][j][e]);
                         if (args.accumulate) {
                             const double2 o = kBatch ? old[jj][e] : Cb[roff + (long long)c * args.s_col];
                             v.x += o.x;

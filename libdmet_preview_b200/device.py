@@ -70,6 +70,13 @@ class Device(object):
     def zeros(self, shape, dtype=torch.float64):
         return torch.zeros(shape, dtype=dtype, device=self.torch_device)
 
+    def set_option(self, name, value):
+        """handle option (include/ldm_b200.h: "zgemm_3m" = 1 three-multiplication complex products, 0 classical);
+        returns the previous value"""
+        old = C.c_int(0)
+        check(self.lib.ldm_set_option(self.h, name.encode(), int(value), C.byref(old)))
+        return old.value
+
     def release_workspaces(self):
         """free the ERI pipeline's cached device workspaces (they are kept between builds otherwise)"""
         check(self.lib.ldm_release_workspaces(self.h))

@@ -23,7 +23,17 @@ def _z(rng, *shape):
     (1, 1, 517, 200, 31, 1, 1, 0, 1, False),     # N = 200 -> 256x40 tile family
     (1, 1, 300, 48, 17, 1, 1, 0, 0, False),      # N = 48 -> b=3 family
 ])
-def test_zgemm_tn(dev, za, zb, M, N, K, nseg, nbatch, cA, cB, acc):
+@pytest.mark.parametrize("m3", [1, 0])
+def test_zgemm_tn(dev, za, zb, M, N, K, nseg, nbatch, cA, cB, acc, m3):
+    """both forms of the complex product: three real multiplications (default) and the classical four"""
+    old = dev.set_option("zgemm_3m", m3)
+    try:
+        _zgemm_case(dev, za, zb, M, N, K, nseg, nbatch, cA, cB, acc)
+    finally:
+        dev.set_option("zgemm_3m", old)
+
+
+def _zgemm_case(dev, za, zb, M, N, K, nseg, nbatch, cA, cB, acc):
     rng = np.random.default_rng(M + N + K)
     A, B = _z(rng, za, M, K), _z(rng, zb, N, K)
     segs = np.zeros((nbatch, nseg, 4), dtype=np.int32)
@@ -41,6 +51,41 @@ def test_zgemm_tn(dev, za, zb, M, N, K, nseg, nbatch, cA, cB, acc):
     dev.zgemm_tn(dev.to_device(A, torch.complex128), dev.to_device(B, torch.complex128), segs, Cd,
                  c_off=np.arange(nbatch) * M * N, s_outer=N, alpha=0.75, accumulate=acc, nbatch=nbatch, nseg=nseg)
     assert np.abs(Cd.cpu().numpy() - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def test_zgemm_3m_rounding_only(dev):
+    """the 3-multiplication form differs from the 4-multiplication form by rounding: both within a few ulp of
+    |A||B| of an exact (integer-valued) product, and the imaginary part has no systematic cancellation error even
+    when |Re| >> |Im|"""
+    rng = np.random.default_rng(5)
+    M, N, K = 256, 150, 200
+    A = (rng.integers(-8, 9, (1, M, K)) + 1j * rng.integers(-8, 9, (1, M, K))).astype(np.complex128)
+    B = (rng.integers(-8, 9, (1, N, K)) + 1j * rng.integers(-8, 9, (1, N, K))).astype(np.complex128)
+    exact = A[0] @ B[0].T                               # integers < 2^53: exact in either form
+    outs = []
+    for m3 in (1, 0):
+        old = dev.set_option("zgemm_3m", m3)
+        Cd = dev.empty((1, M, N), torch.complex128)
+        dev.zgemm_tn(dev.to_device(A, torch.complex128), dev.to_device(B, torch.complex128), [[0, 0, 0, 0]], Cd)
+        dev.set_option("zgemm_3m", old)
+        outs.append(Cd.cpu().numpy()[0])
+        assert np.array_equal(outs[-1], exact)
+    # generic data, nearly real product: Im is ~1e-6 of Re
+    A = _z(rng, 1, M, K)
+    B = _z(rng, 1, N, K)
+    B.imag *= 1e-6
+    A.imag *= 1e-6
+    ref = A[0] @ B[0].T
+    scale = np.abs(A[0]) @ np.abs(B[0]).T
+    for m3 in (1, 0):
+        old = dev.set_option("zgemm_3m", m3)
+        Cd = dev.empty((1, M, N), torch.complex128)
+        dev.zgemm_tn(dev.to_device(A, torch.complex128), dev.to_device(B, torch.complex128), [[0, 0, 0, 0]], Cd)
+        dev.set_option("zgemm_3m", old)
+        err = np.abs(Cd.cpu().numpy()[0] - ref) / scale
+        assert err.max() < 1e-14, (m3, err.max())
+    with pytest.raises(RuntimeError):
+        dev.set_option("no_such_option", 1)
 
 
 def test_zgemm_strided_output(dev):
