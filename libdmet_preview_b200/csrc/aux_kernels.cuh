@@ -247,6 +247,29 @@ ztranspose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int
     }
 }
 
+// The five real planes of the B operand that the 3-multiplication complex GEMM reads (zgemm_tn.cuh):
+//   F[5 z + 0] = Br, [5 z + 1] = Bi - Br, [5 z + 2] = Br + Bi, [5 z + 3] = -(Br + Bi), [5 z + 4] = Br - Bi
+// for every slice z of B (zb, N, K) complex; rows padded to Kp (even) doubles for the 16-byte TMA stride rule.
+__global__ void zforms_kernel(const double2* __restrict__ B, double* __restrict__ F, long long rows, int K, int Kp,
+                              long long N) {
+    const long long total = rows * K;
+    const long long ps = N * Kp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / K;
+        const int k = (int)(idx - r * K);
+        const long long z = r / N, n = r - z * N;
+        const double2 b = B[idx];
+        double* f = F + (5 * z * N + n) * Kp + k;
+        const double sum = b.x + b.y, dif = b.y - b.x;
+        f[0] = b.x;
+        f[ps] = dif;
+        f[2 * ps] = sum;
+        f[3 * ps] = -sum;
+        f[4 * ps] = -dif;
+    }
+}
+
 // real -> complex widening copy (basis in R-space is real; the GEMM operands are complex)
 __global__ void d2z_kernel(const double* __restrict__ in, double2* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -35,10 +35,11 @@ const char* last_error();
     } while (0)
 
 // Encode a rank-3 FP64 tensor map.  dims/strides are given in doubles / bytes, innermost first;
-// box = (box0, box1, 1).  swizzle128: 128-byte swizzle (box0 must be 16 doubles) else no swizzle.
+// box = (box0, box1, 1).  swizzle: 0 none, 1 = 128-byte swizzle (box0 must be 16 doubles), 2 = 64-byte swizzle
+// (box0 must be 8 doubles).
 int encode_tmap_f64_3d(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
-                       bool swizzle128);
+                       int swizzle);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------------------

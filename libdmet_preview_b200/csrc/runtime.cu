@@ -41,7 +41,7 @@ static PFN_encodeTiled get_encode() {
 
 int encode_tmap_f64_3d(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
-                       bool swizzle128) {
+                       int swizzle) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -56,7 +56,9 @@ int encode_tmap_f64_3d(CUtensorMap* map, const void* base, uint64_t dim0, uint64
     cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " dims=(" +
@@ -79,7 +81,7 @@ struct ZConfig {
 
 template <int WM, int WN, int FA, int FB, bool M3 = false>
 static ZConfig make_zconfig() {
-    using T = ZTile<WM, WN, FA, FB>;
+    using T = ZTile<WM, WN, FA, FB, M3>;
     return ZConfig{T::BM, T::BN, T::THREADS, T::SMEM, zgemm_tn_kernel<WM, WN, FA, FB, M3>, M3};
 }
 
@@ -161,11 +163,12 @@ struct ldm_context {
     bool zgemm_3m = true;        // complex products with three real multiplications (see zgemm_tn.cuh)
     // grow-only workspace pool of the ERI pipeline (X, S_sym, S_pln, panel, ring): cudaMalloc/cudaFree of GB-sized
     // buffers costs tens of ms per build and cudaFree synchronises the device, so they are kept across builds
-    void* ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[5] = {0, 0, 0, 0, 0};
+    void* ws[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[7] = {0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t bforms_ev = nullptr;   // last use of the WS_BFORMS planes (ldm_zgemm_tn may be called on any stream)
 };
 
-enum { WS_XT = 0, WS_SSYM = 1, WS_SPLN = 2, WS_PANEL = 3, WS_RING = 4 };
+enum { WS_XT = 0, WS_SSYM = 1, WS_SPLN = 2, WS_PANEL = 3, WS_RING = 4, WS_BFORMS = 5, WS_CTFORMS = 6, WS_COUNT = 7 };
 
 static int ws_get(ldm_handle h, int slot, size_t bytes, void** out) {
     if (h->ws_bytes[slot] < bytes) {
@@ -183,7 +186,7 @@ static int ws_get(ldm_handle h, int slot, size_t bytes, void** out) {
 }
 
 static void ws_release(ldm_handle h) {
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < WS_COUNT; ++i) {
         if (h->ws[i]) cudaFree(h->ws[i]);
         h->ws[i] = nullptr;
         h->ws_bytes[i] = 0;
@@ -276,6 +279,7 @@ int ldm_destroy(ldm_handle h) {
     if (h->scratch_d) cudaFree(h->scratch_d);
     if (h->scratch_h) cudaFreeHost(h->scratch_h);
     if (h->imag_d) cudaFree(h->imag_d);
+    if (h->bforms_ev) cudaEventDestroy(h->bforms_ev);
     if (h->jk_part_d) cudaFree(h->jk_part_d);
     delete h;
     return 0;
@@ -365,6 +369,23 @@ static int launch_zgemm(ldm_handle h, cudaStream_t st, const ZConfig& cfg, const
     return 0;
 }
 
+// B operand of a 3M launch: build the five real planes in workspace `slot` and encode their tensor map
+static int make_bforms(ldm_handle h, cudaStream_t st, int slot, const void* B_d, int zb_count, int N, int K, int BN,
+                       CUtensorMap* tm) {
+    const int Kp = K + (K & 1);
+    void* F = nullptr;
+    int rc = ws_get(h, slot, (size_t)ZFORM_PLANES * zb_count * N * Kp * 8, &F);
+    if (rc) return rc;
+    const long long rows = (long long)zb_count * N;
+    const long long total = rows * K;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16);
+    zforms_kernel<<<grid, 256, 0, st>>>(static_cast<const double2*>(B_d), static_cast<double*>(F), rows, K, Kp, N);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return encode_tmap_f64_3d(tm, F, (uint64_t)K, (uint64_t)N, (uint64_t)ZFORM_PLANES * zb_count, 8ull * Kp,
+                              8ull * Kp * N, 8, BN, 2);
+}
+
 static int launch_dgemm(ldm_handle h, cudaStream_t st, const double* A, long long lda, const double* B, long long ldb,
                         int M, int N, int K, double* C, long long ldc, double alpha, int accumulate, int lower_only) {
     if (M <= 0 || N <= 0) return 0;
@@ -400,8 +421,15 @@ int ldm_zgemm_tn(ldm_handle h, void* stream, const void* A_d, int za_count, cons
     int rc = encode_tmap_f64_3d(&tmA, A_d, 2ull * K, (uint64_t)M, (uint64_t)za_count, 16ull * K, 16ull * K * M, 16,
                                 cfg.BM, true);
     if (rc) return rc;
-    rc = encode_tmap_f64_3d(&tmB, B_d, 2ull * K, (uint64_t)N, (uint64_t)zb_count, 16ull * K, 16ull * K * N, 8, cfg.BN,
-                            false);
+    if (cfg.m3) {
+        // the planes live in one workspace of the handle: order this call behind the previous user's GEMM
+        if (!h->bforms_ev) LDM_CUDA_OK(cudaEventCreateWithFlags(&h->bforms_ev, cudaEventDisableTiming));
+        else LDM_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, h->bforms_ev, 0));
+        rc = make_bforms(h, (cudaStream_t)stream, WS_BFORMS, B_d, zb_count, N, K, cfg.BN, &tmB);
+    } else {
+        rc = encode_tmap_f64_3d(&tmB, B_d, 2ull * K, (uint64_t)N, (uint64_t)zb_count, 16ull * K, 16ull * K * N, 8,
+                                cfg.BN, false);
+    }
     if (rc) return rc;
     std::vector<ZSeg> segs((size_t)nseg * nbatch);
     for (size_t i = 0; i < segs.size(); ++i) {
@@ -418,6 +446,7 @@ int ldm_zgemm_tn(ldm_handle h, void* stream, const void* A_d, int za_count, cons
                       static_cast<double2*>(C_d), c_off_h ? offs.data() : nullptr, rdiv, s_outer, s_inner, s_col,
                       alpha, accumulate);
     if (rc) return rc;
+    if (cfg.m3) LDM_CUDA_OK(cudaEventRecord(h->bforms_ev, (cudaStream_t)stream));
     return 0;
 }
 
@@ -895,7 +924,10 @@ int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int 
     rc = ws_get(h, WS_PANEL, (size_t)nspin * p->npair * p->ldx * 8, &q);
     if (rc) return rc;
     p->XT = static_cast<double*>(q);
-    rc = encode_tmap_f64_3d(&p->tmCT, CT_d, 2ull * nao, (uint64_t)neo, (uint64_t)nspin * nkpts, 16ull * nao,
+    if (p->cfg->m3)
+        rc = make_bforms(h, p->st, WS_CTFORMS, CT_d, nspin * nkpts, neo, nao, p->cfg->BN, &p->tmCT);
+    else
+        rc = encode_tmap_f64_3d(&p->tmCT, CT_d, 2ull * nao, (uint64_t)neo, (uint64_t)nspin * nkpts, 16ull * nao,
                                 16ull * nao * neo, 8, p->cfg->BN, false);
     if (rc) return rc;
     rc = encode_tmap_f64_3d(&p->tmXt, p->Xt, 2ull * nao, (uint64_t)naux * neo, (uint64_t)nspin * p->G, 16ull * nao,

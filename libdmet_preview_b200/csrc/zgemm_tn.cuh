@@ -21,12 +21,17 @@
 //      touches differ in bit 2 and the swizzle sends them to disjoint bank groups;
 //   B: rows 2q, 2q+1 of a 64-byte slab are one 128-byte line.
 //
-// M3 = true selects the 3-multiplication form of the complex product (Karatsuba / "3M"):
-//   P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi);   Re = P1 - P2,  Im = P3 - P1 - P2
-// i.e. three real DMMAs per complex fragment pair instead of four, for one extra DADD per loaded fragment and a
-// third accumulator set (so the 3M tiles are narrower: FB <= 13).  The kernel is DMMA-bound, so this is a 4/3
-// reduction of the executed tensor work; the result differs from the 4-multiplication form by rounding only
-// (normwise bound of the same order, |error| ~ 1e-15 relative to |A||B| here against the 1e-10 parity bar).
+// M3 = true selects the 3-multiplication form of the complex product (Gauss / "3M"):
+//   k1 = (Ar + Ai) Br,  k2 = Ar (Bi - Br),  k3 = Ai (Br + Bi);   Re = k1 - k3,  Im = k1 + k2
+// i.e. three real DMMAs per complex fragment pair instead of four and a third accumulator set (so the 3M tiles are
+// narrower: FB <= 13).  The kernel is DMMA-bound, so this is a 4/3 reduction of the executed tensor work; the result
+// differs from the 4-multiplication form by rounding only (normwise bound of the same order, |error| ~ 1e-15
+// relative to |A||B| here against the 1e-10 parity bar).  All linear forms of B are precomputed in memory
+// (`zforms_kernel`: five real planes Br, D = Bi - Br, S = Br + Bi, -S, -D per slice; conj(B) uses Br, -S, -D), so
+// the producer just picks three planes per segment and the only extra arithmetic in the loop is one DADD per A
+// fragment -- DADDs share the FP64 pipe with the DMMAs and each one costs tensor issue slots.
+// 3M stage: A tile as above; B = 3 planes of BN rows x 64 B (8 real k), 64-byte swizzled by TMA so that the
+// LDS.64 fragment loads of 8 rows x 4 k are bank-conflict free.
 #pragma once
 #include "common.cuh"
 
@@ -53,13 +58,16 @@ struct ZGemmArgs {
     int tiles_m, tiles_n;
 };
 
-template <int WM, int WN, int FA, int FB>
+constexpr int ZFORM_PLANES = 5;      // Br, D, S, -S, -D
+
+template <int WM, int WN, int FA, int FB, bool M3 = false>
 struct ZTile {
     static constexpr int BM = WM * FA * 8;
     static constexpr int BN = WN * FB * 8;
     static constexpr int A_BYTES = BM * 128;
     static constexpr int B_SLAB = BN * 64;
-    static constexpr int STAGE_BYTES = A_BYTES + 2 * B_SLAB;
+    static constexpr int TX_BYTES = A_BYTES + (M3 ? 3 : 2) * B_SLAB;      // what TMA delivers per stage
+    static constexpr int STAGE_BYTES = (TX_BYTES + 1023) / 1024 * 1024;     // stages stay 1024-byte aligned (swizzle)
     static constexpr int NCONS = WM * WN;
     static constexpr int THREADS = (NCONS + 4) * 32;   // + one producer warpgroup
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
@@ -70,7 +78,7 @@ template <int WM, int WN, int FA, int FB, bool M3>
 __global__ void __launch_bounds__((WM * WN + 4) * 32, 1)
 zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ZGemmArgs args) {
-    using T = ZTile<WM, WN, FA, FB>;
+    using T = ZTile<WM, WN, FA, FB, M3>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + T::STAGES * T::STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
@@ -107,14 +115,22 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const ZSeg* segs = args.segs + (size_t)b * args.nseg;
                 for (int s = 0; s < args.nseg; ++s) {
                     const int az = segs[s].az, bz = segs[s].bz;
+                    // 3M: planes (Br, D, S) of slice bz, or (Br, -S, -D) for conj(B)
+                    const int pl0 = ZFORM_PLANES * bz, pl1 = pl0 + (segs[s].conjB ? 3 : 1), pl2 = pl1 + 1;
                     for (int kt = 0; kt < ktiles; ++kt) {
                         mbar_wait(bar_base + 8 * (T::STAGES + stage), phase ^ 1);
                         const uint32_t full = bar_base + 8 * stage;
                         const uint32_t dst = smem_base + stage * T::STAGE_BYTES;
-                        mbar_expect_tx(full, T::STAGE_BYTES);
+                        mbar_expect_tx(full, T::TX_BYTES);
                         tma_load_3d(dst, &tmA, full, kt * 16, tm * T::BM, az);
-                        tma_load_3d(dst + T::A_BYTES, &tmB, full, kt * 16, tn * T::BN, bz);
-                        tma_load_3d(dst + T::A_BYTES + T::B_SLAB, &tmB, full, kt * 16 + 8, tn * T::BN, bz);
+                        if constexpr (M3) {
+                            tma_load_3d(dst + T::A_BYTES, &tmB, full, kt * 8, tn * T::BN, pl0);
+                            tma_load_3d(dst + T::A_BYTES + T::B_SLAB, &tmB, full, kt * 8, tn * T::BN, pl1);
+                            tma_load_3d(dst + T::A_BYTES + 2 * T::B_SLAB, &tmB, full, kt * 8, tn * T::BN, pl2);
+                        } else {
+                            tma_load_3d(dst + T::A_BYTES, &tmB, full, kt * 16, tn * T::BN, bz);
+                            tma_load_3d(dst + T::A_BYTES + T::B_SLAB, &tmB, full, kt * 16 + 8, tn * T::BN, bz);
+                        }
                         if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -131,7 +147,15 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // per-thread smem offsets inside a stage
     const uint32_t a_row_off = (uint32_t)((wm * FA * 8 + pg) * 128);
     const uint32_t a_c0 = (uint32_t)((t ^ pg) * 16);       // k-step 0 ; k-step 1 is a_c0 ^ 64
-    const uint32_t b_off = (uint32_t)(T::A_BYTES + (wn * FB * 8 + g) * 64 + t * 16);
+    // 4M: (re, im) of k = 4 kk + t in slab kk.
+    // 3M: real word k = 4 kk + t of a 64-byte-swizzled row (16-byte chunk index xor ((row >> 1) & 3)).  64-bit
+    // shared loads are served per half-warp (MMA rows g = 0..3 / 4..7), so MMA column g reads tile row
+    // permB(g) = g with bits 1 and 2 swapped: rows {0,1,4,5} / {2,3,6,7} then fall into four different 32-byte bank
+    // groups.  The epilogue applies the same permutation to the output column.  kk = 1 is b_off ^ 32.
+    const int pgb = (g & 1) | ((g & 2) << 1) | ((g & 4) >> 1);
+    const uint32_t b_off = M3 ? (uint32_t)(T::A_BYTES + (wn * FB * 8 + pgb) * 64 +
+                                           (((t >> 1) ^ ((pgb >> 1) & 3)) << 4) + (t & 1) * 8)
+                              : (uint32_t)(T::A_BYTES + (wn * FB * 8 + g) * 64 + t * 16);
 
     // A stage is handed back to the producer one iteration late, right after the wait for the NEXT stage: the
     // wait loop is a control-flow boundary behind all MMAs of the previous stage, so every fragment load of that
@@ -146,7 +170,7 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int tn = rem - tm * args.tiles_n;
         const ZSeg* segs = args.segs + (size_t)b * args.nseg;
 
-        // 4M: cr = Re, ci = Im.   3M: cr = P1, ci = P2, cs = P3.
+        // 4M: cr = Re, ci = Im.   3M: cr = k1, ci = k2, cs = k3.
         double cr[FA][FB][2], ci[FA][FB][2], cs[M3 ? FA : 1][M3 ? FB : 1][2];
 #pragma unroll
         for (int i = 0; i < FA; ++i)
@@ -180,26 +204,37 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if constexpr (M3) ain[i] = x + aip[i];            // Ar + sa * Ai
                         else ain[i] = xor_hi(y, mA ^ 0x80000000u);        // -sa * Ai
                     }
-                    const uint32_t b_addr = sbase + b_off + kk * T::B_SLAB;
-                    // software pipeline over the B fragments: fragment j+1 is in flight while the MMAs of j issue
-                    double br, bi, br_n = 0.0, bi_n = 0.0;
-                    lds128(b_addr, br, bi);
+                    if constexpr (M3) {
+                        // ain[i] holds Ar + sa Ai.  Fragment j+1 is in flight while the MMAs of j issue.
+                        const uint32_t b_addr = sbase + (b_off ^ (kk * 32));
+                        double f0 = lds64(b_addr), f1 = lds64(b_addr + T::B_SLAB), f2 = lds64(b_addr + 2 * T::B_SLAB);
+                        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
-                    for (int j = 0; j < FB; ++j) {
-                        if (j + 1 < FB) lds128(b_addr + (j + 1) * 512, br_n, bi_n);
-                        bi = xor_hi(bi, mB);                  //  sb * Bi
-                        if constexpr (M3) {
-                            // the products that need no operand sum go first: the DADD below has the length of
-                            // 2 FA MMAs to complete before its first consumer issues
+                        for (int j = 0; j < FB; ++j) {
+                            if (j + 1 < FB) {
+                                g0 = lds64(b_addr + (j + 1) * 512);
+                                g1 = lds64(b_addr + (j + 1) * 512 + T::B_SLAB);
+                                g2 = lds64(b_addr + (j + 1) * 512 + 2 * T::B_SLAB);
+                            }
 #pragma unroll
                             for (int i = 0; i < FA; ++i) {
-                                dmma884(cr[i][j][0], cr[i][j][1], ar[i], br);
-                                dmma884(ci[i][j][0], ci[i][j][1], aip[i], bi);
+                                dmma884(cr[i][j][0], cr[i][j][1], ain[i], f0);     // k1 = (Ar + Ai) Br
+                                dmma884(ci[i][j][0], ci[i][j][1], ar[i], f1);      // k2 = Ar (Bi - Br)
+                                dmma884(cs[i][j][0], cs[i][j][1], aip[i], f2);     // k3 = Ai (Br + Bi)
                             }
-                            const double bs = br + bi;
+                            f0 = g0;
+                            f1 = g1;
+                            f2 = g2;
+                        }
+                    } else {
+                        const uint32_t b_addr = sbase + b_off + kk * T::B_SLAB;
+                        // software pipeline over the B fragments: fragment j+1 is in flight while the MMAs of j issue
+                        double br, bi, br_n = 0.0, bi_n = 0.0;
+                        lds128(b_addr, br, bi);
 #pragma unroll
-                            for (int i = 0; i < FA; ++i) dmma884(cs[i][j][0], cs[i][j][1], ain[i], bs);
-                        } else {
+                        for (int j = 0; j < FB; ++j) {
+                            if (j + 1 < FB) lds128(b_addr + (j + 1) * 512, br_n, bi_n);
+                            bi = xor_hi(bi, mB);                  //  sb * Bi
 #pragma unroll
                             for (int i = 0; i < FA; ++i) {
                                 dmma884(cr[i][j][0], cr[i][j][1], ar[i], br);
@@ -207,9 +242,9 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 dmma884(cr[i][j][0], cr[i][j][1], ain[i], bi);
                                 dmma884(ci[i][j][0], ci[i][j][1], aip[i], br);
                             }
+                            br = br_n;
+                            bi = bi_n;
                         }
-                        br = br_n;
-                        bi = bi_n;
                     }
                 }
                 prev_stage = stage;
@@ -222,6 +257,7 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // only then stores: a load/store chain per element would expose one DRAM round trip per element.
         double2* Cb = args.C + (args.c_off ? args.c_off[b] : 0ll);
         const double alpha = args.alpha;
+        auto col_in_frag = [](int q) { return M3 ? ((q & 1) | ((q & 2) << 1) | ((q & 4) >> 1)) : q; };
         constexpr int JB = FB > 23 ? 1 : (FB > 20 ? 2 : 4);   // the widest tiles have no registers to spare
         constexpr bool kBatch = FB <= 23;
 #pragma unroll
@@ -237,7 +273,7 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int jj = 0; jj < JB; ++jj)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const int c = tn * T::BN + wn * FB * 8 + (j0 + jj) * 8 + 2 * t + e;
+                            const int c = tn * T::BN + wn * FB * 8 + (j0 + jj) * 8 + col_in_frag(2 * t + e);
                             old[jj][e] = (j0 + jj < FB && c < args.N) ? Cb[roff + (long long)c * args.s_col]
                                                                       : make_double2(0.0, 0.0);
                         }
@@ -248,12 +284,12 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int j = j0 + jj;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int c = tn * T::BN + wn * FB * 8 + j * 8 + 2 * t + e;
+                        const int c = tn * T::BN + wn * FB * 8 + j * 8 + col_in_frag(2 * t + e);
                         if (c >= args.N) continue;
                         double2 v;
                         if constexpr (M3)
-                            v = make_double2(alpha * (cr[i][j][e] - ci[i][j][e]),
-                                             alpha * (cs[i][j][e] - cr[i][j][e] - ci[i][j][e]));
+                            v = make_double2(alpha * (cr[i][j][e] - cs[i][j][e]),
+                                             alpha * (cr[i][j][e] + ci[i][j][e]));
                         else
                             v = make_double2(alpha * cr[i][j][e], alpha * ci[i][j][e]);
                         if (args.accumulate) {
