@@ -77,14 +77,20 @@ class ClockSampler(object):
         self.samples = []
         self.stop = False
         self.th = threading.Thread(target=self.run, daemon=True)
+        # NVML is initialised here, before the timed region: nvmlInit takes ~15 ms and serialises with CUDA calls
+        self.nv = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = (nv, nv.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self.nv = None
 
     def _nvml(self):
         """in-process NVML sampling (no fork per sample, nothing that stalls the driver for milliseconds)"""
-        import pynvml as nv
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
-                 else nv.nvmlClocksThrottleReasonHwSlowdown),
+        nv, h = self.nv
+        bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown",
+                                        getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
                 ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
                                                 getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
@@ -105,11 +111,12 @@ class ClockSampler(object):
             time.sleep(0.05)
 
     def run(self):
-        try:
-            self._nvml()
-            return
-        except Exception:
-            pass
+        if self.nv is not None:
+            try:
+                self._nvml()
+                return
+            except Exception:
+                pass
         while not self.stop:
             try:
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -331,7 +338,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step()
+        step({})                  # same code path as the timed steps (kernel-time events included)
     barrier()
     l0 = dev.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
