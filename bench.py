@@ -459,15 +459,22 @@ def run_ours(args):
         Lat.set_Ham(None, gdf, C_ao_lo_h, eri_symmetry=4, ovlp=ovlp, hcore=hcore, rdm1=rdm1, vhf=vhf)
         torch.cuda.synchronize()
         t_set = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        bas = slater.get_emb_basis(Lat, Lat.rdm1_lo_R * 0.5)
-        t_basis = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        Ham, _ = slater.embHam(Lat, bas, None, group=args.group, kl_group=args.kl_group)
-        torch.cuda.synchronize()
-        t_ham = time.perf_counter() - t0
+        # two iterations: the first pays one-off costs (page-locking the 1 GB result buffer, pipeline workspaces),
+        # the second is what every further DMET iteration costs
+        first = None
+        for it in range(2):
+            t0 = time.perf_counter()
+            bas = slater.get_emb_basis(Lat, Lat.rdm1_lo_R * 0.5)
+            t_basis = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            Ham, _ = slater.embHam(Lat, bas, None, group=args.group, kl_group=args.kl_group)
+            torch.cuda.synchronize()
+            t_ham = time.perf_counter() - t0
+            if first is None:
+                first = t_basis + t_ham
+            del Ham
         dmet_iter = {"seconds": t_basis + t_ham, "get_emb_basis_s": t_basis, "embHam_s": t_ham,
-                     "set_Ham_once_s": t_set, "neo": int(bas.shape[-1]),
+                     "first_iteration_s": first, "set_Ham_once_s": t_set, "neo": int(bas.shape[-1]),
                      "note": "ConstructImpHam of this path (libdmet/dmet/HubPhSymm.py:74-100): bath SVD on the host, "
                              "ERI build with the GDF blocks generated on the device, one-body part and J/K on the "
                              "device, results returned as numpy"}
