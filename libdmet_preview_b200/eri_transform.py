@@ -145,14 +145,34 @@ class ResidentGDF(object):
 
 
 def as_provider(cell, mydf):
-    """Accept an in-memory provider (duck-typed: .kpts_scaled .kmesh .nao .naux .load) or a PySCF GDF."""
+    """Accept an in-memory provider (duck-typed: .kpts_scaled .kmesh .nao .naux .load), a PySCF GDF, or any object
+    carrying the three members of a GDF this path reads -- `_cderi` (path of the cderi file), `kpts`, `cell` --
+    which is served from the file by `gdf_file.GDFFile` (no PySCF needed)."""
     if all(hasattr(mydf, a) for a in ("kpts_scaled", "nao", "naux", "load")):
         return mydf
     try:
         from pyscf.pbc import df as _pdf
     except ImportError:
         _pdf = None
-    if _pdf is not None and isinstance(mydf, _pdf.GDF) and not isinstance(mydf, _pdf.MDF):
+    if _pdf is not None:
+        if not isinstance(mydf, _pdf.GDF) or isinstance(mydf, _pdf.MDF):
+            raise ValueError("Unknown DF type for embedding ERI construction.")     # eri_transform.py:89
+        if mydf._cderi is None:
+            mydf.build()                                                            # sr_loop, l.197-198
+    cderi = getattr(mydf, "_cderi", None)
+    if isinstance(cderi, str) and hasattr(mydf, "kpts"):
+        import os
+        from .gdf_file import GDFFile
+        from . import h5lite
+        if os.path.exists(cderi):
+            try:
+                prov = GDFFile(cderi, cell=cell if cell is not None else getattr(mydf, "cell", None), kpts=mydf.kpts)
+                prov.blockdim = getattr(mydf, "blockdim", prov.blockdim)
+                return prov
+            except h5lite.H5FormatError:
+                if _pdf is None:
+                    raise
+    if _pdf is not None:
         return PyscfGDFProvider(cell, mydf)
     raise ValueError("Unknown DF type for embedding ERI construction.")     # eri_transform.py:89
 
@@ -675,20 +695,18 @@ class LoGDF(object):
         return np.ascontiguousarray(self._unpacked(self._pos[(kj, ki)]).conj().transpose(0, 2, 1))
 
     def save(self, fname):
-        """write the reference's file layout (`j3c-kptij`, `j3c/<pos>/0`); needs h5py, or a name ending in .npz"""
+        """write the reference's file layout (`j3c-kptij`, `j3c/<pos>/0`; eri_transform.py:1357-1398) through
+        `h5lite.Writer`; a name ending in .npz gives a numpy archive instead"""
         kptij = np.asarray([(self.kpts[i], self.kpts[j]) for i, j in self.kptij_idx]) if self.kpts is not None \
             else np.asarray([(self.kpts_scaled[i], self.kpts_scaled[j]) for i, j in self.kptij_idx])
         if fname.endswith(".npz"):
             np.savez(fname, **{"j3c-kptij": kptij}, **{"j3c/%d/0" % k: v for k, v in self.j3c.items()})
             return
-        try:
-            import h5py
-        except ImportError:
-            raise RuntimeError("writing %s needs h5py (not installed); pass fname=None or a .npz name" % fname)
-        with h5py.File(fname, "w") as f:
+        from . import h5lite
+        with h5lite.Writer(fname) as f:
             f["j3c-kptij"] = kptij
-            for k, v in self.j3c.items():
-                f["j3c/%d/0" % k] = v
+            for k in sorted(self.j3c):
+                f["j3c/%d/0" % k] = self.j3c[k]
 
 
 def transform_gdf_to_lo(mydf, C_ao_lo, fname="gdf_ints_lo.h5", t_reversal_symm=True, **kwargs):
@@ -749,8 +767,13 @@ def transform_gdf_to_lo(mydf, C_ao_lo, fname="gdf_ints_lo.h5", t_reversal_symm=T
     out = LoGDF(provider, nlo, pairs, j3c)
     if fname is not None:
         out.save(fname)
-        if isinstance(provider, PyscfGDFProvider):
-            mydf_lo = mydf.__class__(out.cell if nlo != nao else mydf.cell, mydf.kpts)
+        if provider is not mydf:     # a GDF object came in: hand a GDF object back whose _cderi is the new file
+            try:                     # (l.1399-1407)
+                mydf_lo = mydf.__class__(out.cell if nlo != nao else mydf.cell, mydf.kpts)
+            except TypeError:
+                import copy
+                mydf_lo = copy.copy(mydf)
+                mydf_lo.cell = out.cell if nlo != nao else mydf.cell
             mydf_lo._cderi = fname
             return mydf_lo
     return out

@@ -1,0 +1,926 @@
+"""Reader and writer for the subset of the HDF5 file format that PySCF's density-fitting files use.
+
+The reference reads its GDF tensor through h5py (`eri_transform.py:159-227`: `get_naoaux`, `sr_loop` -> PySCF
+`_load3c` over `j3c/<pair>/<segment>` datasets and the `j3c-kptij` list) and writes the LO-basis tensor the same way
+(`eri_transform.py:1357-1398`).  h5py / libhdf5 are not available in this image, so this module implements the file
+format directly -- only what those files contain, as written by libhdf5 with its default ("earliest") format
+settings:
+
+    superblock version 0 / 1 (and 2 / 3 headers pointing at version-1 object headers), user block
+    "old style" groups: symbol-table message -> version-1 B-tree + local heap + symbol-table nodes (any depth)
+    version-1 object headers with continuation blocks
+    dataspace messages version 1 / 2 (simple, scalar), no maximum dimensions needed
+    datatypes: fixed point, IEEE floating point, fixed-length strings, compounds of those (h5py stores complex128
+               as the compound {"r": f64, "i": f64}, bit-identical to numpy complex128)
+    data layouts: compact, contiguous, chunked (version-1 chunk B-tree; optional deflate + shuffle filters)
+
+Anything else raises `H5FormatError` by name (new-style groups with fractal heaps, variable-length data, external
+files, version-4 layouts, virtual datasets).  Metadata is parsed in Python -- a GDF file holds a few thousand small
+headers -- while array payloads never pass through Python objects: `Dataset.read_direct` issues `preadv`-style reads
+straight into the caller's (pinned) buffer and `Dataset.memmap` maps contiguous datasets in place.
+
+The writer produces the same flavour of file (superblock 0, symbol-table groups with one B-tree level, contiguous
+little-endian datasets).  It has been checked only against this reader (which in turn is checked against a file
+written by the real HDF5 library, see tests/test_h5lite.py), not against libhdf5 itself.
+"""
+import os
+import struct
+import zlib
+
+import numpy as np
+
+UNDEF = 0xFFFFFFFFFFFFFFFF
+SIGNATURE = b"\x89HDF\r\n\x1a\n"
+
+
+class H5FormatError(IOError):
+    """the file uses a feature outside the supported subset, or is not HDF5 at all"""
+
+
+# ---------------------------------------------------------------------------------------------------------
+# low-level cursor
+# ---------------------------------------------------------------------------------------------------------
+class _Cur(object):
+    """little-endian cursor over a bytes object"""
+    __slots__ = ("b", "p")
+
+    def __init__(self, b, p=0):
+        self.b, self.p = b, p
+
+    def u(self, n):
+        v = int.from_bytes(self.b[self.p:self.p + n], "little")
+        self.p += n
+        return v
+
+    def raw(self, n):
+        v = self.b[self.p:self.p + n]
+        self.p += n
+        return v
+
+    def skip(self, n):
+        self.p += n
+
+    def align(self, n, origin=0):
+        r = (self.p - origin) % n
+        if r:
+            self.p += n - r
+
+    def cstr(self):
+        e = self.b.index(b"\0", self.p)
+        s = self.b[self.p:e]
+        self.p = e + 1
+        return s
+
+
+# ---------------------------------------------------------------------------------------------------------
+# datatype message <-> numpy dtype
+# ---------------------------------------------------------------------------------------------------------
+def _parse_dtype(c):
+    """datatype message at cursor c -> numpy dtype (cursor is left behind the message)"""
+    b0 = c.u(1)
+    cls, ver = b0 & 0x0F, b0 >> 4
+    bits = c.u(3)
+    size = c.u(4)
+    if cls == 0:                                            # fixed point
+        c.skip(4)                                           # bit offset, precision
+        if bits & 1:
+            order = ">"
+        else:
+            order = "<"
+        return np.dtype("%s%s%d" % (order, "i" if bits & 8 else "u", size))
+    if cls == 1:                                            # floating point
+        c.skip(12)
+        if size not in (2, 4, 8):
+            raise H5FormatError("floating-point type of %d bytes" % size)
+        return np.dtype("%sf%d" % (">" if bits & 1 else "<", size))
+    if cls == 3:                                            # fixed-length string
+        return np.dtype("S%d" % size)
+    if cls == 6:                                            # compound
+        nmemb = bits & 0xFFFF
+        names, formats, offsets = [], [], []
+        for _ in range(nmemb):
+            start = c.p
+            name = c.cstr()
+            if ver < 3:
+                c.align(8, start)
+                off = c.u(4)
+            else:
+                nb = 1
+                while size >> (8 * nb):
+                    nb += 1
+                off = c.u(nb)
+            dims = ()
+            if ver == 1:
+                rank = c.u(1)
+                c.skip(3 + 4 + 4)
+                d = [c.u(4) for _ in range(4)]
+                dims = tuple(d[:rank])
+            sub = _parse_dtype(c)
+            names.append(name.decode())
+            formats.append((sub, dims) if dims else sub)
+            offsets.append(off)
+        dt = np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": size})
+        return _complex_view(dt)
+    if cls == 9:                                            # variable length: strings only (h5py stores str that way)
+        base = _parse_dtype(c)
+        if bits & 0x0F != 1:
+            raise H5FormatError("variable-length sequences of %s are not supported" % base)
+        return np.dtype("O", metadata={"vlen_str_bytes": size})
+    if cls == 10:                                           # array (inside compounds written by newer libraries)
+        rank = c.u(1)
+        if ver == 2:
+            c.skip(3)
+        dims = tuple(c.u(4) for _ in range(rank))
+        if ver == 2:
+            c.skip(4 * rank)
+        sub = _parse_dtype(c)
+        return np.dtype((sub, dims))
+    raise H5FormatError("datatype class %d is not supported (variable-length, reference, enum, ...)" % cls)
+
+
+def _complex_view(dt):
+    """h5py's complex convention: compound {"r", "i"} of two equal floats -> numpy complex"""
+    if dt.names == ("r", "i") and dt.fields["r"][0] == dt.fields["i"][0] and dt.fields["r"][0].kind == "f" \
+            and dt.fields["r"][1] == 0 and dt.fields["i"][1] == dt.fields["r"][0].itemsize \
+            and dt.itemsize == 2 * dt.fields["r"][0].itemsize:
+        f = dt.fields["r"][0]
+        return np.dtype("%sc%d" % (f.byteorder if f.byteorder in "<>" else "<", dt.itemsize))
+    return dt
+
+
+def _encode_dtype(dt):
+    """numpy dtype -> datatype message bytes (version 1 encodings, little endian)"""
+    dt = np.dtype(dt)
+    if dt.kind == "c":
+        f = np.dtype("<f%d" % (dt.itemsize // 2))
+        body = b""
+        for name, off in (("r", 0), ("i", f.itemsize)):
+            body += name.encode().ljust(8, b"\0") + struct.pack("<IB3xI4x4I", off, 0, 0, 0, 0, 0, 0)
+            body += _encode_dtype(f)
+        return struct.pack("<BBBBI", 0x16, 2, 0, 0, dt.itemsize) + body
+    if dt.byteorder == ">":
+        raise H5FormatError("the writer stores little-endian data only")
+    if dt.kind in "iu":
+        bits = 8 if dt.kind == "i" else 0
+        return struct.pack("<BBBBIHH", 0x10, bits, 0, 0, dt.itemsize, 0, 8 * dt.itemsize)
+    if dt.kind == "f":
+        # bit field: little endian, implied msb normalisation (0x20), sign location in byte 1
+        prec = 8 * dt.itemsize
+        expo = {2: (10, 5, 15), 4: (23, 8, 127), 8: (52, 11, 1023)}[dt.itemsize]
+        return struct.pack("<BBBBIHHBBBBI", 0x11, 0x20, prec - 1, 0, dt.itemsize, 0, prec, expo[0], expo[1], 0,
+                           expo[0], expo[2])
+    if dt.kind == "S":
+        return struct.pack("<BBBBI", 0x13, 0, 0, 0, dt.itemsize)        # null-terminated ASCII
+    raise H5FormatError("cannot store dtype %s" % dt)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reader
+# ---------------------------------------------------------------------------------------------------------
+def _byte_view(out):
+    """writable flat byte view of a C-contiguous numpy array (or of anything exposing a plain buffer)"""
+    if isinstance(out, np.ndarray):
+        if not out.flags.c_contiguous or not out.flags.writeable:
+            raise ValueError("destination must be a writable C-contiguous array")
+        return memoryview(out.reshape(-1).view(np.uint8))
+    return memoryview(out).cast("B")
+
+
+def _byte_view_ro(a):
+    return memoryview(a.reshape(-1).view(np.uint8))
+
+
+class _Node(object):
+    def __init__(self, f, name, addr):
+        self.file, self.name, self._addr = f, name, addr
+
+    def __repr__(self):
+        return "<%s %r>" % (type(self).__name__, self.name)
+
+
+class Dataset(_Node):
+    """one dataset: `.shape`, `.dtype`, `ds[...]` (numpy indexing on the first axis is served by partial reads for
+    contiguous data), `.read_direct(out, rows=slice)` into a caller buffer, `.memmap()` for contiguous layouts"""
+
+    def __init__(self, f, name, addr, msgs):
+        _Node.__init__(self, f, name, addr)
+        self.shape, self.dtype = None, None
+        self._layout = None
+        self._filters = []
+        for mtype, body in msgs:
+            c = _Cur(body)
+            if mtype == 0x01:
+                self.shape = self._dataspace(c)
+            elif mtype == 0x03:
+                self.dtype = _parse_dtype(c)
+            elif mtype == 0x08:
+                self._layout = self._parse_layout(c)
+            elif mtype == 0x0B:
+                self._filters = self._parse_filters(c)
+        if self.shape is None or self.dtype is None or self._layout is None:
+            raise H5FormatError("%s: incomplete dataset header" % name)
+
+    # -- header messages ---------------------------------------------------------------------------
+    def _dataspace(self, c):
+        ver = c.u(1)
+        rank = c.u(1)
+        c.u(1)                       # flags: maximum dimensions follow the sizes and are not needed
+        if ver == 1:
+            c.skip(5)
+        elif ver == 2:
+            if c.u(1) == 2:
+                raise H5FormatError("%s: null dataspace" % self.name)
+        else:
+            raise H5FormatError("dataspace message version %d" % ver)
+        L = self.file._L
+        return tuple(c.u(L) for _ in range(rank))
+
+    def _parse_layout(self, c):
+        O, L = self.file._O, self.file._L
+        ver = c.u(1)
+        if ver in (1, 2):
+            rank = c.u(1)
+            cls = c.u(1)
+            c.skip(5)
+            addr = c.u(O) if cls != 0 else None
+            dims = [c.u(4) for _ in range(rank)]
+            if cls == 2:
+                c.u(4)               # element size
+                return ("chunked", addr, tuple(dims))
+            if cls == 1:
+                return ("contiguous", addr, None)
+            n = c.u(4)
+            return ("compact", c.raw(n), None)
+        if ver == 3:
+            cls = c.u(1)
+            if cls == 0:
+                n = c.u(2)
+                return ("compact", c.raw(n), None)
+            if cls == 1:
+                addr = c.u(O)
+                c.u(L)
+                return ("contiguous", addr, None)
+            if cls == 2:
+                rank = c.u(1)
+                addr = c.u(O)
+                dims = [c.u(4) for _ in range(rank)]
+                return ("chunked", addr, tuple(dims[:-1]))
+            raise H5FormatError("%s: layout class %d" % (self.name, cls))
+        raise H5FormatError("%s: data layout message version %d (written with libver='latest'?)" % (self.name, ver))
+
+    def _parse_filters(self, c):
+        ver = c.u(1)
+        n = c.u(1)
+        if ver == 1:
+            c.skip(6)
+        out = []
+        for _ in range(n):
+            fid = c.u(2)
+            nlen = c.u(2) if (ver == 1 or fid >= 256) else 0
+            c.u(2)
+            ncd = c.u(2)
+            if nlen:
+                c.skip(nlen if ver > 1 else (nlen + 7) // 8 * 8)
+            cd = [c.u(4) for _ in range(ncd)]
+            if ver == 1 and ncd % 2:
+                c.skip(4)
+            if fid not in (1, 2, 3):
+                raise H5FormatError("%s: filter %d is not supported (only deflate, shuffle, fletcher32)"
+                                    % (self.name, fid))
+            out.append((fid, cd))
+        return out
+
+    # -- data access -------------------------------------------------------------------------------
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def _row_bytes(self):
+        return (int(np.prod(self.shape[1:], dtype=np.int64)) if len(self.shape) > 1 else 1) * self.dtype.itemsize
+
+    def file_extent(self):
+        """(absolute file offset, nbytes) of a contiguous dataset's payload, None otherwise -- what a direct-storage
+        or pinned-buffer reader needs"""
+        kind, addr, _ = self._layout
+        if kind != "contiguous" or addr == self.file._undef:
+            return None
+        return self.file._base + addr, self.nbytes
+
+    def memmap(self):
+        if self._layout[0] != "contiguous":
+            raise H5FormatError("%s: only contiguous datasets can be mapped" % self.name)
+        ext = self.file_extent()
+        if ext is None or self.nbytes == 0:                 # nothing allocated in the file
+            return np.zeros(self.shape, self.dtype)
+        return np.memmap(self.file._path, dtype=self.dtype, mode="r", offset=ext[0], shape=self.shape)
+
+    def read_direct(self, out, rows=None):
+        """fill the C-contiguous array `out` with rows [r0, r1) of the first axis (all rows by default)"""
+        r0, r1, _ = (rows or slice(None)).indices(self.shape[0] if self.shape else 1)
+        rb = self._row_bytes()
+        nbytes = max(0, r1 - r0) * rb
+        buf = _byte_view(out)
+        if buf.nbytes != nbytes:
+            raise ValueError("%s: destination holds %d bytes, the selection %d" % (self.name, buf.nbytes, nbytes))
+        if nbytes == 0:
+            return out
+        kind, addr, chunk = self._layout
+        if kind == "contiguous":
+            if addr == self.file._undef:                   # never written: fill value 0
+                buf[:] = bytes(nbytes)
+            else:
+                self.file._pread_into(buf, self.file._base + addr + r0 * rb)
+        elif kind == "compact":
+            buf[:] = addr[r0 * rb:r1 * rb]
+        else:
+            full = self._read_chunked()
+            buf[:] = memoryview(np.ascontiguousarray(full[r0:r1])).cast("B")
+        return out
+
+    def _read_chunked(self):
+        _, addr, chunk = self._layout
+        out = np.zeros(self.shape, self.dtype)
+        if addr == self.file._undef:
+            return out
+        esz = self.dtype.itemsize
+        for offs, nbytes, mask, caddr in self.file._chunk_leaves(addr, len(self.shape)):
+            raw = self.file._pread(self.file._base + caddr, nbytes)
+            for n, (fid, cd) in reversed(list(enumerate(self._filters))):
+                if mask >> n & 1:
+                    continue
+                if fid == 1:
+                    raw = zlib.decompress(raw)
+                elif fid == 2:
+                    a = np.frombuffer(raw, np.uint8)
+                    k = len(a) // esz
+                    raw = a[:k * esz].reshape(esz, k).T.tobytes() + a[k * esz:].tobytes()
+                elif fid == 3:
+                    raw = raw[:-4]
+            blk = np.frombuffer(raw, self.dtype, count=int(np.prod(chunk))).reshape(chunk)
+            sel_out = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, chunk, self.shape))
+            sel_blk = tuple(slice(0, s.stop - s.start) for s in sel_out)
+            out[sel_out] = blk[sel_blk]
+        return out
+
+    def _read_vlen_str(self):
+        """variable-length strings: every element is (length, global-heap collection address, object index)"""
+        f = self.file
+        esz = self.dtype.metadata["vlen_str_bytes"]
+        raw = np.empty(self.size * esz, np.uint8)
+        fixed = Dataset.__new__(Dataset)
+        fixed.__dict__.update(self.__dict__)
+        fixed.dtype, fixed.shape = np.dtype("V%d" % esz), (self.size,)
+        fixed.read_direct(raw.view(fixed.dtype))
+        out = np.empty(self.size, object)
+        for n in range(self.size):
+            c = _Cur(raw[n * esz:(n + 1) * esz].tobytes())
+            length, coll, idx = c.u(4), c.u(f._O), c.u(4)
+            out[n] = f._global_heap_object(coll, idx)[:length].decode("utf-8") if length else ""
+        return out.reshape(self.shape)
+
+    def __getitem__(self, key):
+        if self.dtype.metadata and "vlen_str_bytes" in self.dtype.metadata:
+            out = self._read_vlen_str()
+            return out[()] if key == () or key is Ellipsis else out[key]
+        if not self.shape:
+            out = np.empty((), self.dtype)
+            self.read_direct(out.reshape(1))
+            return out[()] if key == () or key is Ellipsis else out[key]
+        if isinstance(key, tuple) and len(key) == 0:
+            key = Ellipsis
+        first = key[0] if isinstance(key, tuple) else key
+        rest = key[1:] if isinstance(key, tuple) else ()
+        if isinstance(first, slice) and first.step in (None, 1) and self._layout[0] != "chunked":
+            r0, r1, _ = first.indices(self.shape[0])
+            out = np.empty((max(0, r1 - r0),) + self.shape[1:], self.dtype)
+            self.read_direct(out, slice(r0, r1))
+            return out[(slice(None),) + rest] if rest else out
+        out = np.empty(self.shape, self.dtype)
+        self.read_direct(out)
+        return out[key]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self[...]
+        return a if dtype is None else a.astype(dtype)
+
+
+class Group(_Node):
+    """old-style group: names resolved through the group's B-tree and local heap"""
+
+    def __init__(self, f, name, addr, btree, heap):
+        _Node.__init__(self, f, name, addr)
+        self._btree, self._heap = btree, heap
+        self._links = None
+
+    def _load(self):
+        if self._links is None:
+            f = self.file
+            heap_data = f._local_heap(self._heap)
+            links = {}
+            for name_off, obj_addr in f._group_leaves(self._btree):
+                e = heap_data.index(b"\0", name_off)
+                links[heap_data[name_off:e].decode()] = obj_addr
+            self._links = links
+        return self._links
+
+    def keys(self):
+        return list(self._load().keys())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self._load())
+
+    def __contains__(self, path):
+        try:
+            self[path]
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, path):
+        node = self
+        if path.startswith("/"):
+            node = self.file._root
+        for part in [p for p in path.split("/") if p]:
+            if not isinstance(node, Group):
+                raise KeyError(path)
+            links = node._load()
+            if part not in links:
+                raise KeyError("%s (no member %r in %s)" % (path, part, node.name))
+            child = (node.name.rstrip("/") + "/" + part)
+            node = node.file._object(child, links[part])
+        return node
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+
+class File(Group):
+    """read-only view of an HDF5 file: `with File(path) as f: f["j3c/0/0"][:]`"""
+
+    def __init__(self, path, mode="r"):
+        if mode != "r":
+            raise ValueError("h5lite.File is read-only; use h5lite.Writer to create files")
+        self._path = path
+        self._fd = os.open(path, os.O_RDONLY)
+        try:
+            self._superblock()
+        except Exception:
+            os.close(self._fd)
+            self._fd = None
+            raise
+        self._cache = {}
+        root = self._object("/", self._root_addr, root_hint=self._root_hint)
+        if not isinstance(root, Group):
+            raise H5FormatError("root object is not a group")
+        Group.__init__(self, self, "/", root._addr, root._btree, root._heap)
+        self._root = self
+
+    # -- plumbing ----------------------------------------------------------------------------------
+    def close(self):
+        if self._fd is not None:
+            os.close(self._fd)
+            self._fd = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _pread(self, off, n):
+        out = bytearray(n)
+        self._pread_into(memoryview(out), off)
+        return bytes(out)
+
+    def _pread_into(self, buf, off):
+        """fill the writable byte view `buf` from file offset `off` (large reads are split: one preadv call moves
+        at most 2 GiB on Linux)"""
+        done, n = 0, buf.nbytes
+        while done < n:
+            got = os.preadv(self._fd, [buf[done:min(n, done + (1 << 30))]], off + done)
+            if got <= 0:
+                raise H5FormatError("%s: unexpected end of file at offset %d" % (self._path, off + done))
+            done += got
+
+    # -- superblock --------------------------------------------------------------------------------
+    def _superblock(self):
+        size = os.fstat(self._fd).st_size
+        off = 0
+        while True:                                       # the signature sits at 0, 512, 1024, 2048, ... (user block)
+            if off + 8 > size:
+                raise H5FormatError("%s is not an HDF5 file (no signature)" % self._path)
+            if self._pread(off, 8) == SIGNATURE:
+                break
+            off = 512 if off == 0 else off * 2
+        c = _Cur(self._pread(off, min(256, size - off)), 8)
+        ver = c.u(1)
+        self._root_hint = None
+        if ver in (0, 1):
+            c.skip(4)                                     # free-space, root-group, reserved, shared-header versions
+            self._O, self._L = c.u(1), c.u(1)
+            c.skip(1)
+            self._leaf_k, self._int_k = c.u(2), c.u(2)
+            c.skip(4)
+            if ver == 1:
+                c.skip(4)
+            O = self._O
+            self._undef = (1 << (8 * O)) - 1
+            base = c.u(O)
+            c.skip(O)                                     # free-space info
+            self._eof = c.u(O)
+            c.skip(O)                                     # driver info
+            c.skip(O)                                     # root entry: link name offset
+            self._root_addr = c.u(O)
+            cache = c.u(4)
+            c.skip(4)
+            if cache == 1:
+                self._root_hint = (c.u(O), c.u(O))
+        elif ver in (2, 3):
+            self._O, self._L = c.u(1), c.u(1)
+            c.skip(1)
+            O = self._O
+            self._undef = (1 << (8 * O)) - 1
+            base = c.u(O)
+            c.skip(O)                                     # superblock extension
+            self._eof = c.u(O)
+            self._root_addr = c.u(O)
+        else:
+            raise H5FormatError("superblock version %d" % ver)
+        # libhdf5 records base address 0 for files with a user block written through the standard driver and
+        # resolves every address relative to the superblock position
+        self._base = base if base != 0 else off
+        if base != 0 and base != off:
+            raise H5FormatError("base address %d differs from the superblock offset %d" % (base, off))
+
+    # -- object headers ----------------------------------------------------------------------------
+    def _messages(self, addr):
+        """[(type, body bytes)] of the version-1 object header at `addr` (continuation blocks followed)"""
+        O, L = self._O, self._L
+        head = self._pread(self._base + addr, 16)
+        if head[:4] == b"OHDR":
+            raise H5FormatError("version-2 object headers (file written with libver='latest') are not supported")
+        c = _Cur(head)
+        if c.u(1) != 1:
+            raise H5FormatError("object header version %d at %d" % (head[0], addr))
+        c.skip(1)
+        nmsg = c.u(2)
+        c.skip(4)
+        hsize = c.u(4)
+        blocks = [(addr + 16, hsize)]
+        msgs = []
+        while blocks and len(msgs) < nmsg:
+            baddr, blen = blocks.pop(0)
+            c = _Cur(self._pread(self._base + baddr, blen))
+            while c.p + 8 <= blen and len(msgs) < nmsg:
+                mtype, msize = c.u(2), c.u(2)
+                c.skip(4)
+                body = c.raw(msize)
+                if mtype == 0x10:
+                    cc = _Cur(body)
+                    blocks.append((cc.u(O), cc.u(L)))
+                msgs.append((mtype, body))
+        return msgs
+
+    def _object(self, name, addr, root_hint=None):
+        if addr in self._cache:
+            return self._cache[addr]
+        msgs = self._messages(addr)
+        types = [t for t, _ in msgs]
+        if 0x11 in types:
+            c = _Cur(msgs[types.index(0x11)][1])
+            node = Group(self, name, addr, c.u(self._O), c.u(self._O))
+        elif 0x08 in types:
+            node = Dataset(self, name, addr, msgs)
+        elif root_hint is not None:
+            node = Group(self, name, addr, *root_hint)
+        elif 0x02 in types or 0x06 in types:
+            raise H5FormatError("%s: new-style group (link messages / fractal heap); rewrite the file with the "
+                                "default libver" % name)
+        else:
+            raise H5FormatError("%s: object with message types %s" % (name, sorted(set(types))))
+        self._cache[addr] = node
+        return node
+
+    # -- groups ------------------------------------------------------------------------------------
+    def _local_heap(self, addr):
+        c = _Cur(self._pread(self._base + addr, 8 + 2 * self._L + self._O))
+        if c.raw(4) != b"HEAP":
+            raise H5FormatError("local heap signature missing at %d" % addr)
+        c.skip(4)
+        size = c.u(self._L)
+        c.skip(self._L)
+        return self._pread(self._base + c.u(self._O), size)
+
+    def _global_heap_object(self, addr, index):
+        O, L = self._O, self._L
+        head = _Cur(self._pread(self._base + addr, 8 + L))
+        if head.raw(4) != b"GCOL":
+            raise H5FormatError("global heap signature missing at %d" % addr)
+        head.skip(4)
+        size = head.u(L)
+        c = _Cur(self._pread(self._base + addr, size), 8 + L)
+        while c.p + 8 + L <= size:
+            idx = c.u(2)
+            c.skip(6)
+            n = c.u(L)
+            if idx == 0:
+                break
+            if idx == index:
+                return c.raw(n)
+            c.skip((n + 7) // 8 * 8)
+        raise H5FormatError("global heap object %d not found at %d" % (index, addr))
+
+    def _btree_node(self, addr):
+        O = self._O
+        head = self._pread(self._base + addr, 8 + 2 * O)
+        if head[:4] != b"TREE":
+            raise H5FormatError("B-tree signature missing at %d" % addr)
+        return head[4], head[5], int.from_bytes(head[6:8], "little"), addr + 8 + 2 * O
+
+    def _group_leaves(self, addr):
+        """(heap offset of the name, object header address) of every entry below the group B-tree node at `addr`"""
+        O, L = self._O, self._L
+        ntype, level, used, body = self._btree_node(addr)
+        if ntype != 0:
+            raise H5FormatError("group B-tree expected at %d" % addr)
+        c = _Cur(self._pread(self._base + body, used * (L + O) + L))
+        children = []
+        for _ in range(used):
+            c.skip(L)
+            children.append(c.u(O))
+        for ch in children:
+            if level > 0:
+                for e in self._group_leaves(ch):
+                    yield e
+            else:
+                esz = 2 * O + 24
+                s = _Cur(self._pread(self._base + ch, 8))
+                if s.raw(4) != b"SNOD":
+                    raise H5FormatError("symbol-table node signature missing at %d" % ch)
+                s.skip(2)
+                nsym = s.u(2)
+                e = _Cur(self._pread(self._base + ch + 8, nsym * esz))
+                for n in range(nsym):
+                    e.p = n * esz
+                    yield e.u(O), e.u(O)
+
+    def _chunk_leaves(self, addr, rank):
+        """(offsets, stored bytes, filter mask, address) of every chunk below the chunk B-tree node at `addr`"""
+        O = self._O
+        ntype, level, used, body = self._btree_node(addr)
+        if ntype != 1:
+            raise H5FormatError("chunk B-tree expected at %d" % addr)
+        ksz = 8 + 8 * (rank + 1)
+        c = _Cur(self._pread(self._base + body, used * (ksz + O) + ksz))
+        for _ in range(used):
+            nbytes, mask = c.u(4), c.u(4)
+            offs = tuple(c.u(8) for _ in range(rank))
+            c.skip(8)
+            child = c.u(O)
+            if level > 0:
+                for e in self._chunk_leaves(child, rank):
+                    yield e
+            else:
+                yield offs, nbytes, mask, child
+
+
+# ---------------------------------------------------------------------------------------------------------
+# writer
+# ---------------------------------------------------------------------------------------------------------
+class Writer(object):
+    """Create an HDF5 file of the flavour described in the module header.
+
+        with Writer("gdf_ints_lo.h5") as w:
+            w["j3c-kptij"] = kptij
+            w["j3c/0/0"] = block            # groups are created on the way
+
+    Array payloads are written immediately (so a 758 GB tensor streams block by block); the group structure is
+    written when the file is closed.  Names may be assigned once."""
+    O = L = 8
+    LEAF_K = 4               # libhdf5's defaults: a symbol-table node holds up to 2 * LEAF_K entries,
+    INT_K = 16               # a B-tree node up to 2 * INT_K children
+    CHUNK_K = 32             # chunk B-tree nodes up to 2 * CHUNK_K chunks (superblock 0 implies 32; one node is written)
+
+    def __init__(self, path):
+        self._path = path
+        self._f = open(path, "wb")
+        self._tree = {}                    # name -> dict (group) | int (object header address)
+        self._sb_size = 8 + 8 + 8 + 4 * 8 + 40      # signature, versions/sizes, K + flags, 4 addresses, root entry
+        self._f.write(bytes(self._sb_size))
+        self._pos = self._sb_size
+
+    # -- raw allocation ----------------------------------------------------------------------------
+    def _alloc(self, data, align=8):
+        pad = (-self._pos) % align
+        if pad:
+            self._f.write(bytes(pad))
+            self._pos += pad
+        addr = self._pos
+        self._f.write(data)
+        self._pos += len(data) if not isinstance(data, memoryview) else data.nbytes
+        return addr
+
+    @staticmethod
+    def _message(mtype, body, flags=0):
+        body = body + bytes((-len(body)) % 8)
+        return struct.pack("<HHB3x", mtype, len(body), flags) + body
+
+    def _object_header(self, messages):
+        blob = b"".join(messages)
+        return self._alloc(struct.pack("<BxHII4x", 1, len(messages), 1, len(blob)) + blob)
+
+    # -- datasets ----------------------------------------------------------------------------------
+    def _write_chunked(self, a, chunks, compression, shuffle):
+        """chunk payloads + one level-0 chunk B-tree; returns (B-tree address, filter pipeline message or None)"""
+        rank, esz = a.ndim, a.dtype.itemsize
+        grid = [range(0, s, c) for s, c in zip(a.shape, chunks)]
+        leaves = []
+        for offs in np.ndindex(*[len(g) for g in grid]):
+            o = tuple(g[i] for g, i in zip(grid, offs))
+            blk = np.zeros(chunks, a.dtype)
+            src = a[tuple(slice(x, x + c) for x, c in zip(o, chunks))]
+            blk[tuple(slice(0, n) for n in src.shape)] = src
+            raw = blk.tobytes()
+            if shuffle:
+                raw = np.frombuffer(raw, np.uint8).reshape(-1, esz).T.tobytes()
+            if compression:
+                raw = zlib.compress(raw, 4)
+            leaves.append((o, len(raw), self._alloc(raw)))
+        if len(leaves) > 2 * self.CHUNK_K:
+            raise H5FormatError("more than %d chunks per dataset" % (2 * self.CHUNK_K))
+        node = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(leaves), UNDEF, UNDEF)
+        for o, n, addr in leaves:
+            node += struct.pack("<II", n, 0) + b"".join(struct.pack("<Q", x) for x in o) + struct.pack("<Q", 0)
+            node += struct.pack("<Q", addr)
+        node += struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", s) for s in a.shape) + struct.pack("<Q", 0)
+        ksz = 8 + 8 * (rank + 1)
+        node += bytes(24 + 2 * self.CHUNK_K * (ksz + 8) + ksz - len(node))
+        filt = []
+        if shuffle:
+            filt.append(struct.pack("<HHHH", 2, 0, 1, 1) + struct.pack("<II", esz, 0))
+        if compression:
+            filt.append(struct.pack("<HHHH", 1, 0, 1, 1) + struct.pack("<II", 4, 0))
+        pipeline = struct.pack("<BB6x", 1, len(filt)) + b"".join(filt) if filt else None
+        return self._alloc(node), pipeline
+
+    def _create_vlen_str(self, node, key, text):
+        """scalar variable-length UTF-8 string (what h5py writes for `f[name] = "text"`): the payload lives in a
+        global heap collection, the dataset holds (length, collection address, object index 1)"""
+        raw = text.encode("utf-8")
+        body = struct.pack("<HH4xQ", 1, 1, len(raw)) + raw + bytes((-len(raw)) % 8)
+        size = max(4096, 16 + len(body) + 16)
+        free = size - 16 - len(body)
+        coll = b"GCOL" + struct.pack("<B3xQ", 1, size) + body + struct.pack("<HH4xQ", 0, 0, free)
+        coll_addr = self._alloc(coll + bytes(size - len(coll)))
+        elem = struct.pack("<IQI", len(raw), coll_addr, 1)
+        dtype = struct.pack("<BBBBI", 0x19, 0x01, 0x01, 0, 16) + struct.pack("<BBBBI", 0x13, 0, 0, 0, 1)
+        space = struct.pack("<BBB5x", 1, 0, 0)
+        layout = struct.pack("<BBQQ", 3, 1, self._alloc(elem), len(elem))
+        node[key] = self._object_header([self._message(0x01, space), self._message(0x03, dtype, flags=1),
+                                         self._message(0x05, struct.pack("<BBBB", 2, 2, 0, 0)),
+                                         self._message(0x08, layout)])
+
+    def create_dataset(self, name, data, chunks=None, compression=None, shuffle=False):
+        text = data if isinstance(data, str) else None
+        a = np.asarray(data) if text is None else np.empty(())
+        if a.dtype.byteorder == ">":
+            a = a.astype(a.dtype.newbyteorder("<"))
+        a = np.require(a, requirements="C")                # (ascontiguousarray would turn scalars into 1-d arrays)
+        parts = [p for p in name.split("/") if p]
+        node = self._tree
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+            if not isinstance(node, dict):
+                raise ValueError("%s: %r is a dataset" % (name, p))
+        if parts[-1] in node:
+            raise ValueError("%s exists already" % name)
+        if text is not None:
+            return self._create_vlen_str(node, parts[-1], text)
+        space = struct.pack("<BBB5x", 1, a.ndim, 0) + b"".join(struct.pack("<Q", s) for s in a.shape)
+        fill = struct.pack("<BBBB", 2, 2, 0, 0)            # version 2, allocate late, write at allocation, undefined
+        msgs = [self._message(0x01, space), self._message(0x03, _encode_dtype(a.dtype), flags=1),
+                self._message(0x05, fill)]
+        if chunks is not None or compression or shuffle:
+            chunks = tuple(chunks) if chunks is not None else tuple(max(1, s) for s in a.shape)
+            if a.ndim == 0 or len(chunks) != a.ndim:
+                raise ValueError("%s: chunk shape %s does not fit data of shape %s" % (name, chunks, a.shape))
+            bt, pipeline = self._write_chunked(a, chunks, compression, shuffle)
+            layout = struct.pack("<BBBQ", 3, 2, a.ndim + 1, bt)
+            layout += b"".join(struct.pack("<I", c) for c in chunks) + struct.pack("<I", a.dtype.itemsize)
+            if pipeline:
+                msgs.append(self._message(0x0B, pipeline))
+        else:
+            if a.nbytes:
+                daddr = self._alloc(_byte_view_ro(a), align=4096 if a.nbytes >= (1 << 20) else 8)
+            else:
+                daddr = UNDEF
+            layout = struct.pack("<BBQQ", 3, 1, daddr, a.nbytes)
+        msgs.append(self._message(0x08, layout))
+        node[parts[-1]] = self._object_header(msgs)
+
+    def __setitem__(self, name, data):
+        self.create_dataset(name, data)
+
+    # -- groups ------------------------------------------------------------------------------------
+    def _write_group(self, members):
+        """members: name -> dict | address.  Returns (object header address, B-tree address, heap address)."""
+        entries = []
+        for name, v in members.items():
+            if isinstance(v, dict):
+                oh, bt, hp = self._write_group(v)
+                entries.append((name, oh, 1, bt, hp))
+            else:
+                entries.append((name, v, 0, 0, 0))
+        entries.sort(key=lambda e: e[0].encode())          # B-tree order: strcmp of the link names
+        # local heap: offset 0 holds the empty string (key 0 of the B-tree), names are 8-byte aligned
+        heap = bytearray(8)
+        offs = []
+        for e in entries:
+            offs.append(len(heap))
+            nm = e[0].encode() + b"\0"
+            heap += nm + bytes((-len(nm)) % 8)
+        free_off = len(heap)
+        heap += struct.pack("<QQ", 1, 16)                   # one free block: next = 1 (last), size 16
+        heap_data_addr = self._alloc(bytes(heap))
+        heap_addr = self._alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_off, heap_data_addr))
+        # symbol-table nodes (fixed size: 2 * LEAF_K entries), then B-tree levels bottom-up until one node is left
+        per = 2 * self.LEAF_K
+        children = []                                       # (address, largest key below) of the current level
+        for s in range(0, max(1, len(entries)), per):
+            chunk = entries[s:s + per]
+            blob = b"SNOD" + struct.pack("<BxH", 1, len(chunk))
+            for n, (name, oh, cache, bt, hp) in enumerate(chunk):
+                blob += struct.pack("<QQI4x", offs[s + n], oh, cache)
+                blob += (struct.pack("<QQ", bt, hp) if cache else bytes(16))
+            blob += bytes((per - len(chunk)) * 40)
+            children.append((self._alloc(blob), offs[s + len(chunk) - 1] if chunk else 0))
+        fan = 2 * self.INT_K
+        node_size = 24 + fan * 8 + (fan + 1) * 8
+        level = 0
+        while True:
+            groups = [children[s:s + fan] for s in range(0, len(children), fan)]
+            base = self._alloc(b"")                         # aligned position of the first node of this level
+            parents = []
+            low = 0                                         # key 0 of the leftmost node: the empty string at offset 0
+            for n, g in enumerate(groups):
+                left = base + (n - 1) * node_size if n > 0 else UNDEF
+                right = base + (n + 1) * node_size if n + 1 < len(groups) else UNDEF
+                node = b"TREE" + struct.pack("<BBHQQ", 0, level, len(g), left, right) + struct.pack("<Q", low)
+                for addr, key in g:
+                    node += struct.pack("<QQ", addr, key)
+                node += bytes(node_size - len(node))
+                got = self._alloc(node)
+                assert got == base + n * node_size
+                low = g[-1][1]
+                parents.append((got, low))
+            if len(parents) == 1:
+                bt_addr = parents[0][0]
+                break
+            children, level = parents, level + 1
+        oh_addr = self._object_header([self._message(0x11, struct.pack("<QQ", bt_addr, heap_addr))])
+        return oh_addr, bt_addr, heap_addr
+
+    def close(self):
+        if self._f is None:
+            return
+        oh, bt, hp = self._write_group(self._tree)
+        eof = self._pos
+        sb = SIGNATURE + struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, self.O, self.L, 0)
+        sb += struct.pack("<HHI", self.LEAF_K, self.INT_K, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+        sb += struct.pack("<QQI4xQQ", 0, oh, 1, bt, hp)
+        assert len(sb) == self._sb_size
+        self._f.seek(0)
+        self._f.write(sb)
+        self._f.close()
+        self._f = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, etype, *exc):
+        if etype is None:
+            self.close()
+        else:
+            self._f.close()
+            self._f = None

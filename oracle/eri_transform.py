@@ -318,3 +318,41 @@ def transform_gdf_to_lo(mydf, C_ao_lo, t_reversal_symm=True, blksize=240):
         if mask[pos] != -1:
             out[int(mask[pos])] = stored.conj()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GDF tensor on disk (eri_transform.py:159-227)
+# ---------------------------------------------------------------------------------------------------------
+class FileGDF(object):
+    """GDF provider over an open h5py-like cderi file, following the reference's own access pattern: `get_naoaux`
+    (159-193: rows of `j3c/<k>` -- or of its segment '0' -- for every stored pair, naux = the maximum) and
+    `sr_loop` (195-227: `_load3c`, Hermitian unpacking of k_i == k_j blocks, cast to complex128).  Auxiliary rows
+    a pair does not have stay zero, as in the reference's accumulation buffers (l.365-378)."""
+
+    def __init__(self, feri, cell, kpts):
+        self.feri, self.cell = feri, cell
+        self.kpts = np.asarray(kpts, dtype=float)
+        self.kpts_scaled = cell.get_scaled_kpts(self.kpts)
+        sk = self.kpts_scaled.round(8)
+        self.kmesh = [len(np.unique(sk[:, d])) for d in range(3)]
+        self.nao = int(cell.nao_nr())
+        self.blockdim = 240
+        if "j3c-kptij" in feri:                                                   # l.164-168
+            keys = ["j3c/%d" % k for k in range(feri["j3c-kptij"].shape[0])]
+        else:
+            keys = ["j3c/%s" % k for k in feri["j3c"].keys()]
+        rows = []
+        for key in keys:                                                          # l.170-176
+            entry = feri[key]
+            rows.append(entry["0"].shape[0] if hasattr(entry, "keys") else entry.shape[0])
+        self.naux = int(max(rows))
+
+    def load(self, ki, kj):
+        nao = self.nao
+        j3c = lib.load3c(self.feri, "j3c", self.kpts[[ki, kj]], "j3c-kptij", nao)
+        Lpq = np.asarray(j3c[0:j3c.shape[0]])
+        if ki == kj and Lpq.shape[-1] != nao * nao:                               # l.201, 216-217
+            Lpq = lib.unpack_tril(Lpq).reshape(-1, nao * nao)
+        out = np.zeros((self.naux, nao, nao), dtype=np.complex128)
+        out[:Lpq.shape[0]] = np.asarray(Lpq, dtype=np.complex128).reshape(-1, nao, nao)
+        return out

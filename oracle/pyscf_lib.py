@@ -171,3 +171,58 @@ def dot_eri_dm(eri, dm, hermi=0, with_j=True, with_k=True):
         vj = None if vj is None else vj[0]
         vk = None if vk is None else vk[0]
     return vj, vk
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cderi file access: pyscf.pbc.df.df._load3c (called at eri_transform.py:221) and pyscf.df.addons.load (171)
+# ---------------------------------------------------------------------------------------------------------
+def kpts_member(kpt, kpts):
+    """pyscf.pbc.lib.kpts_helper.member: positions of `kpt` in `kpts` (rows compared within KPT_DIFF_TOL)"""
+    kpts = np.asarray(kpts).reshape(len(kpts), -1)
+    return np.where(np.abs(kpts - np.asarray(kpt).reshape(1, -1)).max(axis=1) < KPT_DIFF_TOL)[0]
+
+
+class KPairLoader(object):
+    """What `_load3c.__enter__` hands out for one k-point pair: `.shape` and `[rows]` over the stored entry.  Column
+    segments '0', '1', ... of a group are stacked horizontally; when only the swapped pair is stored, full
+    (nao*nao column) data come back conjugate-transposed in the two AO indices and Hermitian-packed data
+    conjugated."""
+
+    def __init__(self, entry, swapped, nao):
+        self.segs = [entry[str(n)] for n in range(len(entry))] if hasattr(entry, "keys") else [entry]
+        self.swapped, self.nao = swapped, nao
+
+    @property
+    def shape(self):
+        return (self.segs[0].shape[0], sum(s.shape[1] for s in self.segs))
+
+    def __getitem__(self, rows):
+        v = np.hstack([np.asarray(s[rows]) for s in self.segs])
+        if not self.swapped:
+            return v
+        nao = self.nao
+        if v.shape[-1] == nao * nao:
+            return np.ascontiguousarray(v.reshape(-1, nao, nao).transpose(0, 2, 1).conj()).reshape(-1, nao * nao)
+        return v.conj()
+
+
+def load3c(feri, label, kpti_kptj, kptij_label, nao):
+    """`_load3c(cderi, label, kpti_kptj, kptij_label)` on an open h5py-like file: the stored pair, else the swapped
+    one.  Files without the pair list (PySCF >= 2.1: `kpts` + `j3c/<ki * nkpts + kj>`) are addressed by index."""
+    kpti_kptj = np.asarray(kpti_kptj)
+    if kptij_label in feri:
+        kptij = np.asarray(feri[kptij_label][...])
+        hit = kpts_member(kpti_kptj, kptij)
+        if len(hit):
+            return KPairLoader(feri["%s/%d" % (label, hit[0])], False, nao)
+        hit = kpts_member(kpti_kptj[[1, 0]], kptij)
+        if not len(hit):
+            raise KeyError("%s for the k-point pair %s is not in the file" % (label, kpti_kptj))
+        return KPairLoader(feri["%s/%d" % (label, hit[0])], True, nao)
+    kpts = np.asarray(feri["kpts"][...])
+    ki, kj = int(kpts_member(kpti_kptj[0], kpts)[0]), int(kpts_member(kpti_kptj[1], kpts)[0])
+    for key, swapped in (("%s/%d" % (label, ki * len(kpts) + kj), False),
+                         ("%s/%d" % (label, kj * len(kpts) + ki), True)):
+        if key in feri:
+            return KPairLoader(feri[key], swapped, nao)
+    raise KeyError("%s for the k-point pair (%d, %d) is not in the file" % (label, ki, kj))

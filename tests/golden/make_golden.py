@@ -232,7 +232,57 @@ def gen_gdf_lo():
         save(name, **out)
 
 
+FILE_CASES = {
+    # name: kmesh, nao, naux, neo, spin, cderi layout options (tests/helpers.py: write_case_file)
+    "eri_file_122": dict(kmesh=[1, 2, 2], nao=4, naux=9, neo=5, spin=1, nsegments=2, pack_diagonal=True,
+                         drop={(2, 1): 8, (3, 3): 7}),
+    "eri_file_113": dict(kmesh=[1, 1, 3], nao=5, naux=8, neo=6, spin=2, nsegments=1, pack_diagonal=True, drop={}),
+}
+
+
+def gen_eri_file():
+    """the reference's get_naoaux / sr_loop / get_emb_eri / transform_gdf_to_lo over a REAL cderi file (PySCF's v1
+    layout: `j3c-kptij`, `j3c/<pair>/<segment>`, Hermitian-packed diagonal pairs, real Gamma block, fewer auxiliary
+    rows for some pairs) written by libdmet_preview_b200.gdf_file.write_gdf_file and read through h5lite, which
+    stands in for h5py"""
+    import tempfile
+    from libdmet_preview_b200 import h5lite
+    from libdmet_preview_b200.gdf_file import write_gdf_file
+    for name, c in FILE_CASES.items():
+        gdf, C, basis = problem(c["kmesh"], c["nao"], c["naux"], c["neo"], spin=c["spin"])
+        gdf.cell = GoldenCell(c["nao"])
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, name + "_cderi.h5")
+            write_gdf_file(path, gdf, version="v1", nsegments=c["nsegments"], pack_diagonal=c["pack_diagonal"],
+                           naux_of=c["drop"])
+            ref_stubs.FILE_NAO[path] = c["nao"]
+            mydf = stub_df.GDF(gdf.cell, gdf.kpts)
+            mydf._cderi = path
+            out = dict(kmesh=np.array(c["kmesh"]), nao=c["nao"], naux=c["naux"], neo=c["neo"], spin=c["spin"],
+                       gdf_seed=gdf.seed, gdf_scale=gdf.scale, C_ao_lo=C, basis=basis)
+            ref_log.verbose = "FATAL"            # "aux basis drop may happened" (eri_transform.py:191-192)
+            out["naoaux"] = ref_eri.get_naoaux(mydf)
+            ref_log.verbose = "RESULT"
+            out["s4_trs"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4)
+            out["s4_plain"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=4,
+                                                  t_reversal_symm=False)
+            out["s1_trs"] = ref_eri.get_emb_eri(gdf.cell, mydf, C_ao_lo=C, basis=basis, symmetry=1)
+            # LO-basis tensor written by the reference into a real file, read back dataset by dataset
+            lo_path = os.path.join(tmp, name + "_lo.h5")
+            Clo = synthetic.make_C_ao_lo(c["kmesh"], c["nao"], c["nao"] - 1, seed=41)
+            mydf_lo = ref_eri.transform_gdf_to_lo(mydf, Clo, fname=lo_path)
+            assert mydf_lo._cderi == lo_path
+            out["C_lo"] = Clo
+            with h5lite.File(lo_path) as f:
+                out["lo_kptij"] = f["j3c-kptij"][...]
+                for k in range(len(out["lo_kptij"])):
+                    assert f["j3c/%d" % k].keys() == ["0"]
+                    out["lo_%d" % k] = f["j3c/%d/0" % k][...]
+        save(name, **out)
+
+
 if __name__ == "__main__":
+    gen_eri_file()
     gen_gdf_lo()
     gen_gso_embham()
     gen_gso()

@@ -26,6 +26,7 @@ _STUB_ROOTS = ("pyscf", "h5py", "matplotlib", "mpi4py", "mpi4pyscf", "block2", "
 
 GDF_REGISTRY = {}     # cderi key -> provider
 H5_WRITTEN = {}       # file name -> {dataset name: array} written through the h5py stub
+FILE_NAO = {}         # path of a real cderi file -> nao (PySCF's loader knows it from the cell)
 
 
 class _PlaceholderMeta(type):
@@ -152,6 +153,11 @@ def _populate(m):
     elif name == "pyscf.pbc.df.df":
         @contextlib.contextmanager
         def _load3c(cderi, label, kpti_kptj, kptij_label=None):
+            if cderi not in GDF_REGISTRY:        # a real file on disk: PySCF's lookup restated over h5lite
+                from libdmet_preview_b200 import h5lite
+                with h5lite.File(cderi) as feri:
+                    yield olib.load3c(feri, label, kpti_kptj, kptij_label, FILE_NAO[cderi])
+                return
             prov = GDF_REGISTRY[cderi]
             ks = prov.cell.get_scaled_kpts(np.asarray(kpti_kptj))
             from oracle.fourier import kpt_member
@@ -166,16 +172,41 @@ def _populate(m):
     elif name == "pyscf.df.addons":
         @contextlib.contextmanager
         def load(cderi, dataname):
+            if cderi not in GDF_REGISTRY:
+                from libdmet_preview_b200 import h5lite
+                with h5lite.File(cderi) as feri:
+                    yield feri[dataname]
+                return
             prov = GDF_REGISTRY[cderi]
             yield np.empty((prov.naux, 1))
         m.load = load
     elif name == "h5py":
-        class Group(object):
-            pass
+        from libdmet_preview_b200 import h5lite
+        Group = h5lite.Group       # the reference asks isinstance(entry, h5py.Group) (eri_transform.py:172)
+
+        class _RealOut(object):
+            """mode "w" on a name ending in .h5: a real file through h5lite.Writer"""
+
+            def __init__(self, fname):
+                self.w = h5lite.Writer(fname)
+
+            def __setitem__(self, key, value):
+                self.w[key] = np.asarray(value)
+
+            def close(self):
+                self.w.close()
 
         class File(object):
             """mode "r": a view of a registered in-memory GDF (only `j3c-kptij` is read through h5py by the reference,
-            the blocks go through `_load3c`); mode "w": datasets land in H5_WRITTEN[fname]"""
+            the blocks go through `_load3c`), or -- for a name that is not registered -- the real file, opened with
+            h5lite; mode "w": datasets land in H5_WRITTEN[fname] (real file when the name ends in .h5)"""
+
+            def __new__(cls, fname, mode="r"):
+                if mode == "w" and fname.endswith(".h5"):
+                    return _RealOut(fname)
+                if mode != "w" and fname not in GDF_REGISTRY:
+                    return h5lite.File(fname)
+                return object.__new__(cls)
 
             def __init__(self, fname, mode="r"):
                 self.mode = mode

@@ -124,3 +124,18 @@ def gso_basis(kmesh, nao, nemb, seed=0):
     nk = int(np.prod(kmesh))
     q, _ = np.linalg.qr(np.random.default_rng(700 + seed).standard_normal((nk * 2 * nao, nemb)))
     return q.reshape(nk, 2 * nao, nemb)
+
+
+# cderi-file cases of tests/golden/make_golden.py (FILE_CASES): layout options used when the file was written
+FILE_CASES = {
+    "eri_file_122": dict(nsegments=2, pack_diagonal=True, drop={(2, 1): 8, (3, 3): 7}),
+    "eri_file_113": dict(nsegments=1, pack_diagonal=True, drop={}),
+}
+
+
+def write_case_file(path, gdf, name, version="v1"):
+    """the cderi file of a golden case, rewritten from the seeded provider (the fixtures store seeds, not tensors)"""
+    from libdmet_preview_b200.gdf_file import write_gdf_file
+    c = FILE_CASES[name]
+    return write_gdf_file(str(path), gdf, version=version, nsegments=c["nsegments"], pack_diagonal=c["pack_diagonal"],
+                          naux_of=c["drop"])

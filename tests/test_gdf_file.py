@@ -1,0 +1,121 @@
+"""CPU: GDF tensors on disk -- `gdf_file.GDFFile` serves PySCF-layout cderi files the way the reference reads them
+(`get_naoaux` / `sr_loop` -> `_load3c`, eri_transform.py:159-227), checked against the oracle's restatement of that
+access pattern, against the in-memory tensor the file was written from, and against golden results the reference's
+own `get_emb_eri` / `transform_gdf_to_lo` produced from such a file (tests/golden/make_golden.py: gen_eri_file)."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from libdmet_preview_b200 import synthetic, h5lite
+from libdmet_preview_b200 import eri_transform as et
+from libdmet_preview_b200.gdf_file import GDFFile, write_gdf_file
+from oracle import eri_transform as oe
+from helpers import write_case_file
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gdf_of(d):
+    return synthetic.SyntheticGDF([int(x) for x in d["kmesh"]], int(d["nao"]), int(d["naux"]), seed=int(d["gdf_seed"]),
+                                  scale=float(d["gdf_scale"]))
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("nsegments,pack", [(1, True), (3, True), (2, False)])
+def test_blocks_equal_the_tensor_written(tmp_path, version, nsegments, pack):
+    gdf = synthetic.SyntheticGDF([2, 1, 3], 5, 11, seed=3)
+    drop = {(1, 0): 9, (2, 2): 10}
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, version=version, nsegments=nsegments, pack_diagonal=pack,
+                          naux_of=drop)
+    with GDFFile(path, cell=gdf.cell) as f, h5lite.File(path) as raw:
+        assert f.version == version and f.kmesh == [2, 1, 3] and f.nao == 5 and f.naux == 11 and f.aux_drop
+        assert np.allclose(f.kpts_scaled, gdf.kpts_scaled) and np.allclose(f.kpts, gdf.kpts)
+        assert f.kptij_idx == [(i, j) for i in range(6) for j in range(i + 1)]
+        ora = oe.FileGDF(raw, gdf.cell, gdf.kpts)                 # the reference's access pattern, restated
+        assert ora.naux == 11
+        for i in range(6):
+            for j in range(6):
+                want = gdf.load(i, j).copy()
+                rows = drop.get((i, j), drop.get((j, i), 11))
+                want[rows:] = 0.0
+                got = f.load(i, j)
+                assert got.dtype == np.complex128 and got.flags.c_contiguous
+                assert np.array_equal(got, want), (i, j)
+                assert np.array_equal(ora.load(i, j), want), (i, j)
+        # storage: Gamma block real, diagonal packed when asked, column segments
+        g00 = raw["j3c/0"]
+        assert len(g00) == nsegments and g00["0"].dtype == np.float64
+        ncol = sum(g00[str(s)].shape[1] for s in range(nsegments))
+        assert ncol == (15 if pack else 25)
+        # a destination buffer (e.g. pinned memory) is filled in place
+        buf = np.full((11, 5, 5), 7.0 + 7.0j)
+        assert f.load(4, 1, out=buf) is buf and np.array_equal(buf, gdf.load(4, 1))
+        assert f.load(0, 1, out=buf) is buf and np.array_equal(buf[:9], gdf.load(0, 1)[:9]) and not buf[9:].any()
+
+
+def test_caller_kpoint_order_and_errors(tmp_path):
+    gdf = synthetic.SyntheticGDF([1, 2, 2], 3, 4, seed=8)
+    perm = [2, 0, 3, 1]
+    for version in ("v1", "v2"):
+        path = write_gdf_file(str(tmp_path / (version + ".h5")), gdf, version=version)
+        f = GDFFile(path, cell=gdf.cell, kpts=gdf.kpts[perm])
+        for a in range(4):
+            for b in range(4):
+                assert np.array_equal(f.load(a, b), gdf.load(perm[a], perm[b]))
+        # lattice vectors instead of a cell: nao comes from the column count
+        f2 = GDFFile(path, lattice_vectors=gdf.cell.lattice_vectors())
+        assert f2.nao == 3 and f2.kmesh == [1, 2, 2]
+        with pytest.raises(ValueError):
+            GDFFile(path)
+        with pytest.raises(ValueError):
+            GDFFile(path, cell=gdf.cell, kpts=gdf.kpts + 0.01)
+    # only some pairs stored: the others are served transposed, missing ones raise
+    path = write_gdf_file(str(tmp_path / "few.h5"), gdf, pairs=[(0, 0), (1, 1), (2, 2), (3, 3), (0, 1), (3, 2)])
+    f = GDFFile(path, cell=gdf.cell)
+    assert np.array_equal(f.load(1, 0), gdf.load(1, 0)) and np.array_equal(f.load(2, 3), gdf.load(2, 3))
+    with pytest.raises(KeyError):
+        f.load(0, 2)
+    # not a cderi file
+    with h5lite.Writer(str(tmp_path / "other.h5")) as w:
+        w["x"] = np.zeros(3)
+    with pytest.raises(KeyError):
+        GDFFile(str(tmp_path / "other.h5"), cell=gdf.cell)
+    cell2d = synthetic.SyntheticCell(3, dimension=2)
+    with pytest.raises(NotImplementedError):                      # eri_transform.py:226-227
+        GDFFile(path, cell=cell2d)
+
+
+def test_as_provider_accepts_a_gdf_like_object_with_a_cderi_path(tmp_path):
+    gdf = synthetic.SyntheticGDF([1, 1, 3], 4, 6, seed=5)
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf)
+    mydf = types.SimpleNamespace(_cderi=path, kpts=gdf.kpts, cell=gdf.cell, blockdim=120)
+    prov = et.as_provider(gdf.cell, mydf)
+    assert isinstance(prov, GDFFile) and prov.blockdim == 120 and prov.naux == 6
+    assert np.array_equal(prov.load(2, 1), gdf.load(2, 1))
+    assert et.as_provider(gdf.cell, gdf) is gdf
+    with pytest.raises(ValueError):                               # eri_transform.py:89
+        et.as_provider(gdf.cell, object())
+    with pytest.raises(ValueError):
+        et.as_provider(gdf.cell, types.SimpleNamespace(_cderi=str(tmp_path / "missing.h5"), kpts=gdf.kpts))
+
+
+@pytest.mark.parametrize("name", ["eri_file_122", "eri_file_113"])
+def test_oracle_from_file_vs_reference_python(tmp_path, name):
+    """golden: the reference's own get_naoaux / get_emb_eri / transform_gdf_to_lo run over the same file"""
+    d = np.load(os.path.join(G, name + ".npz"))
+    gdf = _gdf_of(d)
+    path = write_case_file(tmp_path / "cderi.h5", gdf, name)
+    C, basis = d["C_ao_lo"], d["basis"]
+    with GDFFile(path, cell=gdf.cell, kpts=gdf.kpts) as f, h5lite.File(path) as raw:
+        assert f.naux == int(d["naoaux"]) == int(d["naux"])
+        for prov in (f, oe.FileGDF(raw, gdf.cell, gdf.kpts)):
+            for key, kw in (("s4_trs", {}), ("s4_plain", dict(t_reversal_symm=False)), ("s1_trs", dict(symmetry=1))):
+                got = oe.get_emb_eri(gdf.cell, prov, C_ao_lo=C, basis=basis, **kw)
+                assert got.shape == d[key].shape and np.abs(got - d[key]).max() < 1e-13, key
+        lo = oe.transform_gdf_to_lo(f, d["C_lo"])
+        assert np.allclose(d["lo_kptij"], [(gdf.kpts[i], gdf.kpts[j]) for i, j in f.kptij_idx])
+        for k in range(len(d["lo_kptij"])):
+            want = d["lo_%d" % k]
+            assert lo[k].shape == want.shape and lo[k].dtype == want.dtype and np.abs(lo[k] - want).max() < 1e-13
