@@ -2,8 +2,8 @@
  *
  * The reference (gkclab/libdmet_preview) has no FFI layer: the seam is a set of module-level Python functions
  * whose arithmetic runs in PySCF's C libraries.  Each entry point below names the reference routine (file:line
- * under /root/reference) whose work it takes over; `libdmet_preview_b200/*.py` binds them with ctypes and
- * re-exposes the reference's Python signatures.
+ * under /root/reference) whose work it takes over; the Python modules of `libdmet_preview_b200` bind them with
+ * ctypes and re-expose the reference's Python signatures.
  *
  * Conventions
  *   - every function returns 0 on success, a negative code on failure; ldm_last_error() gives the message

@@ -332,21 +332,61 @@ def _host_block(provider, ki, kj, l0, l1, naux_full):
     return L[l0:l1]                      # leading-index slice of a C-contiguous block: still contiguous
 
 
+def _staging_buffers(provider, count):
+    """`count` host buffers of one GDF block each, page-locked when a CUDA device is present (so that the H2D copy in
+    `ldm_eri_block_host` is a single DMA transfer instead of a staged pageable copy); kept on the provider and
+    reused by later calls"""
+    shape = (int(provider.naux), int(provider.nao), int(provider.nao))
+    have = getattr(provider, "_staging", None)
+    if have is None or have[0] != shape or len(have[1]) < count:
+        pin = torch.cuda.is_available()
+        keep = []
+        bufs = []
+        for _ in range(count):
+            t = torch.empty(shape, dtype=torch.complex128, pin_memory=pin)
+            keep.append(t)
+            bufs.append(t.numpy())
+        have = (shape, bufs, keep)
+        try:
+            provider._staging = have
+        except AttributeError:
+            pass
+    return have[1][:count]
+
+
 class _Prefetcher(object):
     """Loads GDF blocks from the provider on a background thread, `depth` blocks ahead of the consumer -- the role
-    of `lib.map_with_prefetch` in the reference's `sr_loop` (eri_transform.py:223).  h5py / numpy release the GIL
-    while reading, so disk or page-cache latency overlaps the host->device copy and the kernels."""
+    of `lib.map_with_prefetch` in the reference's `sr_loop` (eri_transform.py:223).  File reads and numpy release the
+    GIL, so disk or page-cache latency overlaps the host->device copy and the kernels.  Providers whose `load`
+    accepts a destination (`fills_out`, e.g. `gdf_file.GDFFile`) read straight into a ring of page-locked buffers;
+    the consumer hands each buffer back with `done()` once the block is on the device."""
 
     def __init__(self, provider, requests, depth):
         import queue
         import threading
-        self.q = queue.Queue(maxsize=max(1, depth))
+        depth = max(1, depth)
+        self.q = queue.Queue(maxsize=depth)
         self.err = None
+        self.free = None
+        self._lent = {}
+        if getattr(provider, "fills_out", False):
+            self.free = queue.Queue()
+            for b in _staging_buffers(provider, depth + 2):      # queued + one being filled + one being copied
+                self.free.put(b)
 
         def work():
             try:
                 for (ki, kj, l0, l1) in requests:
-                    self.q.put(_host_block(provider, ki, kj, l0, l1, provider.naux))
+                    if self.free is None:
+                        self.q.put(_host_block(provider, ki, kj, l0, l1, provider.naux))
+                        continue
+                    buf = self.free.get()
+                    if buf is None:                  # closed by the consumer
+                        return
+                    provider.load(ki, kj, out=buf)
+                    view = buf[l0:l1]
+                    self._lent[id(view)] = buf
+                    self.q.put(view)
             except BaseException as e:          # surfaced in the consumer
                 self.err = e
                 self.q.put(None)
@@ -358,6 +398,15 @@ class _Prefetcher(object):
         if blk is None and self.err is not None:
             raise self.err
         return blk
+
+    def done(self, blk):
+        """the block has been consumed (copied to the device): its staging buffer may be refilled"""
+        if self.free is not None:
+            self.free.put(self._lent.pop(id(blk)))
+
+    def close(self):
+        if self.free is not None:
+            self.free.put(None)
 
 
 def run_items(build, provider, schedule, items, source="auto", store_map=None, prefetch=2):
@@ -377,25 +426,31 @@ def run_items(build, provider, schedule, items, source="auto", store_map=None, p
     if source == "host" and prefetch:
         reqs = [(ki, kj, l0, l1) for (u, l0, l1) in items for (ki, kj, sym) in schedule.units[u][2]]
         pre = _Prefetcher(provider, reqs, prefetch)
-    for (u, l0, l1) in items:
-        kL, weight, blocks = schedule.units[u]
-        for (ki, kj, sym) in blocks:
-            if source == "resident":
-                slot = provider.fetch(ki, kj, l0, l1)
-                if slot is not None:
-                    build.block_store(ki, kj, sym, slot)
+    try:
+        for (u, l0, l1) in items:
+            kL, weight, blocks = schedule.units[u]
+            for (ki, kj, sym) in blocks:
+                if source == "resident":
+                    slot = provider.fetch(ki, kj, l0, l1)
+                    if slot is not None:
+                        build.block_store(ki, kj, sym, slot)
+                    else:
+                        build.block_host(ki, kj, sym, _host_block(provider, ki, kj, l0, l1, provider.naux))
+                elif source == "host":
+                    blk = pre.next() if pre is not None else _host_block(provider, ki, kj, l0, l1, provider.naux)
+                    build.block_host(ki, kj, sym, blk)
+                    if pre is not None:
+                        pre.done(blk)
+                elif source == "synth":
+                    build.block_synth(ki, kj, sym, provider.keys(ki, kj), provider.scale, l0)
+                elif source == "store":
+                    build.block_store(ki, kj, sym, store_map[(ki, kj, l0)])
                 else:
-                    build.block_host(ki, kj, sym, _host_block(provider, ki, kj, l0, l1, provider.naux))
-            elif source == "host":
-                blk = pre.next() if pre is not None else _host_block(provider, ki, kj, l0, l1, provider.naux)
-                build.block_host(ki, kj, sym, blk)
-            elif source == "synth":
-                build.block_synth(ki, kj, sym, provider.keys(ki, kj), provider.scale, l0)
-            elif source == "store":
-                build.block_store(ki, kj, sym, store_map[(ki, kj, l0)])
-            else:
-                raise ValueError("unknown block source %s" % source)
-        build.end_kl(weight)
+                    raise ValueError("unknown block source %s" % source)
+            build.end_kl(weight)
+    finally:
+        if pre is not None:
+            pre.close()
     build.finish()
 
 
@@ -486,10 +541,11 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
                          t_reversal_symm=True, incore=True, fout="H2.h5", return_device=False, **kwargs):
     """eri_transform.py:235-399.  Same arguments and return layout:
     (spin*(spin+1)/2,) + s4 (npair, npair) / s1 (n,n,n,n) / s8 (npair_pair,), float64, C-contiguous, spin order
-    aa, ab, bb.  `max_memory`, `feri`, `swap_idx`, `fout` are accepted for compatibility (`max_memory` only
-    chose the auxiliary chunk length in the reference and does not change results)."""
-    if not incore:
-        raise NotImplementedError("outcore (HDF5) accumulation is outside the GPU path; use incore=True")
+    aa, ab, bb.  `max_memory`, `feri`, `swap_idx` are accepted for compatibility (`max_memory` only chose the
+    auxiliary chunk length in the reference and does not change results).  `incore=False` writes the s4 tensor to the
+    HDF5 file `fout` (dataset "ccdd", spin order aa, bb, ab) and returns the file opened for reading."""
+    if not incore and not t_reversal_symm:
+        raise NotImplementedError                                         # l.326-327
     provider = as_provider(cell, mydf)
     if getattr(cell, "dimension", 3) == 2 and getattr(cell, "low_dim_ft_type", None) != 'inf_vacuum':
         raise NotImplementedError                                         # l.226-227
@@ -503,6 +559,17 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
                          source=kwargs.get("source", "auto"), group=kwargs.get("group", DEFAULT_GROUP),
                          kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None), imag=imag)
     _report_imag(imag, kwargs)
+    if not incore:
+        # The reference accumulates the s4 ERI in the dataset "ccdd" of `fout`, spin blocks in the order aa, bb, ab
+        # (l.308, 311-320, 486-521), and returns the open file without eri_restore.  Here the build runs on the device
+        # as always; the finished tensor is written once and the file handed back for reading.
+        from . import h5lite
+        host = get_device().to_host(finalize_eri(eri, nemb, 4, spin))
+        if spin == 2:
+            host = host[[0, 2, 1]]
+        with h5lite.Writer(fout) as w:
+            w["ccdd"] = host
+        return h5lite.File(fout)
     eri = finalize_eri(eri, nemb, symmetry, spin)
     if return_device:
         return eri
@@ -600,8 +667,8 @@ def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_cen
     """eri_transform.py:1104-1250: embedding ERI with partial particle-hole transform (generalised spin orbitals).
     Same stage-1 pipeline with two spin flavours; stage 3 is one Gram product of Lambda_a - Lambda_b
     (= the four signed products of `_Lij_s4_to_eri_gso`, l.1252-1284).  Returns (1,) + s4 / s1 / s8 layout."""
-    if not incore:
-        raise NotImplementedError("outcore (HDF5) accumulation is outside the GPU path; use incore=True")
+    if not incore and not t_reversal_symm:
+        raise NotImplementedError                                         # l.326-327
     provider = as_provider(cell, mydf)
     CT = build_CT_gso(provider, C_ao_lo, basis, basis_k, unit_eri)
     nemb = CT.shape[2]

@@ -57,6 +57,8 @@ class GDFFile(object):
     kpts            absolute k-points in the caller's order (mydf.kpts); default: the file's own order
     """
 
+    fills_out = True         # `load(ki, kj, out=buffer)` writes into a caller buffer (pinned staging ring of the pipeline)
+
     def __init__(self, path, cell=None, kpts=None, lattice_vectors=None, label="j3c"):
         self.path = self._cderi = path
         self.cell = cell

@@ -44,3 +44,23 @@ def test_product_does_not_import_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_header_is_plain_c_and_links_from_c(built_lib, tmp_path):
+    """the boundary is a C ABI: include/ldm_b200.h compiles as C99 (no C++ or torch types in the signatures) and a C
+    client linked against the library can call it (version / error string only -- no GPU here)"""
+    import shutil
+    import subprocess
+    import pytest
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "client.c"
+    src.write_text('#include <stdio.h>\n#include "ldm_b200.h"\n'
+                   'int main(void) { printf("%d %s\\n", ldm_version(), ldm_last_error() ? "ok" : "null"); return 0; }\n')
+    exe = str(tmp_path / "client")
+    libdir = os.path.dirname(built_lib)
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", exe, "-L", libdir, "-l:libldm_b200.so", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode().split()
+    assert int(out[0]) >= 100 and out[1] == "ok"

@@ -119,3 +119,49 @@ def test_oracle_from_file_vs_reference_python(tmp_path, name):
         for k in range(len(d["lo_kptij"])):
             want = d["lo_%d" % k]
             assert lo[k].shape == want.shape and lo[k].dtype == want.dtype and np.abs(lo[k] - want).max() < 1e-13
+
+
+def test_prefetcher_streams_file_blocks_through_a_buffer_ring(tmp_path):
+    """run_items with a file provider: blocks are read on the background thread into a small ring of staging buffers
+    (page-locked on a GPU box) that the consumer hands back after each host->device copy"""
+    from libdmet_preview_b200.schedule import build_schedule, work_items
+    gdf = synthetic.SyntheticGDF([1, 2, 2], 4, 10, seed=6)
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, nsegments=2)
+    f = GDFFile(path, cell=gdf.cell)
+    sch = build_schedule(f.kpts_scaled, True)
+
+    class Recorder(object):
+        def __init__(self):
+            self.blocks, self.ptrs, self.kl = [], set(), 0
+
+        def block_host(self, ki, kj, sym, L):
+            self.blocks.append((ki, kj, np.array(L)))            # "copied to the device"
+            self.ptrs.add(L.__array_interface__["data"][0])
+            L[...] = np.nan                                         # a recycled buffer must be refilled completely
+
+        def end_kl(self, weight):
+            self.kl += 1
+
+        def finish(self):
+            self.done = True
+
+    for nsplit in (1, 2):
+        items = work_items(sch, f.naux, nsplit)
+        for (l0, l1) in sorted({(a, b) for (_, a, b) in items}):
+            sub = [it for it in items if (it[1], it[2]) == (l0, l1)]
+            rec = Recorder()
+            et.run_items(rec, f, sch, sub, source="auto", prefetch=2)
+            want = [(ki, kj) for (u, _, _) in sub for (ki, kj, sym) in sch.units[u][2]]
+            assert [(b[0], b[1]) for b in rec.blocks] == want and rec.kl == len(sub) and rec.done
+            for ki, kj, L in rec.blocks:
+                assert np.array_equal(L, gdf.load(ki, kj)[l0:l1])
+            assert len(rec.ptrs) <= 4                                # prefetch depth 2 -> ring of 4 buffers
+    assert len(f._staging[1]) == 4                                   # kept on the provider for the next call
+
+    # a failing read surfaces in the consumer
+    class Broken(GDFFile):
+        def load(self, ki, kj, out=None):
+            raise IOError("disk gone")
+    b = Broken(path, cell=gdf.cell)
+    with pytest.raises(IOError):
+        et.run_items(Recorder(), b, sch, work_items(sch, b.naux, 1), source="host")

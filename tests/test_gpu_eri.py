@@ -98,7 +98,7 @@ def test_entry_variants(dev):
     with pytest.raises(ValueError):
         et.get_emb_eri(gdf.cell, object(), C_ao_lo=C, basis=basis)                  # unknown DF type
     with pytest.raises(NotImplementedError):
-        et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, incore=False)
+        et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, incore=False, t_reversal_symm=False)   # l.326-327
 
 
 def test_device_tensors_in_and_out(dev):

@@ -66,3 +66,19 @@ def test_file_resident_and_lo_round_trip(dev, tmp_path, version, nsegments, pack
     eye = np.asarray([np.eye(nao, dtype=np.complex128)] * len(gdf.kpts))
     via_lo = et.get_emb_eri(lo.cell, flo, C_ao_lo=eye, basis=basis)
     assert np.abs(via_lo - ref).max() < TOL
+
+
+@pytest.mark.parametrize("spin", [1, 2])
+def test_outcore_eri_file(dev, tmp_path, spin):
+    """incore=False: the s4 ERI lands in dataset "ccdd" of `fout`, spin blocks ordered aa, bb, ab
+    (eri_transform.py:308, 311-320, 486-521), and the open file is returned"""
+    from libdmet_preview_b200 import eri_transform as et
+    gdf, C, basis = problem([1, 2, 2], 5, 11, 6, spin=spin)
+    fout = str(tmp_path / "H2.h5")
+    mem = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis)
+    f = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, incore=False, fout=fout)
+    assert f.keys() == ["ccdd"] and os.path.exists(fout)
+    got = f["ccdd"][...]
+    assert got.dtype == np.float64 and got.shape == mem.shape
+    assert np.array_equal(got, mem if spin == 1 else mem[[0, 2, 1]])
+    f.close()
