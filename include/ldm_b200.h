@@ -145,6 +145,19 @@ int ldm_max_abs(ldm_handle h, void* stream, const double* x_d, int64_t n, double
  * eri_transform.py:1104-1284).  Call right after ldm_eri_begin.                                              */
 int ldm_eri_set_mode(ldm_handle h, int gso);
 int ldm_eri_block_host(ldm_handle h, int ki, int kj, int sym, const void* L_h);
+/* A block as it is STORED in a PySCF cderi file (reference: sr_loop -> PySCF _load3c + lib.unpack_tril + cast,
+ * libdmet/basis_transform/eri_transform.py:195-227): src_h is the (rows, ncols) C-contiguous entry, complex128 or --
+ * LDM_STORED_REAL -- float64; ncols = nao*nao, or nao*(nao+1)/2 for a Hermitian-packed k_i == k_j entry;
+ * LDM_STORED_SWAPPED: the entry is the one of the pair (k_j, k_i) and is conjugate-transposed in its two orbital
+ * indices (plain conjugate when packed); rows < naux of the build leaves the remaining auxiliary rows zero.  The
+ * raw bytes cross PCIe once and are widened / unpacked / transposed on the device (ldm_unpack_stored).        */
+#define LDM_STORED_SWAPPED 1
+#define LDM_STORED_REAL 2
+int ldm_eri_block_stored(ldm_handle h, int ki, int kj, int sym, const void* src_h, int rows, int64_t ncols,
+                         int flags);
+/* device -> device form of the same conversion: src_d (rows, ncols) -> out_d (naux, nao, nao) complex128 */
+int ldm_unpack_stored(ldm_handle h, void* stream, const void* src_d, void* out_d, int naux, int rows, int nao,
+                      int64_t ncols, int flags);
 int ldm_eri_block_store(ldm_handle h, int ki, int kj, int sym, int slot);
 int ldm_eri_block_synth(ldm_handle h, int ki, int kj, int sym, int aux_offset, uint32_t key_ij, uint32_t key_ji,
                         uint32_t key_mij, uint32_t key_mji, double scale);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "ldm_eri_set_imag": (C.c_int, [vp, vp]),
     "ldm_max_abs": (C.c_int, [vp, vp, vp, C.c_int64, c_f64p]),
     "ldm_eri_block_host": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_eri_block_stored": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int64, C.c_int]),
+    "ldm_unpack_stored": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int]),
     "ldm_eri_block_store": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ldm_eri_block_synth": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.c_double]),

@@ -247,6 +247,74 @@ ztranspose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Stored cderi entry -> GDF block (PySCF _load3c + sr_loop semantics on the device; gdf_file.py).
+//   src   (rows, ncols) as it lies in the file: complex128, or float64 when `real`;
+//         ncols = nao*nao (full) or nao*(nao+1)/2 (`packed`: Hermitian lower triangle, row-major pack_tril)
+//   out   (naux, nao, nao) complex128; aux rows >= rows are zero ("aux basis drop")
+//   swapped: the entry belongs to the pair (k_j, k_i): out[L][p][q] = conj(src[L][q][p])
+// One CTA per 32x32 output tile of one auxiliary row: the source tile (the mirrored one for swapped entries and for
+// the upper triangle of packed entries) is read with its fast index along threadIdx.x, parked in shared memory and
+// written out transposed / conjugated as needed, so that both the loads and the stores are coalesced.  HBM-bound:
+// 8-16 B read + 16 B written per element.
+// ----------------------------------------------------------------------------------------------------------
+template <bool REAL>
+__device__ __forceinline__ double2 stored_elem(const void* __restrict__ src, size_t idx) {
+    if (REAL) return make_double2(static_cast<const double*>(src)[idx], 0.0);
+    return static_cast<const double2*>(src)[idx];
+}
+
+template <bool REAL>
+__global__ void __launch_bounds__(256)
+unpack_stored_kernel(const void* __restrict__ src, double2* __restrict__ out, int naux, int rows, int nao,
+                     long long ncols, int packed, int swapped) {
+    __shared__ double2 tile[32][33];
+    const int p0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
+    // source tile: rows r0.., columns c0.. of the (nao x nao) matrix the entry describes
+    const bool mirror = packed ? (p0 < q0) : (swapped != 0);       // read tile (q0, p0) and transpose it
+    const int r0 = mirror ? q0 : p0, c0 = mirror ? p0 : q0;
+    for (int L = blockIdx.z; L < naux; L += gridDim.z) {
+        double2* o = out + (size_t)L * nao * nao;
+        if (L >= rows) {
+            for (int dy = threadIdx.y; dy < 32; dy += 8) {
+                const int p = p0 + dy, q = q0 + threadIdx.x;
+                if (p < nao && q < nao) o[(size_t)p * nao + q] = make_double2(0.0, 0.0);
+            }
+            continue;
+        }
+        const size_t base = (size_t)L * (size_t)ncols;
+        for (int dy = threadIdx.y; dy < 32; dy += 8) {
+            const int r = r0 + dy, c = c0 + threadIdx.x;
+            double2 v = make_double2(0.0, 0.0);
+            if (r < nao && c < nao) {
+                if (!packed) v = stored_elem<REAL>(src, base + (size_t)r * nao + c);
+                else if (r >= c) v = stored_elem<REAL>(src, base + (size_t)r * (r + 1) / 2 + c);
+            }
+            tile[dy][threadIdx.x] = v;
+        }
+        __syncthreads();
+        for (int dy = threadIdx.y; dy < 32; dy += 8) {
+            const int p = p0 + dy, q = q0 + threadIdx.x;
+            if (p < nao && q < nao) {
+                double2 v;
+                if (packed) {
+                    // lower triangle stored; upper = conj of the mirrored element (unpack_tril, HERMITIAN)
+                    if (p0 > q0 || (p0 == q0 && dy >= (int)threadIdx.x)) v = tile[dy][threadIdx.x];
+                    else { v = tile[threadIdx.x][dy]; v.y = -v.y; }
+                    if (swapped) v.y = -v.y;               // packed entry of the swapped pair: plain conjugate
+                } else if (swapped) {
+                    v = tile[threadIdx.x][dy];
+                    v.y = -v.y;
+                } else {
+                    v = tile[dy][threadIdx.x];
+                }
+                o[(size_t)p * nao + q] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // The five real planes of the B operand that the 3-multiplication complex GEMM reads (zgemm_tn.cuh):
 //   F[5 z + 0] = Br, [5 z + 1] = Bi - Br, [5 z + 2] = Br + Bi, [5 z + 3] = -(Br + Bi), [5 z + 4] = Br - Bi
 // for every slice z of B (zb, N, K) complex; rows padded to Kp (even) doubles for the 16-byte TMA stride rule.

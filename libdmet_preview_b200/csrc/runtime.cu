@@ -163,12 +163,13 @@ struct ldm_context {
     bool zgemm_3m = true;        // complex products with three real multiplications (see zgemm_tn.cuh)
     // grow-only workspace pool of the ERI pipeline (X, S_sym, S_pln, panel, ring): cudaMalloc/cudaFree of GB-sized
     // buffers costs tens of ms per build and cudaFree synchronises the device, so they are kept across builds
-    void* ws[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[7] = {0, 0, 0, 0, 0, 0, 0};
+    void* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t bforms_ev = nullptr;   // last use of the WS_BFORMS planes (ldm_zgemm_tn may be called on any stream)
 };
 
-enum { WS_XT = 0, WS_SSYM = 1, WS_SPLN = 2, WS_PANEL = 3, WS_RING = 4, WS_BFORMS = 5, WS_CTFORMS = 6, WS_COUNT = 7 };
+enum { WS_XT = 0, WS_SSYM = 1, WS_SPLN = 2, WS_PANEL = 3, WS_RING = 4, WS_BFORMS = 5, WS_CTFORMS = 6, WS_STORED = 7,
+       WS_COUNT = 8 };
 
 static int ws_get(ldm_handle h, int slot, size_t bytes, void** out) {
     if (h->ws_bytes[slot] < bytes) {
@@ -563,6 +564,36 @@ int ldm_ztranspose(ldm_handle h, void* stream, const void* in_d, void* out_d, in
     ztranspose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_cast<const double2*>(in_d),
                                                                        static_cast<double2*>(out_d), rows, cols, conj,
                                                                        scale);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+static int check_stored_shape(int naux, int rows, int nao, int64_t ncols, int flags, int* packed) {
+    LDM_REQUIRE(naux > 0 && nao > 0 && rows >= 0 && rows <= naux, "stored entry: rows must lie in [0, naux]");
+    LDM_REQUIRE((flags & ~(LDM_STORED_SWAPPED | LDM_STORED_REAL)) == 0, "stored entry: unknown flags");
+    const int64_t full = (int64_t)nao * nao, tri = (int64_t)nao * (nao + 1) / 2;
+    LDM_REQUIRE(ncols == full || ncols == tri, "stored entry: ncols must be nao*nao or nao*(nao+1)/2");
+    *packed = (ncols != full) ? 1 : 0;
+    return 0;
+}
+
+int ldm_unpack_stored(ldm_handle h, void* stream, const void* src_d, void* out_d, int naux, int rows, int nao,
+                      int64_t ncols, int flags) {
+    LDM_REQUIRE(h && out_d && (src_d || rows == 0), "arguments");
+    int packed = 0;
+    int rc = check_stored_shape(naux, rows, nao, ncols, flags, &packed);
+    if (rc) return rc;
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    const int nt = (nao + 31) / 32;
+    dim3 grid(nt, nt, std::min(naux, 32768));
+    const int swapped = (flags & LDM_STORED_SWAPPED) ? 1 : 0;
+    if (flags & LDM_STORED_REAL)
+        unpack_stored_kernel<true><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+            src_d, static_cast<double2*>(out_d), naux, rows, nao, (long long)ncols, packed, swapped);
+    else
+        unpack_stored_kernel<false><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+            src_d, static_cast<double2*>(out_d), naux, rows, nao, (long long)ncols, packed, swapped);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -1022,6 +1053,39 @@ int ldm_eri_block_host(ldm_handle h, int ki, int kj, int sym, const void* L_h) {
     LDM_CUDA_OK(cudaMemcpyAsync(p->ring + (size_t)slot * block_elems(p), L_h, bytes, cudaMemcpyHostToDevice,
                                 p->copy_st));
     LDM_CUDA_OK(cudaStreamSynchronize(p->copy_st));   // source buffer is consumed when we return
+    p->h2d_bytes += (int64_t)bytes;
+    return push_block(h, ki, kj, sym, slot, 0);
+}
+
+int ldm_eri_block_stored(ldm_handle h, int ki, int kj, int sym, const void* src_h, int rows, int64_t ncols,
+                         int flags) {
+    LDM_REQUIRE(h && h->plan && (src_h || rows == 0), "arguments");
+    EriPlan* p = h->plan;
+    LDM_REQUIRE(ki >= 0 && ki < p->nk && kj >= 0 && kj < p->nk, "k index");
+    int packed = 0;
+    int rc = check_stored_shape(p->naux, rows, p->nao, ncols, flags, &packed);
+    if (rc) return rc;
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    int slot;
+    rc = ring_acquire(h, &slot);
+    if (rc) return rc;
+    double2* dst = p->ring + (size_t)slot * block_elems(p);
+    const size_t bytes = (size_t)rows * (size_t)ncols * ((flags & LDM_STORED_REAL) ? 8 : 16);
+    if (flags == 0 && !packed) {
+        // already in block layout: straight into the ring slot, absent auxiliary rows zeroed
+        if (bytes) LDM_CUDA_OK(cudaMemcpyAsync(dst, src_h, bytes, cudaMemcpyHostToDevice, p->copy_st));
+        if (rows < p->naux)
+            LDM_CUDA_OK(cudaMemsetAsync(reinterpret_cast<char*>(dst) + bytes, 0, block_elems(p) * 16 - bytes,
+                                        p->copy_st));
+    } else {
+        void* raw = nullptr;
+        rc = ws_get(h, WS_STORED, block_elems(p) * 16, &raw);
+        if (rc) return rc;
+        if (bytes) LDM_CUDA_OK(cudaMemcpyAsync(raw, src_h, bytes, cudaMemcpyHostToDevice, p->copy_st));
+        rc = ldm_unpack_stored(h, p->copy_st, raw, dst, p->naux, rows, p->nao, ncols, flags);
+        if (rc) return rc;
+    }
+    LDM_CUDA_OK(cudaStreamSynchronize(p->copy_st));   // source buffer (and the raw scratch) are consumed on return
     p->h2d_bytes += (int64_t)bytes;
     return push_block(h, ki, kj, sym, slot, 0);
 }

@@ -219,6 +219,22 @@ class Device(object):
         check(self.lib.ldm_max_abs(self.h, self.stream, _ptr(x), x.numel(), C.byref(out)))
         return out.value
 
+    def unpack_stored(self, src, naux, nao, flags=0, out=None):
+        """stored cderi entry (rows, ncols) on the device -> (naux, nao, nao) complex128 block
+        (ldm_unpack_stored: widen real data, unpack the Hermitian lower triangle, conjugate-transpose swapped
+        pairs, zero the auxiliary rows the entry lacks)"""
+        rows, ncols = int(src.shape[0]), int(src.shape[1])
+        if src.dtype == torch.float64:
+            flags |= 2
+        elif src.dtype != torch.complex128:
+            raise TypeError("stored entries are float64 or complex128")
+        src = src.contiguous()
+        if out is None:
+            out = self.empty((naux, nao, nao), torch.complex128)
+        check(self.lib.ldm_unpack_stored(self.h, self.stream, _ptr(src) if rows else None, _ptr(out), int(naux), rows,
+                                         int(nao), ncols, int(flags)))
+        return out
+
     def synth_block(self, out, naux, nao, keys, scale, aux_offset=0):
         check(self.lib.ldm_synth_block(self.h, self.stream, _ptr(out), naux, nao, int(aux_offset), int(keys[0]),
                                        int(keys[1]), int(keys[2]), int(keys[3]), float(scale)))

@@ -23,6 +23,7 @@ from .make_basis import add_spin_dim
 ERI_IMAG_TOL = 1e-6     # eri_transform.py:32
 DEFAULT_GROUP = None      # (k_i, k_j) blocks per stage-1 launch; None = choose from the block size (auto_groups)
 DEFAULT_KL_GROUP = None   # transfer momenta per stage-3 launch; None = auto
+DEVICE_UNPACK = True      # file-backed providers: ship stored entries as they are, unpack / transpose on the device
 
 
 def auto_groups(nao, naux, nemb, nspin, group=None, kl_group=None):
@@ -132,6 +133,13 @@ class ResidentGDF(object):
         inner = self.inner
         if hasattr(inner, "keys") and hasattr(inner, "scale"):
             get_device().synth_block(t[slot], l1 - l0, self.nao, inner.keys(ki, kj), inner.scale, aux_offset=l0)
+        elif DEVICE_UNPACK and hasattr(inner, "load_stored"):
+            # file-backed provider: the stored entry crosses PCIe as it is and is unpacked into the slot on the device
+            e = inner.load_stored(ki, kj, l0, l1, _staging_buffers(inner, 1)[0])
+            dev = get_device()
+            src = torch.from_numpy(e.data).to(dev.torch_device)
+            dev.unpack_stored(src, l1 - l0, self.nao, e.flags, out=t[slot])
+            dev.synchronize()                  # the staging buffer is reused by the next fetch
         else:
             L = inner.load(ki, kj)
             L = L if isinstance(L, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(L, dtype=np.complex128))
@@ -301,6 +309,14 @@ class EriBuild(object):
             ptr = L.ctypes.data_as(C.c_void_p)
         check(self.dev.lib.ldm_eri_block_host(self.dev.h, ki, kj, int(sym), ptr))
 
+    def block_stored(self, ki, kj, sym, entry):
+        """a block as it lies in the cderi file (gdf_file.StoredEntry): raw bytes to the device, unpacked there"""
+        a = entry.data
+        assert a.flags.c_contiguous and a.ndim == 2 and a.dtype in (np.complex128, np.float64)
+        ptr = a.ctypes.data_as(C.c_void_p) if a.size else None
+        check(self.dev.lib.ldm_eri_block_stored(self.dev.h, ki, kj, int(sym), ptr, int(a.shape[0]), int(a.shape[1]),
+                                                int(entry.flags)))
+
     def block_store(self, ki, kj, sym, slot):
         check(self.dev.lib.ldm_eri_block_store(self.dev.h, ki, kj, int(sym), int(slot)))
 
@@ -359,9 +375,11 @@ class _Prefetcher(object):
     of `lib.map_with_prefetch` in the reference's `sr_loop` (eri_transform.py:223).  File reads and numpy release the
     GIL, so disk or page-cache latency overlaps the host->device copy and the kernels.  Providers whose `load`
     accepts a destination (`fills_out`, e.g. `gdf_file.GDFFile`) read straight into a ring of page-locked buffers;
-    the consumer hands each buffer back with `done()` once the block is on the device."""
+    the consumer hands each buffer back with `done()` once the block is on the device.  With `stored=True` the
+    buffers receive the entries as they lie in the file (`load_stored`: packed / swapped / real data are NOT
+    expanded on the host) and the device does the unpacking (`ldm_eri_block_stored`)."""
 
-    def __init__(self, provider, requests, depth):
+    def __init__(self, provider, requests, depth, stored=False):
         import queue
         import threading
         depth = max(1, depth)
@@ -369,6 +387,7 @@ class _Prefetcher(object):
         self.err = None
         self.free = None
         self._lent = {}
+        self.stored = bool(stored) and hasattr(provider, "load_stored")
         if getattr(provider, "fills_out", False):
             self.free = queue.Queue()
             for b in _staging_buffers(provider, depth + 2):      # queued + one being filled + one being copied
@@ -383,8 +402,11 @@ class _Prefetcher(object):
                     buf = self.free.get()
                     if buf is None:                  # closed by the consumer
                         return
-                    provider.load(ki, kj, out=buf)
-                    view = buf[l0:l1]
+                    if self.stored:
+                        view = provider.load_stored(ki, kj, l0, l1, buf)
+                    else:
+                        provider.load(ki, kj, out=buf)
+                        view = buf[l0:l1]
                     self._lent[id(view)] = buf
                     self.q.put(view)
             except BaseException as e:          # surfaced in the consumer
@@ -425,7 +447,7 @@ def run_items(build, provider, schedule, items, source="auto", store_map=None, p
     pre = None
     if source == "host" and prefetch:
         reqs = [(ki, kj, l0, l1) for (u, l0, l1) in items for (ki, kj, sym) in schedule.units[u][2]]
-        pre = _Prefetcher(provider, reqs, prefetch)
+        pre = _Prefetcher(provider, reqs, prefetch, stored=DEVICE_UNPACK and hasattr(build, "block_stored"))
     try:
         for (u, l0, l1) in items:
             kL, weight, blocks = schedule.units[u]
@@ -438,7 +460,10 @@ def run_items(build, provider, schedule, items, source="auto", store_map=None, p
                         build.block_host(ki, kj, sym, _host_block(provider, ki, kj, l0, l1, provider.naux))
                 elif source == "host":
                     blk = pre.next() if pre is not None else _host_block(provider, ki, kj, l0, l1, provider.naux)
-                    build.block_host(ki, kj, sym, blk)
+                    if pre is not None and pre.stored:
+                        build.block_stored(ki, kj, sym, blk)
+                    else:
+                        build.block_host(ki, kj, sym, blk)
                     if pre is not None:
                         pre.done(blk)
                 elif source == "synth":

@@ -25,6 +25,36 @@ from .schedule import KPT_DIFF_TOL
 _KPT_FILE_TOL = 1e-6     # PySCF kpts_helper.member tolerance (KPT_DIFF_TOL)
 
 
+STORED_SWAPPED = 1       # include/ldm_b200.h: LDM_STORED_SWAPPED
+STORED_REAL = 2          # LDM_STORED_REAL
+
+
+class StoredEntry(object):
+    """rows of one cderi entry as they lie in the file + the flags the device unpacker needs"""
+    __slots__ = ("data", "flags")
+
+    def __init__(self, data, flags):
+        self.data, self.flags = data, flags
+
+    def expand(self, naux, nao):
+        """host twin of `ldm_unpack_stored` (tests, and providers without a device): (naux, nao, nao) complex128"""
+        out = np.zeros((naux, nao, nao), dtype=np.complex128)
+        a = self.data
+        rows = a.shape[0]
+        if a.shape[1] == nao * nao:
+            full = a.reshape(rows, nao, nao).astype(np.complex128)
+        else:
+            r, c = np.tril_indices(nao)
+            full = np.empty((rows, nao, nao), dtype=np.complex128)
+            full[:, c, r] = a.conj()
+            full[:, r, c] = a
+        if self.flags & STORED_SWAPPED:
+            # full entry of the pair (k_j, k_i): conjugate transpose; packed one: plain conjugate (PySCF _load3c)
+            full = full.conj().transpose(0, 2, 1) if a.shape[1] == nao * nao else full.conj()
+        out[:rows] = full
+        return out
+
+
 def _open(path):
     try:
         return h5lite.File(path)
@@ -166,6 +196,44 @@ class GDFFile(object):
         v[:, c, r] = packed.conj()                              # unpack_tril, HERMITIAN fill (l.216-217)
         v[:, r, c] = packed
         return rows, True
+
+    def load_stored(self, ki, kj, l0, l1, buf):
+        """Rows [l0, l1) of the entry that serves block (k_i, k_j), AS STORED, read into the byte storage of `buf`
+        (any C-contiguous array of at least naux * nao * nao * 16 bytes, e.g. a pinned staging buffer).  Returns a
+        `StoredEntry` whose `.data` is the (rows, ncols) view and `.flags` say how the device has to interpret it
+        (`ldm_eri_block_stored`).  Single-segment entries are one positioned read; column segments are read one
+        after the other into their column ranges."""
+        if (ki, kj) in self._key:
+            key, flags = self._key[(ki, kj)], 0
+        elif (kj, ki) in self._key:
+            key, flags = self._key[(kj, ki)], STORED_SWAPPED
+        else:
+            raise KeyError("k-point pair (%d, %d) is not stored in %s" % (ki, kj, self.path))
+        segs = _segments(self._f[self.label][key])
+        dtype = np.dtype(segs[0].dtype)
+        if dtype not in (np.dtype(np.complex128), np.dtype(np.float64)):
+            raise TypeError("%s: entry %s has dtype %s" % (self.path, key, dtype))
+        if dtype == np.float64:
+            flags |= STORED_REAL
+        nrow = int(segs[0].shape[0])
+        ncol = sum(int(s.shape[1]) for s in segs)
+        nao = self.nao
+        if ncol not in (nao * nao, nao * (nao + 1) // 2):
+            raise ValueError("%s: pair %s has %d columns, expected %d or %d" % (self.path, key, ncol, nao * nao,
+                                                                              nao * (nao + 1) // 2))
+        r0, r1 = min(l0, nrow), min(l1, nrow)
+        raw = buf.reshape(-1).view(np.uint8)
+        data = raw[:(r1 - r0) * ncol * dtype.itemsize].view(dtype).reshape(r1 - r0, ncol)
+        if r1 > r0:
+            if len(segs) == 1 and hasattr(segs[0], "read_direct"):
+                segs[0].read_direct(data, slice(r0, r1))
+            else:
+                c0 = 0
+                for s in segs:
+                    w = int(s.shape[1])
+                    data[:, c0:c0 + w] = s[r0:r1]
+                    c0 += w
+        return StoredEntry(data, flags)
 
     def load(self, ki, kj, out=None):
         """(naux, nao, nao) complex128 block L(k_i, k_j); auxiliary rows a pair does not have are zero.

@@ -165,3 +165,73 @@ def test_prefetcher_streams_file_blocks_through_a_buffer_ring(tmp_path):
     b = Broken(path, cell=gdf.cell)
     with pytest.raises(IOError):
         et.run_items(Recorder(), b, sch, work_items(sch, b.naux, 1), source="host")
+
+
+@pytest.mark.parametrize("version,nsegments,pack", [("v1", 1, True), ("v2", 3, True), ("v1", 2, False)])
+def test_stored_entries_expand_to_the_blocks(tmp_path, version, nsegments, pack):
+    """`load_stored` hands out the entries as they lie in the file (what crosses PCIe with DEVICE_UNPACK); their
+    expansion -- host twin of ldm_unpack_stored -- equals `load`, for every pair, orientation and aux range"""
+    from libdmet_preview_b200.gdf_file import STORED_SWAPPED, STORED_REAL
+    gdf = synthetic.SyntheticGDF([2, 1, 3], 5, 11, seed=3)
+    drop = {(1, 0): 9, (2, 2): 10, (4, 3): 3}
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, version=version, nsegments=nsegments, pack_diagonal=pack,
+                          naux_of=drop)
+    f = GDFFile(path, cell=gdf.cell)
+    buf = np.empty((11, 5, 5), dtype=np.complex128)
+    for (l0, l1) in ((0, 11), (0, 6), (6, 11), (4, 5)):
+        for i in range(6):
+            for j in range(6):
+                buf[...] = np.nan
+                e = f.load_stored(i, j, l0, l1, buf)
+                assert e.data.size == 0 or np.shares_memory(e.data, buf)
+                assert bool(e.flags & STORED_SWAPPED) == (i < j)
+                assert bool(e.flags & STORED_REAL) == (i == 0 and j == 0)
+                if i == j and pack:
+                    assert e.data.shape[1] == 15
+                else:
+                    assert e.data.shape[1] == 25
+                rows_stored = drop.get((i, j), drop.get((j, i), 11))
+                assert e.data.shape[0] == max(0, min(l1, rows_stored) - min(l0, rows_stored))
+                want = f.load(i, j)[l0:l1]
+                assert np.array_equal(e.expand(l1 - l0, 5), want), (i, j, l0, l1)
+
+
+def test_run_items_ships_stored_entries_when_the_build_can_unpack(tmp_path):
+    from libdmet_preview_b200.schedule import build_schedule, work_items
+    gdf = synthetic.SyntheticGDF([1, 2, 2], 4, 10, seed=6)
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, nsegments=2, naux_of={(3, 1): 7})
+    f = GDFFile(path, cell=gdf.cell)
+    sch = build_schedule(f.kpts_scaled, True)
+
+    class Recorder(object):
+        def __init__(self, naux):
+            self.naux, self.blocks, self.bytes = naux, [], 0
+
+        def block_stored(self, ki, kj, sym, entry):
+            self.blocks.append((ki, kj, entry.expand(self.naux, 4)))
+            self.bytes += entry.data.nbytes
+            entry.data[...] = np.nan
+
+        def block_host(self, *a):
+            raise AssertionError("expanded block shipped although the build unpacks on the device")
+
+        def end_kl(self, weight):
+            pass
+
+        def finish(self):
+            pass
+
+    for nsplit in (1, 2):
+        items = work_items(sch, f.naux, nsplit)
+        for (l0, l1) in sorted({(a, b) for (_, a, b) in items}):
+            sub = [it for it in items if (it[1], it[2]) == (l0, l1)]
+            rec = Recorder(l1 - l0)
+            et.run_items(rec, f, sch, sub)
+            want = [(ki, kj) for (u, _, _) in sub for (ki, kj, sym) in sch.units[u][2]]
+            assert [(b[0], b[1]) for b in rec.blocks] == want
+            for ki, kj, L in rec.blocks:
+                full = gdf.load(ki, kj).copy()
+                if (ki, kj) in ((3, 1), (1, 3)):
+                    full[7:] = 0
+                assert np.array_equal(L, full[l0:l1])
+            assert rec.bytes < len(want) * (l1 - l0) * 16 * 16       # packed / real / dropped rows: fewer bytes
