@@ -834,6 +834,10 @@ def transform_gdf_to_lo(mydf, C_ao_lo, fname="gdf_ints_lo.h5", t_reversal_symm=T
             continue
         if synth:
             dev.synth_block(Ld, naux, nao, provider.keys(i, j), provider.scale)
+        elif DEVICE_UNPACK and hasattr(provider, "load_stored"):       # entry as stored -> unpacked on the device
+            e = provider.load_stored(i, j, 0, naux, _staging_buffers(provider, 1)[0])
+            dev.unpack_stored(torch.from_numpy(e.data).to(dev.torch_device), naux, nao, e.flags, out=Ld)
+            dev.synchronize()
         else:
             blk = np.ascontiguousarray(provider.load(i, j), dtype=np.complex128)
             assert blk.size == naux * nao * nao

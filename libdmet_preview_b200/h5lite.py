@@ -566,11 +566,7 @@ class File(Group):
             self._root_addr = c.u(O)
         else:
             raise H5FormatError("superblock version %d" % ver)
-        # libhdf5 records base address 0 for files with a user block written through the standard driver and
-        # resolves every address relative to the superblock position
-        self._base = base if base != 0 else off
-        if base != 0 and base != off:
-            raise H5FormatError("base address %d differs from the superblock offset %d" % (base, off))
+        self._base = base              # every other address in the file is relative to it (= the user-block size)
 
     # -- object headers ----------------------------------------------------------------------------
     def _messages(self, addr):
