@@ -49,7 +49,7 @@ def get_emb_basis(lattice, rho=None, local=True, kind='svd', **kwargs):
     if kind == 'svd':
         return _get_emb_basis_svd(lattice, rho.real, **kwargs)
     elif kind == 'eig':
-        raise NotImplementedError("kind='eig' bath construction is not part of the hot path")
+        return _get_emb_basis_eig(lattice, rho.real, **kwargs)
     else:
         raise ValueError("get_emb_basis: Unknown kind %s" % kind)
 
@@ -106,6 +106,52 @@ def _get_emb_basis_svd(lattice, rdm1, **kwargs):
         basis[s, env_idx, nimp:nimp + nb] = bath
         nbath_cap = min(nbath_cap, nb)
     return basis[:, :, :nimp + nbath_cap].reshape(spin, ncells, nlo, nimp + nbath_cap)
+
+
+def _get_emb_basis_eig(lattice, rdm1, **kwargs):
+    """slater.py:224-318 (fractionally occupied case).  The bath orbitals are the eigenvectors of the
+    environment-environment block of the density matrix whose occupation is neither 0 nor 1 (within `tol_bath`);
+    everything else -- which orbitals generate the bath, zeroing of the virtual impurity rows + Loewdin step, layout
+    of the result -- is as in the SVD construction.  Host LAPACK (`eigh`), like the reference."""
+    opt = dict(imp_idx=lattice.imp_idx, val_idx=lattice.val_idx, valence_bath=True, orth=True, tol_bath=1e-9,
+               localize_bath=None)
+    opt.update({k: v for k, v in kwargs.items() if k in opt})
+    if opt["localize_bath"] is not None:
+        raise NotImplementedError("bath localisation is only defined for model Hamiltonians in the reference")
+    imp_idx, val_idx = list(opt["imp_idx"]), list(opt["val_idx"])
+    ncells, nlo = int(lattice.ncells), int(lattice.nscsites)
+    ntot = ncells * nlo
+    gen_idx = val_idx if opt["valence_bath"] else imp_idx
+    is_gen = np.zeros(ntot, dtype=bool)
+    is_gen[gen_idx] = True
+    is_imp = np.zeros(ntot, dtype=bool)
+    is_imp[imp_idx] = True
+    env_idx = np.flatnonzero(~is_gen)
+    nimp = len(imp_idx)
+
+    rdm1 = np.asarray(rdm1)
+    rdm1 = rdm1[None] if rdm1.ndim == 3 else rdm1
+    assert rdm1.shape[-3:] == (ncells, nlo, nlo)
+    spin = rdm1.shape[0]
+    env_env = lattice.expand(rdm1)[:, env_idx][:, :, env_idx]
+    baths = []
+    for s in range(spin):
+        occ, vec = la.eigh(env_env[s])
+        fractional = (np.abs(occ) > opt["tol_bath"]) & (np.abs(1.0 - occ) > opt["tol_bath"])
+        baths.append(vec[:, fractional])
+    nb = baths[0].shape[1]
+    if any(b.shape[1] != nb for b in baths):       # the reference stacks the spin channels into one array (l.286)
+        raise ValueError("the spin channels have different numbers of bath orbitals: %s"
+                         % [b.shape[1] for b in baths])
+    basis = np.zeros((spin, ntot, nimp + nb))
+    for s in range(spin):
+        bath = baths[s]
+        if nb > 0 and opt["orth"]:
+            bath[is_imp[env_idx]] = 0.0
+            bath = vec_lowdin(bath)
+        basis[s, imp_idx, :nimp] = np.eye(nimp)
+        basis[s, env_idx, nimp:] = bath
+    return basis.reshape(spin, ncells, nlo, nimp + nb)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -57,12 +57,48 @@ def check_span_same_space(a, b, ovlp=None, tol=1e-8):
 # get_emb_basis
 # ---------------------------------------------------------------------------------------------------------
 def get_emb_basis(lattice, rho=None, local=True, kind='svd', **kwargs):
-    """dispatcher (slater.py:98-115); only the local SVD construction is restated"""
+    """dispatcher (slater.py:98-115); the local SVD and eigenvalue constructions are restated"""
     rho = lattice.rdm1_lo_R if rho is None else rho
     assert local, "oracle restates the local branch only"
+    if kind == 'eig':
+        return _get_emb_basis_eig(lattice, np.asarray(rho).real, **kwargs)
     if kind != 'svd':
         raise ValueError("get_emb_basis: Unknown kind %s" % kind)
     return _get_emb_basis_svd(lattice, np.asarray(rho).real, **kwargs)
+
+
+def _get_emb_basis_eig(lattice, rdm1, imp_idx=None, val_idx=None, valence_bath=True, orth=True, tol_bath=1e-9,
+                       **unused):
+    """Bath orbitals = eigenvectors of the environment-environment block of the density matrix with occupation
+    away from 0 and 1 (slater.py:224-318)."""
+    imp_idx = list(lattice.imp_idx if imp_idx is None else imp_idx)
+    val_idx = list(lattice.val_idx if val_idx is None else val_idx)
+    ncells, nlo = lattice.ncells, lattice.nscsites
+    ntot = ncells * nlo
+    generators = val_idx if valence_bath else imp_idx
+    env = np.setdiff1d(np.arange(ntot), generators)
+    env_is_imp = np.isin(env, imp_idx)
+    nimp = len(imp_idx)
+    rdm1 = np.asarray(rdm1)
+    rdm1 = rdm1[None] if rdm1.ndim == 3 else rdm1
+    spin = rdm1.shape[0]
+    block = lattice.expand(rdm1)[:, env][:, :, env]
+    bath = []
+    for s in range(spin):
+        ew, ev = la.eigh(block[s])
+        bath.append(np.asarray([ev[:, i] for i, e in enumerate(ew)
+                                if abs(e) > tol_bath and abs(1 - e) > tol_bath]).T)
+    bath = np.asarray(bath)                                     # (spin, nenv, nbath): equal counts per spin
+    nbath = bath.shape[-1]
+    out = np.zeros((spin, ntot, nimp + nbath))
+    for s in range(spin):
+        B = bath[s]
+        if nbath > 0 and orth:
+            B[env_is_imp] = 0.0
+            B = vec_lowdin(B)
+        out[s, imp_idx, :nimp] = np.eye(nimp)
+        out[s, env, nimp:] = B
+    return out.reshape(spin, ncells, nlo, nimp + nbath)
 
 
 def _get_emb_basis_svd(lattice, rdm1, imp_idx=None, val_idx=None, valence_bath=True, orth=True, tol_bath=1e-9,

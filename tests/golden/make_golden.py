@@ -167,6 +167,24 @@ def gen_emb_basis_hchain():
     save("emb_basis_hchain", rdm1_lo=rdm1_lo, basis=basis, basis_trunc=basis_trunc)
 
 
+def gen_emb_basis_eig():
+    """eigenvalue construction of the bath (slater.py:224-318) on the mean-field density matrices of the embHam
+    cases and on the reference's H-chain fixture"""
+    out = {}
+    for tag, (kmesh, nao, naux, nval, spin) in {"r": ([1, 1, 3], 5, 11, 3, 1), "u": ([1, 2, 2], 4, 9, 2, 2)}.items():
+        Lat, gdf, C, _ = make_ref_lattice(kmesh, nao, naux, nval, spin, 4, "eig_" + tag)
+        rho = Lat.rdm1_lo_R * (0.5 if spin == 1 else 1.0)
+        out["rho_" + tag] = rho
+        out["kmesh_" + tag], out["nao_" + tag], out["nval_" + tag] = np.array(kmesh), nao, nval
+        out["basis_" + tag] = ref_slater.get_emb_basis(Lat, rho, kind='eig')
+        out["basis_full_" + tag] = ref_slater.get_emb_basis(Lat, rho, kind='eig', valence_bath=False)
+    rdm1_lo = np.load(os.path.join(ref_stubs.REF_ROOT, "libdmet", "routine", "test", "rdm1_lo"))
+    Lat = ref_lattice.Lattice(GoldenCell(4), [1, 1, 3])
+    Lat.set_val_virt_core(2, 2, 0)
+    out["basis_hchain"] = ref_slater.get_emb_basis(Lat, rdm1_lo, kind='eig')
+    save("emb_basis_eig", **out)
+
+
 def gen_gso():
     """GSO embedding ERI (eri_transform.py:1104-1284); the reference itself imports
     libdmet.routine.spinless.separate_basis inside the function"""
@@ -282,6 +300,7 @@ def gen_eri_file():
 
 
 if __name__ == "__main__":
+    gen_emb_basis_eig()
     gen_eri_file()
     gen_gdf_lo()
     gen_gso_embham()
