@@ -56,8 +56,15 @@ def install():
             _swap(m, n, getattr(fourier, n))
     _swap(r_mb, "transform_h1_to_lo", make_basis.transform_h1_to_lo)
     _swap(r_mb, "multiply_basis", make_basis.multiply_basis)
+    ref_get_emb_basis = r_sl.get_emb_basis
+
+    def get_emb_basis(lattice, rho=None, local=True, kind='svd', **kwargs):
+        if not local or kwargs.get("localize_bath") is not None:      # model-Hamiltonian baths: reference route
+            return ref_get_emb_basis(lattice, rho, local=local, kind=kind, **kwargs)
+        return slater.get_emb_basis(lattice, rho, local=local, kind=kind, **kwargs)
+
     for n in ("get_emb_basis", "embBasis"):
-        _swap(r_sl, n, slater.get_emb_basis)
+        _swap(r_sl, n, get_emb_basis)
     for n in ("get_emb_Ham", "embHam"):
         _swap(r_sl, n, slater.get_emb_Ham)
     return sorted("%s.%s" % (m.__name__, n) for (m, n) in _saved)
