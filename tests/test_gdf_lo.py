@@ -74,3 +74,72 @@ def test_lo_gdf_npz_round_trip(tmp_path):
     for ki in range(3):
         for kj in range(3):
             assert np.array_equal(back.load(ki, kj), lo.load(ki, kj))
+
+
+class _HostStandIn(object):
+    """stand-in for `device.Device` with the five entry points `transform_gdf_to_lo` drives, each restated with
+    torch CPU tensors from the C-ABI documentation (include/ldm_b200.h) -- exercises the HOST logic of that function
+    (pair loop, time-reversal filling, storage rules, stored-entry route, HDF5 output) without a GPU.  The CUDA
+    kernels themselves are checked in tests/test_gpu_*.py."""
+    import torch as _torch
+    torch_device = _torch.device("cpu")
+
+    def empty(self, shape, dtype):
+        import torch
+        return torch.empty(shape, dtype=dtype)
+
+    def ztranspose(self, x, conj=False, scale=1.0):
+        return x.transpose(-1, -2).contiguous()
+
+    def synchronize(self):
+        pass
+
+    def to_host(self, t):
+        return t.numpy().copy()
+
+    def unpack_stored(self, src, naux, nao, flags=0, out=None):
+        import torch
+        from libdmet_preview_b200.gdf_file import StoredEntry
+        if src.dtype == torch.float64:
+            flags |= 2
+        out.copy_(torch.from_numpy(StoredEntry(src.numpy(), flags).expand(naux, nao)))
+        return out
+
+    def zgemm_tn(self, A, B, segs, C_out, rdiv=1, s_outer=None, s_inner=0, s_col=1, **kw):
+        """C[(r / rdiv) * s_outer + (r % rdiv) * s_inner + n * s_col] = sum_k A[za][r][k] * op(B[zb][n][k])"""
+        import torch
+        (za, zb, _, conj), = segs
+        Bm = B[zb].conj() if conj else B[zb]
+        res = A[za] @ Bm.T
+        r = torch.arange(A.shape[1])
+        n = torch.arange(Bm.shape[0])
+        idx = ((r // rdiv) * s_outer + (r % rdiv) * s_inner)[:, None] + n[None, :] * s_col
+        C_out.reshape(-1)[idx.reshape(-1)] = res.reshape(-1)
+
+
+@pytest.mark.parametrize("device_unpack", [True, False])
+def test_transform_gdf_to_lo_host_logic_from_a_file(tmp_path, monkeypatch, device_unpack):
+    import torch
+    from libdmet_preview_b200 import h5lite
+    from libdmet_preview_b200.gdf_file import GDFFile, write_gdf_file
+    monkeypatch.setattr(et, "get_device", lambda *a: _HostStandIn())
+    monkeypatch.setattr(et, "_to_z", lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)))
+    monkeypatch.setattr(et, "DEVICE_UNPACK", device_unpack)
+    kmesh, nao, nlo, naux = [2, 1, 2], 6, 5, 13
+    gdf = synthetic.SyntheticGDF(kmesh, nao, naux, seed=21)
+    C = synthetic.make_C_ao_lo(kmesh, nao, nlo, seed=22)
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, nsegments=2, naux_of={(2, 1): 9})
+    f = GDFFile(path, cell=gdf.cell, kpts=gdf.kpts)
+    out = str(tmp_path / "lo.h5")
+    lo = et.transform_gdf_to_lo(f, C, fname=out)
+    ref = oe.transform_gdf_to_lo(f, C)
+    assert isinstance(lo, et.LoGDF) and sorted(lo.j3c) == sorted(ref)
+    with h5lite.File(out) as h:
+        for k, v in ref.items():
+            x = h["j3c/%d/0" % k][...]
+            assert x.dtype == v.dtype and x.shape == v.shape and np.abs(x - v).max() < 1e-13
+    # a GDF-like object (path + kpts + cell) comes back as a GDF-like object pointing at the new file
+    import types
+    mydf = types.SimpleNamespace(_cderi=path, kpts=gdf.kpts, cell=gdf.cell)
+    mydf_lo = et.transform_gdf_to_lo(mydf, C, fname=str(tmp_path / "lo2.h5"))
+    assert mydf_lo._cderi.endswith("lo2.h5") and mydf_lo.cell.nao_nr() == nlo and mydf.cell.nao_nr() == nao
