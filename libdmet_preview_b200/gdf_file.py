@@ -9,6 +9,9 @@ What the reference does with the file (`libdmet/basis_transform/eri_transform.py
 Two generations of the layout exist and both are read here:
     v1   `j3c-kptij` (npairs, 2, 3) absolute k-point pairs, `j3c/<position in that list>/<seg>`
     v2   `kpts` (nkpts, 3), `aosym` ('s1' | 's2'), `j3c/<k_i * nkpts + k_j>/<seg>`      (PySCF >= 2.1)
+(v1 is what the reference itself relies on -- it passes 'j3c-kptij' to `_load3c` -- and is pinned by golden results of
+the reference's own code, tests/golden/eri_file_*.npz; v2 follows PySCF's `CDERIArray` key convention and is checked
+against this module's own writer only.)
 A `j3c/<pair>` entry may also be a plain dataset instead of a group of segments (old PySCF, and what
 `transform_gdf_to_lo` writes: `j3c/<pair>/0` only).
 
