@@ -18,7 +18,7 @@ from . import eri_transform
 from .eri_transform import get_emb_eri, get_unit_eri
 from .fourier import IMAG_DISCARD_TOL
 from .integral import Integral, get_eri_format
-from .make_basis import add_spin_dim
+from .make_basis import add_spin_dim, sandwich, _finish
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -521,3 +521,70 @@ def transformResults(rhoEmb, E, basis, ImpHam, H1e=None, **kwargs):
     H1_scaled = get_H1_scaled(H1_scaled, imp_idx)
     E1 = per_spin * np.einsum("spq,sqp", H1_scaled, rhoEmb)
     return rhoImp, E1 + E2 + lattice.getH0(), nelec
+
+
+# ---------------------------------------------------------------------------------------------------------
+# global density matrix by democratic partitioning (slater_helper.py:183-283)
+# ---------------------------------------------------------------------------------------------------------
+def get_rho_glob_R(basis, lattice, rho_emb, symmetric=True, compact=True, sign=None):
+    """Global one-particle density matrix in the LO basis, stripe shape (spin, ncells, nlo, nlo), averaged
+    democratically over the impurity problems of all cells (slater_helper.py:183-270): every cell R carries a
+    translated copy of the embedding problem, its impurity-impurity block counts fully, impurity-environment blocks
+    half, environment-environment blocks not at all.
+
+    The reference builds, for each R, the full-lattice product C_R rho C_R[:nlo]^T and masks it.  With the impurity
+    inside cell 0 the sum over R collapses to
+        rho_R[I] = 1/2 [ (M C_0) rho C_{-I}^T  +  C_I rho (M C_0)^T ]            (M = diagonal impurity mask,
+                                                                                  C_I = rows of cell I)
+    which is ONE batched product on the device: operands [1/2 M C_0 | C_I] and [C_{-I} | 1/2 M C_0] around
+    blockdiag(rho, rho); several fragments (lists of bases / lattices / density matrices) extend the contraction
+    index.  The masked operands are laid out on the host (no arithmetic beyond the mask), the contraction runs in
+    `zgemm_tn` (make_basis.sandwich)."""
+    from collections.abc import Iterable
+    if isinstance(lattice, Iterable):
+        frags = list(zip(basis, lattice, rho_emb))
+    else:
+        frags = [(basis, lattice, rho_emb)]
+    if sign is not None or not compact:
+        raise NotImplementedError("full-shape / signed global density matrices (particle-hole fragments) are "
+                                  "outside the ab-initio path")
+    left, right, blocks = [], [], []
+    spin = ncells = nlo = None
+    for basis_f, lat_f, rho_f in frags:
+        b = np.asarray(basis_f.cpu() if isinstance(basis_f, torch.Tensor) else basis_f, dtype=np.float64)
+        b = b[None] if b.ndim == 3 else b
+        if spin is None:
+            spin, ncells, nlo = b.shape[:3]
+        assert b.shape[:3] == (spin, ncells, nlo)
+        rho = np.asarray(rho_f.cpu() if isinstance(rho_f, torch.Tensor) else rho_f, dtype=np.float64)
+        rho = add_spin_dim(rho, spin, non_spin_dim=2)
+        imp = np.asarray(lat_f.imp_idx, dtype=int)
+        if imp.size and (imp.min() < 0 or imp.max() >= nlo):
+            raise NotImplementedError("impurity orbitals outside the first cell")
+        mask = np.zeros(nlo)
+        mask[imp] = 0.5
+        half = np.broadcast_to((mask[None, :, None] * b[:, 0])[:, None], b.shape)         # 1/2 M C_0 for every cell
+        minus = [lat_f.subtract(0, i) for i in range(ncells)]
+        left += [half, b]
+        right += [b[:, minus], half]
+        blocks += [rho, rho]
+    A1 = np.ascontiguousarray(np.concatenate(left, axis=-1)).reshape(spin * ncells, nlo, -1)
+    A2T = np.ascontiguousarray(np.concatenate(right, axis=-1)).reshape(spin * ncells, nlo, -1)
+    ntot = A1.shape[-1]
+    H = np.zeros((spin, ntot, ntot))
+    off = 0
+    for r in blocks:
+        n = r.shape[-1]
+        H[:, off:off + n, off:off + n] = r
+        off += n
+    out = sandwich(_zdev(A1), False, _zdev(A2T), False, _zdev(H), h_index=np.repeat(np.arange(spin), ncells),
+                   a_index=np.arange(spin * ncells))
+    return _finish(out, (spin, ncells, nlo, nlo), np.float64, False)
+
+
+def get_rho_glob_k(basis, lattice, rho_emb, symmetric=True, compact=True, sign=None):
+    """slater_helper.py:272-283: the same matrix in k space (R2k on the device)."""
+    from collections.abc import Iterable
+    rho_R = get_rho_glob_R(basis, lattice, rho_emb, symmetric=symmetric, compact=compact, sign=sign)
+    lat0 = lattice[0] if isinstance(lattice, Iterable) else lattice
+    return lat0.R2k(rho_R)

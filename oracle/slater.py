@@ -404,3 +404,51 @@ def transformResults(rhoEmb, E, basis, ImpHam, H1e=None, **kwargs):
     H1s = get_H1_scaled(H1s, imp_idx)
     E1 = per_spin * np.einsum("spq,sqp", H1s, rhoEmb)
     return rhoImp, E1 + E2 + lattice.getH0(), nelec
+
+
+# ---------------------------------------------------------------------------------------------------------
+# global density matrix by democratic partitioning (slater_helper.py:158-283)
+# ---------------------------------------------------------------------------------------------------------
+def get_emb_basis_other_cell(lattice, basis, R):
+    """embedding basis of the impurity problem sitting in cell R: cell I of it is cell I - R of the original
+    (slater_helper.py:158-181)"""
+    basis = np.asarray(basis)
+    order = [lattice.subtract(I, R) for I in range(basis.shape[-3])]
+    return basis[..., order, :, :]
+
+
+def get_rho_glob_R(basis, lattice, rho_emb, compact=True):
+    """stripe-shaped global density matrix (spin, ncells, nlo, nlo): for every cell R the full product of the
+    translated embedding basis with the embedded density matrix, impurity-environment blocks halved,
+    environment-environment blocks dropped, summed over R and over fragments (slater_helper.py:183-270, compact
+    branch; lists of bases / lattices / density matrices = several fragments)"""
+    assert compact
+    if isinstance(lattice, (list, tuple)):
+        frags = list(zip(basis, lattice, rho_emb))
+    else:
+        frags = [(basis, lattice, rho_emb)]
+    total = 0.0
+    for basis_I, lat, rho_I in frags:
+        basis_I = np.asarray(basis_I)
+        basis_I = basis_I[None] if basis_I.ndim == 3 else basis_I
+        spin, ncells, nlo, _ = basis_I.shape
+        rho_I = np.asarray(rho_I)
+        rho_I = rho_I[None] if rho_I.ndim == 2 else rho_I
+        if rho_I.shape[0] < spin:
+            rho_I = np.asarray([rho_I[0]] * spin)
+        rho_R = np.zeros((spin, ncells * nlo, nlo))
+        for R in range(ncells):
+            other = get_emb_basis_other_cell(lat, basis_I, R)
+            imp = np.asarray(lat.imp_idx) + R * nlo
+            env = np.setdiff1d(np.arange(ncells * nlo), imp)
+            in_cell0 = np.isin(np.arange(nlo), imp)
+            imp0, env0 = np.flatnonzero(in_cell0), np.flatnonzero(~in_cell0)
+            for s in range(spin):
+                C_R = other[s].reshape(ncells * nlo, -1)
+                block = C_R.dot(rho_I[s]).dot(C_R[:nlo].conj().T)
+                block[np.ix_(imp, env0)] *= 0.5
+                block[np.ix_(env, imp0)] *= 0.5
+                block[np.ix_(env, env0)] = 0.0
+                rho_R[s] += block
+        total = total + rho_R.reshape(spin, ncells, nlo, nlo)
+    return total

@@ -185,6 +185,40 @@ def gen_emb_basis_eig():
     save("emb_basis_eig", **out)
 
 
+def gen_rho_glob():
+    """global density matrix by democratic partitioning through the reference's slater_helper.get_rho_glob_R
+    (slater_helper.py:183-270): one fragment (restricted and unrestricted) and two fragments sharing cell 0"""
+    import libdmet.routine.slater_helper as ref_helper
+    out = {}
+    rng = np.random.default_rng(123)
+    for tag, (kmesh, nlo, neo, spin, imp) in {"r": ([1, 2, 2], 5, 7, 1, [0, 1, 2]), "u": ([2, 1, 3], 4, 6, 2, [0, 1, 2, 3])}.items():
+        Lat = ref_lattice.Lattice(GoldenCell(nlo), kmesh)
+        Lat.set_val_virt_core(len(imp), 0, 0)
+        Lat.val_idx, Lat.virt_idx = list(imp), []
+        nk = int(np.prod(kmesh))
+        basis = rng.standard_normal((spin, nk, nlo, neo))
+        rho = rng.standard_normal((spin, neo, neo))
+        rho = rho + rho.transpose(0, 2, 1)
+        assert list(Lat.imp_idx) == list(imp)
+        out["kmesh_" + tag], out["imp_" + tag] = np.array(kmesh), np.array(imp)
+        out["basis_" + tag], out["rho_" + tag] = basis, rho
+        out["glob_" + tag] = ref_helper.get_rho_glob_R(basis, Lat, rho)
+    # two fragments: orbitals {0, 1} and {2, 3, 4} of a 5-orbital cell, different numbers of embedding orbitals,
+    # a non-symmetric "density matrix" for the second one (the reference does not symmetrise)
+    kmesh, nlo = [1, 1, 3], 5
+    lats, bases, rhos = [], [], []
+    for imp, neo in (([0, 1], 4), ([2, 3, 4], 6)):
+        Lat = ref_lattice.Lattice(GoldenCell(nlo), kmesh)
+        Lat.set_val_virt_core(len(imp), 0, 0)
+        Lat.val_idx, Lat.virt_idx = list(imp), []
+        lats.append(Lat)
+        bases.append(rng.standard_normal((1, 3, nlo, neo)))
+        rhos.append(rng.standard_normal((1, neo, neo)))
+    out["basis_f0"], out["basis_f1"], out["rho_f0"], out["rho_f1"] = bases[0], bases[1], rhos[0], rhos[1]
+    out["glob_f"] = ref_helper.get_rho_glob_R(bases, lats, rhos)
+    save("rho_glob", **out)
+
+
 def gen_gso():
     """GSO embedding ERI (eri_transform.py:1104-1284); the reference itself imports
     libdmet.routine.spinless.separate_basis inside the function"""
@@ -300,6 +334,7 @@ def gen_eri_file():
 
 
 if __name__ == "__main__":
+    gen_rho_glob()
     gen_emb_basis_eig()
     gen_eri_file()
     gen_gdf_lo()
