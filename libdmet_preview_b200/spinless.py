@@ -1,7 +1,8 @@
 """Generalised-spin-orbital (GSO / BCS-type) embedding Hamiltonian -- drop-in for the ab-initio, interacting-bath,
 Hartree-Fock branch of `libdmet.routine.spinless.get_emb_Ham` (`embHam`), spinless.py:433-462, 464-558 (two-body part
 via `get_emb_eri_gso`) and 560-726 (one-body part), with the helpers of spinless_helper.py:31-46 (`separate_basis`),
-349-438 (`transform_trans_inv_k`, `transform_local`, `transform_imp`).
+349-438 (`transform_trans_inv_k`, `transform_local`, `transform_imp`), and for the GSO bath construction
+`get_emb_basis` (spinless.py:34-272, kinds 'svd' and 'eig'; host LAPACK like the reference).
 
 A GSO basis has 2*nao rows per cell (alpha rows, then beta rows).  Lattice quantities come as (3, nkpts, nao, nao)
 stacks (aa, bb, ab); the density matrix is one (nkpts, 2*nao, 2*nao) generalised matrix.  The two-body integrals stay
@@ -22,6 +23,84 @@ from .make_basis import sandwich
 
 def _zdev(a):
     return slater._zdev(a)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GSO bath construction (spinless.py:34-272): host gather + LAPACK, as the reference (and as slater.get_emb_basis)
+# ---------------------------------------------------------------------------------------------------------
+def _gso_index_sets(lattice, valence_bath):
+    """spin-orbital index sets of the generalised problem: orbital i of cell R has the alpha row R*nso + i and the
+    beta row R*nso + nlo + i.  Returns (imp, env, env_is_imp, env_is_alpha)."""
+    ncells, nlo = int(lattice.ncells), int(lattice.nscsites)
+    nso = 2 * nlo
+    both = lambda idx: [int(i) for i in idx] + [int(i) + nlo for i in idx]       # noqa: E731
+    imp = both(lattice.imp_idx)
+    gen = both(lattice.val_idx) if valence_bath else imp
+    is_gen = np.zeros(ncells * nso, dtype=bool)
+    is_gen[gen] = True
+    is_imp = np.zeros(ncells * nso, dtype=bool)
+    is_imp[imp] = True
+    env = np.flatnonzero(~is_gen)
+    return imp, gen, env, is_imp[env], (env % nso) < nlo
+
+
+def _gso_finish(lattice, bath, imp, env, env_is_imp, env_is_alpha, orth, kwargs):
+    """shared tail of both constructions: virtual rows zeroed + Loewdin, columns ordered by decreasing alpha
+    (particle) weight, identity on the impurity rows (spinless.py:124-162 / 240-271)"""
+    if kwargs.get("localize_bath") is not None:
+        raise NotImplementedError("bath localisation is only defined for model Hamiltonians in the reference")
+    if not orth:
+        raise NotImplementedError                                   # l.129-131
+    ncells, nso = int(lattice.ncells), 2 * int(lattice.nscsites)
+    nbath = bath.shape[1]
+    if nbath % 2 != 0:
+        raise ValueError("nbath (%s) should be even in GSO." % nbath)            # l.114
+    if nbath > 0:
+        bath[env_is_imp] = 0.0
+        bath = slater.vec_lowdin(bath)
+    weight = np.einsum("ai,ai->i", bath[env_is_alpha], bath[env_is_alpha])
+    order = np.argsort(weight, kind="mergesort")[::-1]
+    nimp = len(imp)
+    basis = np.zeros((ncells * nso, nimp + nbath))
+    basis[imp, :nimp] = np.eye(nimp)
+    basis[env, nimp:] = bath[:, order]
+    return basis.reshape(ncells, nso, nimp + nbath)
+
+
+def get_emb_basis(lattice, GRho, local=True, kind='svd', **kwargs):
+    """spinless.py:34-53: embedding basis (ncells, 2*nlo, nimp + nbath) of the generalised density matrix
+    GRho (ncells, 2*nlo, 2*nlo); kind 'svd' (58-162) or 'eig' (167-272)."""
+    if not local:
+        raise NotImplementedError
+    if kwargs.get("bath_opt", False):
+        raise NotImplementedError("bath optimisation (get_emb_basis_opt) is outside the path")
+    rdm1 = np.asarray(GRho.cpu() if isinstance(GRho, torch.Tensor) else GRho).real
+    ncells, nso = int(lattice.ncells), 2 * int(lattice.nscsites)
+    assert rdm1.shape == (ncells, nso, nso)
+    valence_bath = kwargs.get("valence_bath", True)
+    orth = kwargs.get("orth", True)
+    tol_bath = kwargs.get("tol_bath", 1e-9)
+    imp, gen, env, env_is_imp, env_is_alpha = _gso_index_sets(lattice, valence_bath)
+    import scipy.linalg as la
+    if kind == 'svd':
+        coupling = rdm1.reshape(ncells * nso, nso)[env][:, gen]
+        u, sigma, _ = la.svd(coupling, full_matrices=False)
+        nbath = kwargs.get("nbath", None)
+        nbath = int(np.count_nonzero(sigma >= tol_bath)) if nbath is None else int(nbath)
+        if np.any(np.abs(sigma[:nbath]) < tol_bath):
+            warnings.warn("Zero singular value exists, \nthis may cause numerical instability.")
+        bath = u[:, :nbath]
+    elif kind == 'eig':
+        occ, vec = la.eigh(lattice.expand(rdm1)[env][:, env])
+        bath = vec[:, (np.abs(occ) > tol_bath) & (np.abs(1.0 - occ) > tol_bath)]
+    elif kind == 'ph':
+        raise NotImplementedError("particle-hole bath (model Hamiltonians) is outside the ab-initio path")
+    else:
+        raise ValueError("get_emb_basis: Unknown kind %s" % kind)
+    return _gso_finish(lattice, np.array(bath), imp, env, env_is_imp, env_is_alpha, orth, kwargs)
+
+
+embBasis = get_emb_basis
 
 
 def transform_trans_inv_k_dev(basis_ka, basis_kb, H_k):

@@ -82,3 +82,48 @@ def get_emb_Ham(lattice, basis, vcor, mu, local=True, int_bath=True, add_vcor=Fa
 
 
 embHam = get_emb_Ham
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GSO bath construction (spinless.py:34-272)
+# ---------------------------------------------------------------------------------------------------------
+def get_emb_basis(lattice, GRho, kind='svd', valence_bath=True, tol_bath=1e-9, nbath=None):
+    """embedding basis (ncells, 2 nlo, nimp + nbath) from the generalised density matrix (ncells, 2 nlo, 2 nlo):
+    bath = left singular vectors of the environment x impurity block ('svd', l.58-162) or the fractionally occupied
+    eigenvectors of the environment block ('eig', l.167-272); impurity rows of the bath zeroed and the bath Loewdin
+    re-orthonormalised; bath columns ordered by decreasing weight on the alpha rows."""
+    import scipy.linalg as la
+    from .slater import vec_lowdin
+    ncells, nlo = lattice.ncells, lattice.nscsites
+    nso = 2 * nlo
+    val_idx = list(lattice.val_idx) + [i + nlo for i in lattice.val_idx]
+    imp_idx = list(lattice.imp_idx) + [i + nlo for i in lattice.imp_idx]
+    generators = val_idx if valence_bath else imp_idx
+    env_idx, virt_mask, alpha_mask = [], [], []
+    for R in range(ncells):
+        for s in range(2):
+            for i in range(nlo):
+                idx = R * nso + s * nlo + i
+                if idx not in generators:
+                    env_idx.append(idx)
+                    virt_mask.append(idx in imp_idx)
+                    alpha_mask.append(s == 0)
+    rdm1 = np.asarray(GRho).real
+    if kind == 'svd':
+        u, sigma, _ = la.svd(rdm1.reshape(ncells * nso, nso)[env_idx][:, generators], full_matrices=False)
+        nbath = int((sigma >= tol_bath).sum()) if nbath is None else nbath
+        B = u[:, :nbath]
+    else:
+        ew, ev = la.eigh(lattice.expand(rdm1)[env_idx][:, env_idx])
+        B = np.asarray([ev[:, i] for i, e in enumerate(ew) if abs(e) > tol_bath and abs(1 - e) > tol_bath]).T
+        nbath = B.shape[-1]
+    assert nbath % 2 == 0
+    B[virt_mask] = 0.0
+    B = vec_lowdin(B)
+    w = np.einsum("ai,ai->i", B[alpha_mask], B[alpha_mask])
+    order = np.argsort(w, kind='mergesort')[::-1]
+    nimp = len(imp_idx)
+    basis = np.zeros((ncells * nso, nimp + nbath))
+    basis[imp_idx, :nimp] = np.eye(nimp)
+    basis[env_idx, nimp:] = B[:, order]
+    return basis.reshape(ncells, nso, nimp + nbath)

@@ -185,6 +185,27 @@ def gen_emb_basis_eig():
     save("emb_basis_eig", **out)
 
 
+def gen_gso_basis():
+    """GSO bath construction through the reference's libdmet.routine.spinless.get_emb_basis (spinless.py:34-272) on
+    the generalised mean-field density matrix of the GSO test lattice"""
+    import libdmet.routine.spinless as ref_spinless
+    import libdmet.system.fourier as ref_f
+    from helpers import GSOLattice
+    out = {}
+    for tag, (kmesh, nao, nval) in {"a": ([1, 1, 3], 3, 2), "b": ([2, 2, 1], 4, 4)}.items():
+        gdf, C, _ = problem(kmesh, nao, 6, 2, spin=2)
+        gdf.cell = GoldenCell(nao)
+        G = GSOLattice(gdf, C, ref_f)
+        GRho = ref_f.k2R(G.rdm1_lo_k, kmesh)
+        Lat = ref_lattice.Lattice(gdf.cell, kmesh)
+        Lat.set_val_virt_core(nval, nao - nval, 0)
+        out["kmesh_" + tag], out["nao_" + tag], out["nval_" + tag], out["GRho_" + tag] = np.array(kmesh), nao, nval, GRho
+        for kind in ("svd", "eig"):
+            out["%s_%s" % (kind, tag)] = ref_spinless.get_emb_basis(Lat, GRho, kind=kind)
+            out["%s_full_%s" % (kind, tag)] = ref_spinless.get_emb_basis(Lat, GRho, kind=kind, valence_bath=False)
+    save("gso_basis", **out)
+
+
 def gen_rho_glob():
     """global density matrix by democratic partitioning through the reference's slater_helper.get_rho_glob_R
     (slater_helper.py:183-270): one fragment (restricted and unrestricted) and two fragments sharing cell 0"""
@@ -334,6 +355,7 @@ def gen_eri_file():
 
 
 if __name__ == "__main__":
+    gen_gso_basis()
     gen_rho_glob()
     gen_emb_basis_eig()
     gen_eri_file()
