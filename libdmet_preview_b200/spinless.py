@@ -259,3 +259,98 @@ def get_emb_Ham(lattice, basis, vcor, mu, local=True, **kwargs):
 
 
 embHam = get_emb_Ham
+
+
+# ---------------------------------------------------------------------------------------------------------
+# energy side of the GSO iteration (spinless.py:754-848, 948-1035)
+# ---------------------------------------------------------------------------------------------------------
+def _so_idx(idx, n):
+    """orbital indices -> (alpha, beta) spin-orbital indices of an n-orbital block (spinless_helper.py:247-259)"""
+    return [int(i) for i in idx], [int(i) + n for i in idx]
+
+
+def transformResults(GRhoEmb, E, lattice, basis, ImpHam, H1e, mu, fit_ghf=False, **kwargs):
+    """spinless.py:754-848: impurity block of the generalised density matrix, fragment energy, electron number
+    (small host matrices, as in slater.transformResults).  E2 = E - <H1> - H0 of the solver is kept; E1 is
+    re-evaluated with the chemical potentials added back, half of JK_core removed and the impurity weights
+    applied."""
+    if fit_ghf:
+        raise NotImplementedError("fit_ghf (several bases) belongs to the correlation-potential fitting")
+    basis = np.asarray(basis)
+    ncells, nso, nbasis = basis.shape
+    nao = nso // 2
+    imp_a, imp_b = _so_idx(lattice.imp_idx, nao)
+    GRhoEmb = np.asarray(GRhoEmb)
+    if GRhoEmb.ndim == 3:                        # density matrices of UHF-type solvers (l.785-791)
+        if GRhoEmb.shape[0] == 1:
+            GRhoEmb = GRhoEmb[0]
+        elif GRhoEmb.shape[0] == 2:
+            GRhoEmb = GRhoEmb.sum(axis=0)
+        else:
+            raise ValueError
+    GRhoImp = basis[0].dot(GRhoEmb).dot(basis[0].conj().T)
+    nelec = GRhoImp[imp_a, imp_a].sum() - GRhoImp[imp_b, imp_b].sum() + len(imp_b)
+    if E is None:
+        return GRhoImp, None, nelec
+    last_dmu = kwargs["last_dmu"]
+    basis_Ra, basis_Rb = separate_basis(basis)
+    H1 = ImpHam.H1["cd"][0]
+    E2 = E - np.einsum("pq,qp->", H1, GRhoEmb) - ImpHam.H0
+    dmu_idx = kwargs.get("dmu_idx", None)
+    dmu_idx = list(lattice.imp_idx) if dmu_idx is None else dmu_idx
+    emb_a, emb_b = _so_idx(kwargs.get("imp_idx", np.arange(lattice.nimp)), lattice.nimp)   # in the embedding basis
+    H1_scaled = np.array(H1, copy=True)
+    mu_mat = np.zeros((2, nao, nao))
+    mu_mat[0][dmu_idx, dmu_idx] = last_dmu       # last_dmu back on the impurity ...
+    mu_mat[1][dmu_idx, dmu_idx] = -last_dmu
+    H1_scaled += transform_imp(basis_Ra, basis_Rb, mu_mat)
+    np.fill_diagonal(mu_mat[0], mu)              # ... and the global mu everywhere (same buffer, as l.829-831)
+    np.fill_diagonal(mu_mat[1], -mu)
+    H1_scaled += transform_local(basis_Ra, basis_Rb, mu_mat)
+    if lattice.JK_core is not None:
+        H1_scaled -= 0.5 * lattice.JK_core
+    H1_scaled = slater.get_H1_scaled(H1_scaled[None], emb_a + emb_b)[0]
+    E1 = np.einsum("pq,qp->", H1_scaled, GRhoEmb)
+    return GRhoImp, E1 + E2 + ImpHam.H0, nelec
+
+
+def get_H_dmet(basis, lattice, ImpHam, last_dmu=None, mu=None, imp_idx=None, dmu_idx=None, add_vcor_to_E=False,
+               vcor=None, compact=True, rdm1_emb=None, veff=None, rebuild_veff=False, E1=None, GV0=None, GV1=None,
+               **kwargs):
+    """spinless.py:948-1035: the GSO DMET Hamiltonian scaled by the number of impurity indices.  One-body part on
+    the device (`transform_trans_inv_k`), two-body weights by `ldm_scale_eri`; the branches that rebuild J/K from a
+    global density matrix through the lattice mean-field object stay with the reference."""
+    if veff is not None or rebuild_veff:
+        raise NotImplementedError("rebuilding JK_core from the global density needs the lattice mean-field object")
+    basis = np.asarray(basis)
+    nbasis = basis.shape[-1]
+    basis_Ra, basis_Rb = separate_basis(basis)
+    basis_k = lattice.R2k_basis(basis)
+    basis_ka, basis_kb = separate_basis(basis_k)
+    emb_a, emb_b = _so_idx(np.arange(lattice.nimp) if imp_idx is None else imp_idx, lattice.nimp)
+    imp = emb_a + emb_b
+    dev = get_device()
+    blocks = slater._s4_blocks_dev(ImpHam.H2["ccdd"], nbasis)                # restore 4-fold symmetry (l.1026)
+    if E1 is None:
+        H1_scaled = transform_trans_inv_k(basis_ka, basis_kb, lattice.getH1(kspace=True))
+        if lattice.JK_core is not None:                                      # double counting cf. the HF energy
+            H1_scaled = H1_scaled + 0.5 * np.asarray(lattice.JK_core)
+        if add_vcor_to_E:
+            H1_scaled = H1_scaled + transform_local(basis_Ra, basis_Rb, vcor.get() * 0.5).real
+            H1_scaled = H1_scaled - transform_imp(basis_Ra, basis_Rb, vcor.get() * 0.5).real
+        if GV1 is not None:
+            H1_scaled = H1_scaled - slater.transform_trans_inv_k(basis_k, GV1)
+        H0 = lattice.getH0()
+    else:                                                                    # E1 given: -(J - K) of the GHF matrix
+        vj, vk = dev.jk_s4(blocks[0], dev.to_device(np.ascontiguousarray(rdm1_emb, dtype=np.float64), torch.float64))
+        H1_scaled = -(vj - vk).cpu().numpy()
+        H0 = float(np.real(E1 + lattice.getH0()))
+    H1_scaled = slater.get_H1_scaled(np.array(H1_scaled, dtype=np.float64)[None], imp)
+    if GV0 is not None:
+        H0 = H0 - GV0 * 0.5
+    H2_dev = slater.get_H2_scaled(torch.stack([blocks[0].clone()]), imp)
+    if compact:
+        H2_scaled = H2_dev.cpu().numpy()
+    else:                                                                    # restore_Ham(.., 1) (l.1032-1034)
+        H2_scaled = dev.restore_s1(H2_dev[0].contiguous(), nbasis).cpu().numpy()[None]
+    return Integral(nbasis, True, False, H0, {"cd": H1_scaled}, {"ccdd": H2_scaled})

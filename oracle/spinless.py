@@ -127,3 +127,66 @@ def get_emb_basis(lattice, GRho, kind='svd', valence_bath=True, tol_bath=1e-9, n
     basis[imp_idx, :nimp] = np.eye(nimp)
     basis[env_idx, nimp:] = B[:, order]
     return basis.reshape(ncells, nso, nimp + nbath)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# energy side of the GSO iteration (spinless.py:754-848, 948-1035)
+# ---------------------------------------------------------------------------------------------------------
+def idx_ao2so(idx, nao):
+    """spinless_helper.py:247-259"""
+    return [i for i in idx], [i + nao for i in idx]
+
+
+def transformResults(GRhoEmb, E, lattice, basis, ImpHam, H1e, mu, **kwargs):
+    """(GRhoImp, Efrag, nelec) of one GSO impurity problem (spinless.py:754-848, fit_ghf=False)"""
+    from .slater import get_H1_scaled
+    ncells, nso, nbasis = basis.shape
+    nao = nso // 2
+    ia, ib = idx_ao2so(lattice.imp_idx, nao)
+    GRhoEmb = np.asarray(GRhoEmb)
+    if GRhoEmb.ndim == 3:
+        GRhoEmb = GRhoEmb[0] if GRhoEmb.shape[0] == 1 else GRhoEmb.sum(axis=0)
+    GRhoImp = basis[0].dot(GRhoEmb).dot(basis[0].conj().T)
+    nelec = GRhoImp[ia, ia].sum() - GRhoImp[ib, ib].sum() + len(ib)
+    if E is None:
+        return GRhoImp, None, nelec
+    last_dmu = kwargs["last_dmu"]
+    Ra, Rb = separate_basis(basis)
+    E2 = E - np.einsum("pq,qp->", ImpHam.H1["cd"][0], GRhoEmb) - ImpHam.H0
+    dmu_idx = kwargs.get("dmu_idx", None)
+    if dmu_idx is None:
+        dmu_idx = lattice.imp_idx
+    ea, eb = idx_ao2so(kwargs.get("imp_idx", np.arange(lattice.nimp)), lattice.nimp)
+    H1_scaled = ImpHam.H1["cd"][0].copy()
+    mu_mat = np.zeros((2, nao, nao))
+    mu_mat[0][dmu_idx, dmu_idx] = last_dmu
+    mu_mat[1][dmu_idx, dmu_idx] = -last_dmu
+    H1_scaled += transform_imp(Ra, Rb, mu_mat)
+    np.fill_diagonal(mu_mat[0], mu)
+    np.fill_diagonal(mu_mat[1], -mu)
+    H1_scaled += transform_local(Ra, Rb, mu_mat)
+    if lattice.JK_core is not None:
+        H1_scaled -= 0.5 * lattice.JK_core
+    H1_scaled = get_H1_scaled(H1_scaled[None], list(ea) + list(eb))[0]
+    E1 = np.einsum("pq,qp->", H1_scaled, GRhoEmb)
+    return GRhoImp, E1 + E2 + ImpHam.H0, nelec
+
+
+def get_H_dmet(basis, lattice, ImpHam, last_dmu=None, mu=None, imp_idx=None, compact=True, **kwargs):
+    """scaled GSO DMET Hamiltonian (spinless.py:948-1035; default branch: E1 from the lattice, JK_core of the last
+    embHam, no vcor / GV terms)"""
+    from .slater import get_H1_scaled, get_H2_scaled
+    from . import pyscf_lib as lib
+    nbasis = basis.shape[-1]
+    basis_k = lattice.R2k_basis(basis)
+    ka, kb = separate_basis(basis_k)
+    ea, eb = idx_ao2so(np.arange(lattice.nimp) if imp_idx is None else imp_idx, lattice.nimp)
+    imp = list(ea) + list(eb)
+    H1 = transform_trans_inv_k(ka, kb, lattice.getH1(kspace=True))
+    H1 = H1 + 0.5 * (lattice.JK_core if lattice.JK_core is not None else 0.0)
+    H1 = get_H1_scaled(np.asarray(H1)[None], imp)
+    H2 = lib.restore(4, np.asarray(ImpHam.H2["ccdd"][0]), nbasis)
+    H2 = get_H2_scaled(np.array(H2)[None], imp)
+    if not compact:
+        H2 = lib.restore(1, H2[0], nbasis)[None]
+    return Integral(nbasis, True, False, lattice.getH0(), {"cd": H1}, {"ccdd": H2})

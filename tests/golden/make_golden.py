@@ -280,9 +280,23 @@ def gen_gso_embham():
         Lat.df = mydf
         basis = gso_basis(kmesh, nao, nemb)
         Ham, _ = ref_spinless.get_emb_Ham(Lat, basis, Vcor(), 0.3)
+        # energy side (spinless.py:754-848, 948-1035)
+        # (sic) with a 4-fold H2 the reference scales ImpHam.H2["ccdd"] IN PLACE here -- `ao2mo.restore(4, ..)` hands
+        # back its input when nothing is to be converted (l.1026-1027) -- so every call gets a fresh copy
+        H2_clean = np.array(Ham.H2["ccdd"])
+        Hd = ref_spinless.get_H_dmet(basis, Lat, Ham, last_dmu=0.1, mu=0.3)
+        Ham.H2["ccdd"] = H2_clean.copy()
+        Hd1 = ref_spinless.get_H_dmet(basis, Lat, Ham, last_dmu=0.1, mu=0.3, compact=False)
+        Ham.H2["ccdd"] = H2_clean.copy()
+        rng = np.random.default_rng(11)
+        GRhoEmb = rng.standard_normal((nemb, nemb))
+        GRhoEmb = GRhoEmb + GRhoEmb.T
+        GRhoImp, Efrag, nelec = ref_spinless.transformResults(GRhoEmb, -2.75, Lat, basis, Ham, None, 0.3,
+                                                              last_dmu=0.1)
         save(name, kmesh=np.array(kmesh), nao=nao, naux=naux, nemb=nemb, sym=sym, gdf_seed=gdf.seed,
              gdf_scale=gdf.scale, C_ao_lo=C, basis=basis, mu=0.3, H1=Ham.H1["cd"], H2=Ham.H2["ccdd"],
-             ovlp=Ham.ovlp, H0=Ham.H0, JK_core=Lat.JK_core)
+             ovlp=Ham.ovlp, H0=Ham.H0, JK_core=Lat.JK_core, Hd_H1=Hd.H1["cd"], Hd_H2=Hd.H2["ccdd"], Hd_H0=Hd.H0,
+             Hd_H2_s1=Hd1.H2["ccdd"], GRhoEmb=GRhoEmb, GRhoImp=GRhoImp, Efrag=Efrag, nelec=nelec)
 
 
 def gen_gdf_lo():

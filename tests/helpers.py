@@ -97,6 +97,10 @@ class GSOLattice(object):
         eye = np.asarray([np.eye(nao, dtype=np.complex128)] * self.nkpts)
         self.ovlp_lo_k = np.asarray((eye, eye, 0 * eye))
         self.rdm1_lo_k = synthetic.make_rdm1_k(synthetic.make_hermitian_k(self.kmesh, 2 * nao, seed=620 + seed), nao)
+        # energy side (get_H_dmet / transformResults): all but the last orbital of cell 0 form the impurity, so that
+        # the embedding space has impurity AND environment spin orbitals and every scaling branch is exercised
+        self.imp_idx = list(range(nao - 1))
+        self.nimp = nao - 1
 
     def R2k_basis(self, basis):
         return self._f.R2k(basis, self.kmesh)

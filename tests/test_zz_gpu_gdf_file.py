@@ -145,3 +145,28 @@ def test_rho_glob_vs_reference_python(dev):
     lats = [lat([1, 1, 3], 5, [0, 1]), lat([1, 1, 3], 5, [2, 3, 4])]
     got = slater.get_rho_glob_R([d["basis_f0"], d["basis_f1"]], lats, [d["rho_f0"], d["rho_f1"]])
     assert np.abs(got - d["glob_f"]).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["gso_embham_113", "gso_embham_221"])
+def test_gso_energy_side_vs_reference_python(dev, name):
+    """GSO get_H_dmet / transformResults (spinless.py:754-848, 948-1035) on the Hamiltonian the device built, against
+    golden results of the reference's own code"""
+    from helpers import GSOLattice
+    from libdmet_preview_b200 import spinless, fourier
+    d = np.load(os.path.join(G, name + ".npz"))
+    gdf = synthetic.SyntheticGDF([int(x) for x in d["kmesh"]], int(d["nao"]), int(d["naux"]), seed=int(d["gdf_seed"]),
+                                 scale=float(d["gdf_scale"]))
+    Lat = GSOLattice(gdf, d["C_ao_lo"], fourier, eri_symmetry=int(d["sym"]))
+    mu = float(d["mu"])
+    Ham, _ = spinless.get_emb_Ham(Lat, d["basis"], None, mu)
+    H2_before = Ham.H2["ccdd"].copy()
+    Hd = spinless.get_H_dmet(d["basis"], Lat, Ham, last_dmu=0.1, mu=mu)
+    assert Hd.H1["cd"].shape == d["Hd_H1"].shape and np.abs(Hd.H1["cd"] - d["Hd_H1"]).max() < TOL
+    assert Hd.H2["ccdd"].shape == d["Hd_H2"].shape and np.abs(Hd.H2["ccdd"] - d["Hd_H2"]).max() < TOL
+    assert Hd.H0 == float(d["Hd_H0"]) and np.array_equal(Ham.H2["ccdd"], H2_before)
+    Hd1 = spinless.get_H_dmet(d["basis"], Lat, Ham, last_dmu=0.1, mu=mu, compact=False)
+    assert Hd1.H2["ccdd"].shape == d["Hd_H2_s1"].shape and np.abs(Hd1.H2["ccdd"] - d["Hd_H2_s1"]).max() < TOL
+    GRhoImp, Efrag, nelec = spinless.transformResults(d["GRhoEmb"], -2.75, Lat, d["basis"], Ham, None, mu,
+                                                      last_dmu=0.1)
+    assert np.abs(GRhoImp - d["GRhoImp"]).max() < TOL and abs(Efrag - float(d["Efrag"])) < 1e-8
+    assert abs(nelec - float(d["nelec"])) < TOL
