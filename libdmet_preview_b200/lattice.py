@@ -183,6 +183,49 @@ class Lattice(object):
             self.vxc_lo_k = add_spin_dim(make_basis.transform_h1_to_lo(self.vxc_ao_k, C), self.spin)
             self.vxc_lo_R = self.k2R(self.vxc_lo_k)
 
+    def update_Ham(self, rdm1_lo_R, veff=None, vhf=None, **kwargs):
+        """lattice.py:565-589 (Knizia's charge self-consistency step): the DMET density matrix replaces the
+        mean-field one, rdm1_lo_R -> rdm1_lo_k -> rdm1_ao_k on the device, and every LO-basis quantity is rebuilt
+        by `set_Ham`.  With `veff` / `vhf` supplied the stored J and K are kept, exactly as in the reference (there
+        `vhf` is then re-formed from the OLD vj, vk -- i.e. it is the stored `vhf_ao_k`); without them J and K have
+        to be rebuilt from the new density by the mean-field object."""
+        self.rdm1_lo_R = rdm1_lo_R
+        self.rdm1_lo_k = self.R2k(self.rdm1_lo_R)
+        self.rdm1_ao_k = make_basis.transform_rdm1_to_ao(self.rdm1_lo_k, self.C_ao_lo)
+        if veff is None and vhf is None:
+            if self.kmf is None:
+                raise ValueError("update_Ham without veff / vhf rebuilds J and K from the new density and needs the "
+                                 "mean-field object (kmf)")
+            vhf_use = None
+        else:
+            vhf_use = self.vhf_ao_k if vhf is None else vhf
+        self.set_Ham(self.kmf, self.df, self.C_ao_lo, self.eri_symmetry, ovlp=self.ovlp_ao_k, hcore=self.hcore_ao_k,
+                     rdm1=self.rdm1_ao_k, fock=None, veff=veff, vhf=vhf_use, vxc=None, H0=self.H0,
+                     use_hcore_as_emb_ham=self.use_hcore_as_emb_ham, hcore_hf_add=self.hcore_hf_add)
+
+    def expand_orb(self, C):
+        """translation-invariant orbitals C[T] ((spin,) ncells, nao, nmo) -> the full supercell coefficient matrix,
+        block (T + R, R) = C[T] (lattice.py:353-377)"""
+        C = np.asarray(C)
+        if C.ndim not in (3, 4):
+            raise ValueError("unknown shape of C, %s" % (C.shape,))
+        assert C.shape[-3] == self.ncells
+        nao, nmo = C.shape[-2:]
+        big = np.zeros(C.shape[:-3] + (self.ncells * nao, self.ncells * nmo), dtype=C.dtype)
+        for i in range(self.ncells):
+            for j in range(self.ncells):
+                r = self.add(i, j)
+                big[..., r * nao:(r + 1) * nao, j * nmo:(j + 1) * nmo] = C[..., i, :, :]
+        return big
+
+    def transpose(self, A):
+        """transpose of a translation-invariant matrix in stripe form: A^T[n] = A[-n]^T (lattice.py:379-397)"""
+        A = np.asarray(A)
+        if A.ndim not in (3, 4):
+            raise ValueError("unknown shape of A, %s" % (A.shape,))
+        minus = [self.cell_pos2idx(-self.cell_idx2pos(n)) for n in range(self.ncells)]
+        return np.ascontiguousarray(np.swapaxes(A[..., minus, :, :], -1, -2))
+
     def update_lo(self, C_ao_lo):
         self.C_ao_lo = np.asarray(C_ao_lo)
         self.transform_obj_to_lo()

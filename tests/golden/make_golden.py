@@ -154,6 +154,30 @@ def gen_embham():
              H0=Ham.H0, norb=Ham.norb)
 
 
+def gen_lattice_misc():
+    """Lattice.update_Ham (lattice.py:565-589) with a supplied HF potential, Lattice.transpose and expand_orb
+    (353-397) through the reference's own Lattice"""
+    out = {}
+    for tag, (kmesh, nao, spin) in {"r": ([1, 2, 2], 4, 1), "u": ([2, 1, 3], 3, 2)}.items():
+        Lat, gdf, C, (hcore, ovlp, vhf, rdm1) = make_ref_lattice(kmesh, nao, 7, 2, spin, 4, "misc_" + tag)
+        rng = np.random.default_rng(17)
+        new_R = Lat.rdm1_lo_R + 0.05 * rng.standard_normal(Lat.rdm1_lo_R.shape)       # "the DMET density matrix"
+        new_vhf = vhf * 1.1
+        out["kmesh_" + tag], out["nao_" + tag], out["spin_" + tag] = np.array(kmesh), nao, spin
+        out["C_" + tag], out["hcore_" + tag], out["ovlp_" + tag] = C, hcore, ovlp
+        out["vhf_" + tag], out["rdm1_" + tag] = vhf, rdm1
+        out["new_R_" + tag], out["new_vhf_" + tag] = new_R, new_vhf
+        out["transpose_" + tag] = Lat.transpose(new_R)
+        out["expand_orb_" + tag] = Lat.expand_orb(new_R)
+        ref_log.verbose = "FATAL"          # k2R of the perturbed matrices warns about imaginary parts
+        Lat.update_Ham(new_R, vhf=new_vhf)
+        ref_log.verbose = "RESULT"
+        for k in ("rdm1_ao_k", "rdm1_lo_k", "rdm1_lo_R", "fock_lo_k", "fock_hf_lo_k", "vhf_lo_R", "veff_lo_k",
+                  "hcore_lo_k"):
+            out["%s_%s" % (k, tag)] = np.asarray(getattr(Lat, k))
+    save("lattice_misc", **out)
+
+
 def gen_emb_basis_hchain():
     """the reference's own fixture libdmet/routine/test/rdm1_lo (H chain 321g, 1x1x3, nval = nvirt = 2;
     test_slater.py:20-54) through the reference's get_emb_basis"""
@@ -369,6 +393,7 @@ def gen_eri_file():
 
 
 if __name__ == "__main__":
+    gen_lattice_misc()
     gen_gso_basis()
     gen_rho_glob()
     gen_emb_basis_eig()

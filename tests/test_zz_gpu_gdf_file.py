@@ -170,3 +170,24 @@ def test_gso_energy_side_vs_reference_python(dev, name):
                                                       last_dmu=0.1)
     assert np.abs(GRhoImp - d["GRhoImp"]).max() < TOL and abs(Efrag - float(d["Efrag"])) < 1e-8
     assert abs(nelec - float(d["nelec"])) < TOL
+
+
+@pytest.mark.parametrize("tag", ["r", "u"])
+def test_update_Ham_vs_reference_python(dev, tag):
+    """Lattice.update_Ham (lattice.py:565-589): DMET density matrix -> k space -> AO basis -> every LO-basis
+    quantity rebuilt, all on the device, against golden results of the reference's own Lattice"""
+    import warnings
+    from libdmet_preview_b200 import lattice as plat
+    d = np.load(os.path.join(G, "lattice_misc.npz"))
+    km, nao = [int(x) for x in d["kmesh_" + tag]], int(d["nao_" + tag])
+    L = plat.Lattice(synthetic.SyntheticCell(nao), km)
+    L.set_Ham(None, None, d["C_" + tag], ovlp=d["ovlp_" + tag], hcore=d["hcore_" + tag], rdm1=d["rdm1_" + tag],
+              vhf=d["vhf_" + tag], H0=1.5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")              # the perturbed density matrix is not exactly real in R space
+        L.update_Ham(d["new_R_" + tag], vhf=d["new_vhf_" + tag])
+    for k in ("rdm1_ao_k", "rdm1_lo_k", "rdm1_lo_R", "fock_lo_k", "fock_hf_lo_k", "vhf_lo_R", "veff_lo_k",
+              "hcore_lo_k"):
+        got, want = np.asarray(getattr(L, k)), d["%s_%s" % (k, tag)]
+        assert got.shape == want.shape and np.abs(got - want).max() < TOL, k
+    assert L.H0 == 1.5 and L.has_Ham
