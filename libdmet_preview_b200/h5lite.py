@@ -19,8 +19,9 @@ files, version-4 layouts, virtual datasets).  Metadata is parsed in Python -- a 
 headers -- while array payloads never pass through Python objects: `Dataset.read_direct` issues `preadv`-style reads
 straight into the caller's (pinned) buffer and `Dataset.memmap` maps contiguous datasets in place.
 
-The writer produces the same flavour of file (superblock 0, symbol-table groups with one B-tree level, contiguous
-little-endian datasets).  It has been checked only against this reader (which in turn is checked against a file
+The writer produces the same flavour of file (superblock 0, symbol-table groups with libhdf5's default node sizes and
+B-trees as deep as the member count needs, contiguous little-endian datasets; chunked / deflate / shuffle and
+variable-length strings on request).  It has been checked only against this reader (which in turn is checked against a file
 written by the real HDF5 library, see tests/test_h5lite.py), not against libhdf5 itself.
 """
 import os
