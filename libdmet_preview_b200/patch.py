@@ -11,10 +11,28 @@ rebinds the names the reference's callers actually resolve (SURVEY.md section 8b
   * `libdmet.basis_transform.make_basis.transform_h1_to_lo / multiply_basis` (looked up through the module at call
     time, lattice.py:609)
   * `libdmet.routine.slater.get_emb_basis / embBasis / get_emb_Ham / embHam`
-Non-GDF density-fitting objects keep going to the reference's own drivers.
-`uninstall()` restores the originals.
+  * `libdmet.routine.slater.get_H_dmet / transformResults / get_rho_glob_R / get_rho_glob_k` (the last two also in
+    `libdmet.routine.slater_helper`, from where `slater` star-imports them)
+  * `libdmet.routine.spinless.get_emb_basis / embBasis / get_emb_Ham / embHam / get_H_dmet / transformResults` and
+    `libdmet.basis_transform.eri_transform.get_emb_eri_gso` (resolved inside `spinless.__embHam2e` at call time)
+Non-GDF density-fitting objects keep going to the reference's own drivers, and every branch this package does not
+mirror (it raises `NotImplementedError` before doing any work of consequence) falls through to the reference's
+function.  `uninstall()` restores the originals.
 """
+import functools
+
 _saved = {}
+
+
+def _with_fallback(ours, ref):
+    """`ours`, except that a branch we do not mirror (NotImplementedError) is served by the reference's function"""
+    @functools.wraps(ours)
+    def call(*args, **kwargs):
+        try:
+            return ours(*args, **kwargs)
+        except NotImplementedError:
+            return ref(*args, **kwargs)
+    return call
 
 
 def _swap(mod, name, new):
@@ -65,8 +83,37 @@ def install():
 
     for n in ("get_emb_basis", "embBasis"):
         _swap(r_sl, n, get_emb_basis)
+    ham = _with_fallback(slater.get_emb_Ham, r_sl.get_emb_Ham)
     for n in ("get_emb_Ham", "embHam"):
-        _swap(r_sl, n, slater.get_emb_Ham)
+        _swap(r_sl, n, ham)
+    # energy side and global density matrix
+    import libdmet.routine.slater_helper as r_slh
+    import libdmet.routine.spinless as r_sp
+    from . import spinless
+    for n in ("get_H_dmet", "transformResults"):
+        _swap(r_sl, n, _with_fallback(getattr(slater, n), getattr(r_sl, n)))
+    for n in ("get_rho_glob_R", "get_rho_glob_k"):
+        f = _with_fallback(getattr(slater, n), getattr(r_slh, n))
+        _swap(r_slh, n, f)
+        _swap(r_sl, n, f)
+    # generalised spin orbitals
+    basis_gso = _with_fallback(spinless.get_emb_basis, r_sp.get_emb_basis)
+    for n in ("get_emb_basis", "embBasis"):
+        _swap(r_sp, n, basis_gso)
+    ham_gso = _with_fallback(spinless.get_emb_Ham, r_sp.get_emb_Ham)
+    for n in ("get_emb_Ham", "embHam"):
+        _swap(r_sp, n, ham_gso)
+    for n in ("get_H_dmet", "transformResults"):
+        _swap(r_sp, n, _with_fallback(getattr(spinless, n), getattr(r_sp, n)))
+    ref_gso = r_eri.get_emb_eri_gso
+
+    def get_emb_eri_gso(cell, mydf, *args, **kwargs):
+        gdf_like = hasattr(mydf, "load") or (isinstance(mydf, pdf.GDF) and not isinstance(mydf, pdf.MDF))
+        if gdf_like and kwargs.get("incore", True):
+            return eri.get_emb_eri_gso(cell, mydf, *args, **kwargs)
+        return ref_gso(cell, mydf, *args, **kwargs)
+
+    _swap(r_eri, "get_emb_eri_gso", get_emb_eri_gso)
     return sorted("%s.%s" % (m.__name__, n) for (m, n) in _saved)
 
 
