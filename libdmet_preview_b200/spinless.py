@@ -294,24 +294,22 @@ def transformResults(GRhoEmb, E, lattice, basis, ImpHam, H1e, mu, fit_ghf=False,
         return GRhoImp, None, nelec
     last_dmu = kwargs["last_dmu"]
     basis_Ra, basis_Rb = separate_basis(basis)
-    H1 = ImpHam.H1["cd"][0]
-    E2 = E - np.einsum("pq,qp->", H1, GRhoEmb) - ImpHam.H0
+    H1 = np.asarray(ImpHam.H1["cd"][0])
+    E2 = E - np.sum(H1 * GRhoEmb.T) - ImpHam.H0
     dmu_idx = kwargs.get("dmu_idx", None)
-    dmu_idx = list(lattice.imp_idx) if dmu_idx is None else dmu_idx
+    dmu_idx = list(lattice.imp_idx) if dmu_idx is None else list(dmu_idx)
     emb_a, emb_b = _so_idx(kwargs.get("imp_idx", np.arange(lattice.nimp)), lattice.nimp)   # in the embedding basis
-    H1_scaled = np.array(H1, copy=True)
-    mu_mat = np.zeros((2, nao, nao))
-    mu_mat[0][dmu_idx, dmu_idx] = last_dmu       # last_dmu back on the impurity ...
-    mu_mat[1][dmu_idx, dmu_idx] = -last_dmu
-    H1_scaled += transform_imp(basis_Ra, basis_Rb, mu_mat)
-    np.fill_diagonal(mu_mat[0], mu)              # ... and the global mu everywhere (same buffer, as l.829-831)
-    np.fill_diagonal(mu_mat[1], -mu)
-    H1_scaled += transform_local(basis_Ra, basis_Rb, mu_mat)
+    # the chemical potentials the solver saw are put back: last_dmu on the chosen orbitals of cell 0, the global mu
+    # on all orbitals of all cells, with opposite signs for the alpha and beta flavours (l.820-833)
+    on_imp = np.zeros((2, nao, nao))
+    on_imp[0][dmu_idx, dmu_idx] = last_dmu
+    on_imp[1][dmu_idx, dmu_idx] = -last_dmu
+    everywhere = np.asarray([mu * np.eye(nao), -mu * np.eye(nao)])
+    H1_scaled = H1 + transform_imp(basis_Ra, basis_Rb, on_imp) + transform_local(basis_Ra, basis_Rb, everywhere)
     if lattice.JK_core is not None:
-        H1_scaled -= 0.5 * lattice.JK_core
-    H1_scaled = slater.get_H1_scaled(H1_scaled[None], emb_a + emb_b)[0]
-    E1 = np.einsum("pq,qp->", H1_scaled, GRhoEmb)
-    return GRhoImp, E1 + E2 + ImpHam.H0, nelec
+        H1_scaled = H1_scaled - 0.5 * np.asarray(lattice.JK_core)
+    H1_scaled = slater.get_H1_scaled(np.array(H1_scaled, dtype=np.float64)[None], emb_a + emb_b)[0]
+    return GRhoImp, np.sum(H1_scaled * GRhoEmb.T) + E2 + ImpHam.H0, nelec
 
 
 def get_H_dmet(basis, lattice, ImpHam, last_dmu=None, mu=None, imp_idx=None, dmu_idx=None, add_vcor_to_E=False,

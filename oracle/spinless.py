@@ -96,18 +96,13 @@ def get_emb_basis(lattice, GRho, kind='svd', valence_bath=True, tol_bath=1e-9, n
     from .slater import vec_lowdin
     ncells, nlo = lattice.ncells, lattice.nscsites
     nso = 2 * nlo
-    val_idx = list(lattice.val_idx) + [i + nlo for i in lattice.val_idx]
-    imp_idx = list(lattice.imp_idx) + [i + nlo for i in lattice.imp_idx]
-    generators = val_idx if valence_bath else imp_idx
-    env_idx, virt_mask, alpha_mask = [], [], []
-    for R in range(ncells):
-        for s in range(2):
-            for i in range(nlo):
-                idx = R * nso + s * nlo + i
-                if idx not in generators:
-                    env_idx.append(idx)
-                    virt_mask.append(idx in imp_idx)
-                    alpha_mask.append(s == 0)
+    two_spins = lambda orbs: np.concatenate([np.asarray(orbs, dtype=int), np.asarray(orbs, dtype=int) + nlo])  # noqa
+    imp_idx = two_spins(lattice.imp_idx)
+    generators = two_spins(lattice.val_idx) if valence_bath else imp_idx
+    every = np.arange(ncells * nso)                      # spin orbital R * nso + s * nlo + i, in increasing order
+    env_idx = every[~np.isin(every, generators)]
+    virt_mask = np.isin(env_idx, imp_idx)                # impurity (virtual) spin orbitals left in the environment
+    alpha_mask = (env_idx % nso) < nlo                   # s == 0 half of every cell
     rdm1 = np.asarray(GRho).real
     if kind == 'svd':
         u, sigma, _ = la.svd(rdm1.reshape(ncells * nso, nso)[env_idx][:, generators], full_matrices=False)
@@ -150,26 +145,23 @@ def transformResults(GRhoEmb, E, lattice, basis, ImpHam, H1e, mu, **kwargs):
     nelec = GRhoImp[ia, ia].sum() - GRhoImp[ib, ib].sum() + len(ib)
     if E is None:
         return GRhoImp, None, nelec
-    last_dmu = kwargs["last_dmu"]
     Ra, Rb = separate_basis(basis)
-    E2 = E - np.einsum("pq,qp->", ImpHam.H1["cd"][0], GRhoEmb) - ImpHam.H0
-    dmu_idx = kwargs.get("dmu_idx", None)
-    if dmu_idx is None:
-        dmu_idx = lattice.imp_idx
+    H1 = np.asarray(ImpHam.H1["cd"][0])
+    E2 = E - np.sum(H1 * GRhoEmb.T) - ImpHam.H0                       # two-body part of the solver energy
+    where = kwargs.get("dmu_idx", None)
+    where = list(lattice.imp_idx) if where is None else list(where)
     ea, eb = idx_ao2so(kwargs.get("imp_idx", np.arange(lattice.nimp)), lattice.nimp)
-    H1_scaled = ImpHam.H1["cd"][0].copy()
-    mu_mat = np.zeros((2, nao, nao))
-    mu_mat[0][dmu_idx, dmu_idx] = last_dmu
-    mu_mat[1][dmu_idx, dmu_idx] = -last_dmu
-    H1_scaled += transform_imp(Ra, Rb, mu_mat)
-    np.fill_diagonal(mu_mat[0], mu)
-    np.fill_diagonal(mu_mat[1], -mu)
-    H1_scaled += transform_local(Ra, Rb, mu_mat)
+    # chemical potentials go back in: last_dmu on the chosen cell-0 orbitals only, mu on every orbital of every cell;
+    # opposite signs for the two spin flavours (the reference reuses one buffer and overwrites its whole diagonal)
+    local = np.zeros((2, nao, nao))
+    local[0][where, where] = kwargs["last_dmu"]
+    local[1][where, where] = -kwargs["last_dmu"]
+    everywhere = np.asarray([np.eye(nao) * mu, np.eye(nao) * (-mu)])
+    H1_eff = H1 + transform_imp(Ra, Rb, local) + transform_local(Ra, Rb, everywhere)
     if lattice.JK_core is not None:
-        H1_scaled -= 0.5 * lattice.JK_core
-    H1_scaled = get_H1_scaled(H1_scaled[None], list(ea) + list(eb))[0]
-    E1 = np.einsum("pq,qp->", H1_scaled, GRhoEmb)
-    return GRhoImp, E1 + E2 + ImpHam.H0, nelec
+        H1_eff = H1_eff - 0.5 * lattice.JK_core
+    H1_eff = get_H1_scaled(np.array(H1_eff)[None], list(ea) + list(eb))[0]
+    return GRhoImp, np.sum(H1_eff * GRhoEmb.T) + E2 + ImpHam.H0, nelec
 
 
 def get_H_dmet(basis, lattice, ImpHam, last_dmu=None, mu=None, imp_idx=None, compact=True, **kwargs):
