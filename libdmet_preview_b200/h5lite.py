@@ -208,16 +208,19 @@ class Dataset(_Node):
         self.shape, self.dtype = None, None
         self._layout = None
         self._filters = []
-        for mtype, body in msgs:
-            c = _Cur(body)
-            if mtype == 0x01:
-                self.shape = self._dataspace(c)
-            elif mtype == 0x03:
-                self.dtype = _parse_dtype(c)
-            elif mtype == 0x08:
-                self._layout = self._parse_layout(c)
-            elif mtype == 0x0B:
-                self._filters = self._parse_filters(c)
+        try:
+            for mtype, body in msgs:
+                c = _Cur(body)
+                if mtype == 0x01:
+                    self.shape = self._dataspace(c)
+                elif mtype == 0x03:
+                    self.dtype = _parse_dtype(c)
+                elif mtype == 0x08:
+                    self._layout = self._parse_layout(c)
+                elif mtype == 0x0B:
+                    self._filters = self._parse_filters(c)
+        except (ValueError, TypeError, IndexError, OverflowError) as e:      # nonsense in a header message
+            raise H5FormatError("%s: malformed dataset header (%s)" % (name, e))
         if self.shape is None or self.dtype is None or self._layout is None:
             raise H5FormatError("%s: incomplete dataset header" % name)
 
@@ -294,7 +297,10 @@ class Dataset(_Node):
     # -- data access -------------------------------------------------------------------------------
     @property
     def size(self):
-        return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+        n = 1
+        for s in self.shape:
+            n *= int(s)
+        return n
 
     @property
     def nbytes(self):
@@ -357,18 +363,21 @@ class Dataset(_Node):
         esz = self.dtype.itemsize
         for offs, nbytes, mask, caddr in self.file._chunk_leaves(addr, len(self.shape)):
             raw = self.file._pread(self.file._base + caddr, nbytes)
-            for n, (fid, cd) in reversed(list(enumerate(self._filters))):
-                if mask >> n & 1:
-                    continue
-                if fid == 1:
-                    raw = zlib.decompress(raw)
-                elif fid == 2:
-                    a = np.frombuffer(raw, np.uint8)
-                    k = len(a) // esz
-                    raw = a[:k * esz].reshape(esz, k).T.tobytes() + a[k * esz:].tobytes()
-                elif fid == 3:
-                    raw = raw[:-4]
-            blk = np.frombuffer(raw, self.dtype, count=int(np.prod(chunk))).reshape(chunk)
+            try:
+                for n, (fid, cd) in reversed(list(enumerate(self._filters))):
+                    if mask >> n & 1:
+                        continue
+                    if fid == 1:
+                        raw = zlib.decompress(raw)
+                    elif fid == 2:
+                        a = np.frombuffer(raw, np.uint8)
+                        k = len(a) // esz
+                        raw = a[:k * esz].reshape(esz, k).T.tobytes() + a[k * esz:].tobytes()
+                    elif fid == 3:
+                        raw = raw[:-4]
+                blk = np.frombuffer(raw, self.dtype, count=int(np.prod(chunk))).reshape(chunk)
+            except (zlib.error, ValueError) as err:
+                raise H5FormatError("%s: corrupt chunk at %s (%s)" % (self.name, offs, err))
             sel_out = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, chunk, self.shape))
             sel_blk = tuple(slice(0, s.stop - s.start) for s in sel_out)
             out[sel_out] = blk[sel_blk]
@@ -387,10 +396,19 @@ class Dataset(_Node):
         for n in range(self.size):
             c = _Cur(raw[n * esz:(n + 1) * esz].tobytes())
             length, coll, idx = c.u(4), c.u(f._O), c.u(4)
-            out[n] = f._global_heap_object(coll, idx)[:length].decode("utf-8") if length else ""
+            out[n] = f._global_heap_object(coll, idx)[:length].decode("utf-8", errors="replace") if length else ""
         return out.reshape(self.shape)
 
+    def _check_extent(self):
+        """a contiguous dataset cannot be larger than the file that holds it (guards allocations on corrupt headers)"""
+        kind, addr, _ = self._layout
+        if kind == "contiguous" and addr != self.file._undef and self.file._base + addr + self.nbytes > self.file._size:
+            raise H5FormatError("%s: %d bytes at offset %d do not fit the file" % (self.name, self.nbytes, addr))
+        if kind == "compact" and self.nbytes > len(addr):
+            raise H5FormatError("%s: compact payload shorter than the dataspace" % self.name)
+
     def __getitem__(self, key):
+        self._check_extent()
         if self.dtype.metadata and "vlen_str_bytes" in self.dtype.metadata:
             out = self._read_vlen_str()
             return out[()] if key == () or key is Ellipsis else out[key]
@@ -430,8 +448,11 @@ class Group(_Node):
             heap_data = f._local_heap(self._heap)
             links = {}
             for name_off, obj_addr in f._group_leaves(self._btree):
-                e = heap_data.index(b"\0", name_off)
-                links[heap_data[name_off:e].decode()] = obj_addr
+                try:
+                    e = heap_data.index(b"\0", name_off)
+                    links[heap_data[name_off:e].decode()] = obj_addr
+                except ValueError as err:                   # name offset outside the heap / not a string
+                    raise H5FormatError("%s: corrupt link name in group %s (%s)" % (f._path, self.name, err))
             self._links = links
         return self._links
 
@@ -452,6 +473,8 @@ class Group(_Node):
             return False
 
     def __getitem__(self, path):
+        if not isinstance(path, str):
+            raise KeyError("%r: groups are indexed by member names" % (path,))
         node = self
         if path.startswith("/"):
             node = self.file._root
@@ -477,6 +500,7 @@ class File(Group):
             raise ValueError("h5lite.File is read-only; use h5lite.Writer to create files")
         self._path = path
         self._fd = os.open(path, os.O_RDONLY)
+        self._size = os.fstat(self._fd).st_size
         try:
             self._superblock()
         except Exception:
@@ -509,6 +533,9 @@ class File(Group):
             pass
 
     def _pread(self, off, n):
+        if off < 0 or n < 0 or off + n > self._size:      # corrupt address / length: fail before allocating
+            raise H5FormatError("%s: read of %d bytes at offset %d beyond the end of the file (%d bytes)"
+                                % (self._path, n, off, self._size))
         out = bytearray(n)
         self._pread_into(memoryview(out), off)
         return bytes(out)
@@ -517,6 +544,9 @@ class File(Group):
         """fill the writable byte view `buf` from file offset `off` (large reads are split: one preadv call moves
         at most 2 GiB on Linux)"""
         done, n = 0, buf.nbytes
+        if off < 0 or off + n > self._size:
+            raise H5FormatError("%s: read of %d bytes at offset %d beyond the end of the file (%d bytes)"
+                                % (self._path, n, off, self._size))
         while done < n:
             got = os.preadv(self._fd, [buf[done:min(n, done + (1 << 30))]], off + done)
             if got <= 0:

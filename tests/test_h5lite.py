@@ -199,3 +199,38 @@ def test_header_continuation_blocks(tmp_path):
     open(q, "wb").write(bytes(raw))
     with h5lite.File(q) as f:
         assert np.array_equal(f["x"][...], a)
+
+
+def test_corrupt_files_fail_cleanly(tmp_path):
+    """random byte flips and truncations: every outcome is a clean read, a KeyError (a damaged name no longer
+    matches) or H5FormatError -- no hang, no giant allocation from a corrupt length field"""
+    import random
+    p = str(tmp_path / "a.h5")
+    with h5lite.Writer(p) as w:
+        for k in range(40):
+            w["j3c/%d/0" % k] = np.arange(6.0).reshape(2, 3) + k
+        w["j3c-kptij"] = np.zeros((40, 2, 3))
+        w.create_dataset("c", np.arange(100.0).reshape(10, 10), chunks=(4, 4), compression="gzip")
+    raw = open(p, "rb").read()
+    rnd = random.Random(1)
+    q = str(tmp_path / "f.h5")
+    outcomes = set()
+    for trial in range(300):
+        b = bytearray(raw)
+        if trial % 3 == 0:
+            b = b[:rnd.randrange(8, len(b))]
+        else:
+            for _ in range(rnd.randrange(1, 6)):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        with open(q, "wb") as fh:
+            fh.write(bytes(b))
+        try:
+            with h5lite.File(q) as f:
+                for k in f["j3c"].keys():
+                    f["j3c"][k]["0"][...]
+                f["j3c-kptij"][...]
+                f["c"][...]
+            outcomes.add("ok")
+        except (h5lite.H5FormatError, KeyError) as e:
+            outcomes.add(type(e).__name__)
+    assert outcomes <= {"ok", "H5FormatError", "KeyError"} and "H5FormatError" in outcomes
