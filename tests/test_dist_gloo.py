@@ -25,7 +25,7 @@ class SlicedProvider(object):
         return self.p.load(ki, kj)[self.l0:self.l1]
 
 
-def _worker(rank, world, port, nsplit, out):
+def _worker(rank, world, port, nsplit, out, cderi=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -33,6 +33,12 @@ def _worker(rank, world, port, nsplit, out):
         from libdmet_preview_b200.schedule import build_schedule
         from oracle import eri_transform as oe
         gdf, C, basis = problem([1, 2, 3], 5, 12, 6)
+        if cderi is not None:          # every rank opens the same cderi file and reads only the blocks of its items
+            from libdmet_preview_b200.gdf_file import GDFFile
+            mem, gdf = gdf, GDFFile(cderi, cell=gdf.cell, kpts=gdf.kpts)
+            loads = []
+            inner = gdf.load
+            gdf.load = lambda ki, kj, out=None: (loads.append((ki, kj)), inner(ki, kj, out))[1]
         sch = build_schedule(gdf.kpts_scaled, True)
 
         def compute(items):
@@ -51,6 +57,9 @@ def _worker(rank, world, port, nsplit, out):
         items = ldist.rank_items(sch, gdf.nao, gdf.naux, 6, 1, world, nsplit)
         flat = sorted(i for p in items for i in p)
         assert len(flat) == len(set(flat)) == len(sch.units) * (nsplit or 1) or nsplit is None
+        if cderi is not None and rank == 1:          # this rank touched only the pairs of its own work items
+            mine = {(ki, kj) for (u, _, _) in items[1] for (ki, kj, _) in sch.units[u][2]}
+            assert set(loads) == mine and len(mine) < sch.nblocks
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -65,6 +74,27 @@ def test_two_ranks_equal_serial(nsplit):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, nsplit, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) < 1e-10
+
+
+def test_two_ranks_read_one_cderi_file(tmp_path):
+    """the sharded build over a GDF tensor on disk: both ranks open the same PySCF-layout file (gdf_file.GDFFile) and
+    each reads only the (k_i, k_j) pairs of its own work items"""
+    from libdmet_preview_b200.gdf_file import write_gdf_file
+    gdf, _, _ = problem([1, 2, 3], 5, 12, 6)
+    cderi = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, nsegments=2)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1, out, cderi)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
