@@ -40,7 +40,8 @@ class StoredEntry(object):
         self.data, self.flags = data, flags
 
     def expand(self, naux, nao):
-        """host twin of `ldm_unpack_stored` (tests, and providers without a device): (naux, nao, nao) complex128"""
+        """what `ldm_unpack_stored` produces from this entry, (naux, nao, nao) complex128 -- layout only, used by the
+        tests to check the device kernel and the stored-entry bookkeeping"""
         out = np.zeros((naux, nao, nao), dtype=np.complex128)
         a = self.data
         rows = a.shape[0]
