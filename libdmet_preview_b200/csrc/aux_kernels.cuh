@@ -90,21 +90,40 @@ struct DftTables {
     double2 w[3][64];     // w[d][k * n_d + r] = exp(-+ 2 pi i k r / n_d), filled on the host
 };
 
-// one n-point DFT over a line held in registers
+// one n-point DFT over a line held in registers.  Lines of 2 and 4 points (the common meshes: 2x2x2 ... 4x4x4) are
+// butterflies of additions only -- their twiddles are 1, -1, -+i -- so the kernel stays bound by HBM also for the
+// real-input / real-output variants, which move 24 instead of 32 bytes per element; other lengths are a dense sum.
 template <int ND>
 __device__ __forceinline__ void dft_line(double2 (&v)[ND], const double2* __restrict__ tw, double2 (&o)[ND]) {
+    if constexpr (ND == 1) {
+        o[0] = v[0];
+    } else if constexpr (ND == 2) {
+        o[0] = make_double2(v[0].x + v[1].x, v[0].y + v[1].y);
+        o[1] = make_double2(v[0].x - v[1].x, v[0].y - v[1].y);
+    } else if constexpr (ND == 4) {
+        const double s = tw[ND + 1].y;            // w = exp(-+ 2 pi i / 4) = (0, s), s = -1 (R -> k) or +1 (k -> R)
+        const double2 t0 = make_double2(v[0].x + v[2].x, v[0].y + v[2].y);
+        const double2 t1 = make_double2(v[0].x - v[2].x, v[0].y - v[2].y);
+        const double2 t2 = make_double2(v[1].x + v[3].x, v[1].y + v[3].y);
+        const double2 t3 = make_double2(s * (v[3].y - v[1].y), s * (v[1].x - v[3].x));      // w * (v1 - v3)
+        o[0] = make_double2(t0.x + t2.x, t0.y + t2.y);
+        o[2] = make_double2(t0.x - t2.x, t0.y - t2.y);
+        o[1] = make_double2(t1.x + t3.x, t1.y + t3.y);
+        o[3] = make_double2(t1.x - t3.x, t1.y - t3.y);
+    } else {
 #pragma unroll
-    for (int k = 0; k < ND; ++k) {
-        double re = 0.0, im = 0.0;
+        for (int k = 0; k < ND; ++k) {
+            double re = 0.0, im = 0.0;
 #pragma unroll
-        for (int r = 0; r < ND; ++r) {
-            const double2 w = tw[k * ND + r];
-            re = fma(w.x, v[r].x, re);
-            re = fma(-w.y, v[r].y, re);
-            im = fma(w.x, v[r].y, im);
-            im = fma(w.y, v[r].x, im);
+            for (int r = 0; r < ND; ++r) {
+                const double2 w = tw[k * ND + r];
+                re = fma(w.x, v[r].x, re);
+                re = fma(-w.y, v[r].y, re);
+                im = fma(w.x, v[r].y, im);
+                im = fma(w.y, v[r].x, im);
+            }
+            o[k] = make_double2(re, im);
         }
-        o[k] = make_double2(re, im);
     }
 }
 
@@ -350,57 +369,80 @@ __global__ void d2z_kernel(const double* __restrict__ in, double2* __restrict__ 
 //   S_pln [L][n][m]  : sum over the blocks it does not, stored transposed, S_pln[L][n][m] = T[L][m][n]
 //   Lambda[L, tri(m,n)] = S_sym[L][m][n] + S_sym[L][n][m] + S_pln[L][n][m]     (m >= n; pack_tril, l.375)
 // Output goes K-contiguous for the stage-3 GEMM:  XT[P][col_re + L] = Re Lambda, XT[P][col_im + L] = Im Lambda.
-// One CTA handles a 16x16 (m, n) tile for 16 consecutive L: reads are 256-byte rows, writes are 128-byte rows.
+// One CTA handles a 16x16 (m, n) tile (n-tile <= m-tile only: the grid's x index runs over those pairs) for 16
+// consecutive L: reads are 256-byte rows, writes are 128-byte rows.  The loads of 4 consecutive L are issued together
+// (12 independent 16-byte loads per thread in flight, two CTAs per SM) and each batch costs one barrier: after it,
+// thread (tx, ty) is the only one that touches element [l][tx][ty].
 // ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <bool GSO>
+__global__ void __launch_bounds__(256, 2)
 pack_sym_kernel(const double2* __restrict__ S_sym, const double2* __restrict__ S_pln,
                 const double2* __restrict__ S_sym2, const double2* __restrict__ S_pln2, double* __restrict__ XT,
                 int naux, int neo, long long ldx, long long col_re, long long col_im) {
-    // the optional second set (S_sym2, S_pln2) is SUBTRACTED: Lambda_a - Lambda_b of the generalised-spin-orbital
-    // (GSO) embedding ERI (reference: _Lij_s4_to_eri_gso, eri_transform.py:1252-1284, whose four signed Gram
+    // GSO: the second set (S_sym2, S_pln2) is SUBTRACTED: Lambda_a - Lambda_b of the generalised-spin-orbital
+    // embedding ERI (reference: _Lij_s4_to_eri_gso, eri_transform.py:1252-1284, whose four signed Gram
     // products equal one Gram product of the difference)
     extern __shared__ double2 v_raw[];
     double2 (*v)[16][17] = reinterpret_cast<double2 (*)[16][17]>(v_raw);   // [L][m][n]
-    const int tm = blockIdx.x, tn = blockIdx.y;
-    if (tn > tm) return;
-    const int L0 = blockIdx.z * 16;
+    int tm = (int)((sqrtf(8.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
+    while ((tm + 1) * (tm + 2) / 2 <= (int)blockIdx.x) ++tm;
+    while (tm * (tm + 1) / 2 > (int)blockIdx.x) --tm;
+    const int tn = (int)blockIdx.x - tm * (tm + 1) / 2;
+    const int L0 = blockIdx.y * 16;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const size_t n2 = (size_t)neo * neo;
-    for (int l = 0; l < 16; ++l) {
-        const int L = L0 + l;
-        const int m = tm * 16 + ty, n = tn * 16 + tx;      // contiguous reads along n:  S[L][m][n]
-        const int m2 = tm * 16 + tx, n2i = tn * 16 + ty;    // contiguous reads along m:  S[L][n][m]
-        double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
-        if (L < naux) {
-            const size_t o1 = (size_t)L * n2 + (size_t)m * neo + n;
-            const size_t o2 = (size_t)L * n2 + (size_t)n2i * neo + m2;
-            if (m < neo && n < neo) {
-                if (S_sym) { const double2 q = S_sym[o1]; a.x += q.x; a.y += q.y; }
-                if (S_sym2) { const double2 q = S_sym2[o1]; a.x -= q.x; a.y -= q.y; }
-            }
-            if (m2 < neo && n2i < neo) {
-                if (S_sym) { const double2 q = S_sym[o2]; b.x += q.x; b.y += q.y; }
-                if (S_pln) { const double2 q = S_pln[o2]; b.x += q.x; b.y += q.y; }
-                if (S_sym2) { const double2 q = S_sym2[o2]; b.x -= q.x; b.y -= q.y; }
-                if (S_pln2) { const double2 q = S_pln2[o2]; b.x -= q.x; b.y -= q.y; }
+    const int m = tm * 16 + ty, n = tn * 16 + tx;      // contiguous reads along n:  S[L][m][n]
+    const int m2 = tm * 16 + tx, n2i = tn * 16 + ty;    // contiguous reads along m:  S[L][n][m]
+    const bool in1 = m < neo && n < neo, in2 = m2 < neo && n2i < neo;
+    const size_t o1 = (size_t)m * neo + n, o2 = (size_t)n2i * neo + m2;
+    const double2 zero = make_double2(0.0, 0.0);
+    constexpr int LB = 4;
+#pragma unroll 1
+    for (int lb = 0; lb < 16; lb += LB) {
+        double2 a1[LB], b1[LB], b2[LB], a2[GSO ? LB : 1], b3[GSO ? LB : 1], b4[GSO ? LB : 1];
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const bool ok = L0 + lb + l < naux;
+            const size_t base = (size_t)(L0 + lb + l) * n2;
+            a1[l] = (ok && in1 && S_sym) ? S_sym[base + o1] : zero;
+            b1[l] = (ok && in2 && S_sym) ? S_sym[base + o2] : zero;
+            b2[l] = (ok && in2 && S_pln) ? S_pln[base + o2] : zero;
+            if constexpr (GSO) {
+                a2[l] = (ok && in1 && S_sym2) ? S_sym2[base + o1] : zero;
+                b3[l] = (ok && in2 && S_sym2) ? S_sym2[base + o2] : zero;
+                b4[l] = (ok && in2 && S_pln2) ? S_pln2[base + o2] : zero;
             }
         }
-        v[l][ty][tx] = a;                 // (m = ty, n = tx)
+        double2 bs[LB];
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            double2 a = a1[l];
+            bs[l] = make_double2(b1[l].x + b2[l].x, b1[l].y + b2[l].y);
+            if constexpr (GSO) {
+                a.x -= a2[l].x;
+                a.y -= a2[l].y;
+                bs[l].x -= b3[l].x + b4[l].x;
+                bs[l].y -= b3[l].y + b4[l].y;
+            }
+            v[lb + l][ty][tx] = a;            // (m = ty, n = tx)
+        }
         __syncthreads();
-        double2 acc = v[l][tx][ty];       // element (m = tx, n = ty), whose transposed-read part is this thread's b
-        __syncthreads();
-        acc.x += b.x;
-        acc.y += b.y;
-        v[l][tx][ty] = acc;
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            double2 acc = v[lb + l][tx][ty];  // element (m = tx, n = ty), whose transposed-read part is this thread's b
+            acc.x += bs[l].x;
+            acc.y += bs[l].y;
+            v[lb + l][tx][ty] = acc;
+        }
     }
     __syncthreads();
     // write: 16 pairs per pass, 16 L each (128-byte rows of XT)
     const int l = threadIdx.x & 15;
     for (int pp = threadIdx.x >> 4; pp < 256; pp += 16) {
         const int mi = pp >> 4, ni = pp & 15;
-        const int m = tm * 16 + mi, n = tn * 16 + ni;
-        if (m >= neo || n > m || L0 + l >= naux) continue;
-        const long long P = (long long)m * (m + 1) / 2 + n;
+        const int mm = tm * 16 + mi, nn = tn * 16 + ni;
+        if (mm >= neo || nn > mm || L0 + l >= naux) continue;
+        const long long P = (long long)mm * (mm + 1) / 2 + nn;
         const double2 val = v[l][mi][ni];
         XT[P * ldx + col_re + L0 + l] = val.x;
         if (col_im >= 0) XT[P * ldx + col_im + L0 + l] = val.y;
@@ -419,20 +461,39 @@ __global__ void fill_cols_kernel(double* __restrict__ XT, long long rows, long l
 // eri[P][Q] = eri[Q][P] for Q > P : fills the upper triangle from the lower one (the reference's lib.dot
 // produces both, eri_transform.py:455-459).
 // ----------------------------------------------------------------------------------------------------------
+// One CTA per 64x64 tile on or below the diagonal (1-D grid over the nt(nt+1)/2 such tiles, no idle CTAs); 16 words
+// per thread in flight, 512-byte row segments on both sides, transposition through a padded shared-memory tile.
+constexpr int MIRROR_T = 64;
 __global__ void __launch_bounds__(256)
 mirror_lower_kernel(double* __restrict__ E, int n, long long ld) {
-    __shared__ double tile[32][33];
-    const int tp = blockIdx.y, tq = blockIdx.x;   // source tile (rows tp, cols tq), tq <= tp
-    if (tq > tp) return;
-    for (int dy = threadIdx.y; dy < 32; dy += 8) {
-        const int r = tp * 32 + dy, c = tq * 32 + threadIdx.x;
-        if (r < n && c < n) tile[dy][threadIdx.x] = E[(long long)r * ld + c];
-    }
+    __shared__ double tile[MIRROR_T][MIRROR_T + 1];
+    // tile (tp, tq), tq <= tp, from the linear index
+    const long long t = blockIdx.x;
+    int tp = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)(tp + 1) * (tp + 2) / 2 <= t) ++tp;
+    while ((long long)tp * (tp + 1) / 2 > t) --tp;
+    const int tq = (int)(t - (long long)tp * (tp + 1) / 2);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double v[2 * MIRROR_T / 8];
+#pragma unroll
+    for (int i = 0; i < MIRROR_T / 8; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = tp * MIRROR_T + ty + 8 * i, c = tq * MIRROR_T + tx + 32 * h;
+            v[2 * i + h] = (r < n && c < n) ? E[(long long)r * ld + c] : 0.0;
+        }
+#pragma unroll
+    for (int i = 0; i < MIRROR_T / 8; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) tile[ty + 8 * i][tx + 32 * h] = v[2 * i + h];
     __syncthreads();
-    for (int dy = threadIdx.y; dy < 32; dy += 8) {
-        const int r = tq * 32 + dy, c = tp * 32 + threadIdx.x;   // destination (rows tq, cols tp)
-        if (r < n && c < n && c > r) E[(long long)r * ld + c] = tile[threadIdx.x][dy];
-    }
+#pragma unroll
+    for (int i = 0; i < MIRROR_T / 8; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = tq * MIRROR_T + ty + 8 * i, c = tp * MIRROR_T + tx + 32 * h;   // destination (rows tq, cols tp)
+            if (r < n && c < n && c > r) E[(long long)r * ld + c] = tile[tx + 32 * h][ty + 8 * i];
+        }
 }
 
 // ----------------------------------------------------------------------------------------------------------

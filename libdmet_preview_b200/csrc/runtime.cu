@@ -212,8 +212,10 @@ static int ensure_attrs(ldm_handle h) {
                                      210 * 1024));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_bulk_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      210 * 1024));
-    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)pack_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     16 * 16 * 17 * 16));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)pack_sym_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 16 * 17 * 16));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)pack_sym_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 16 * 17 * 16));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)restore_s1_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     h->attrs_set = true;
@@ -462,8 +464,8 @@ int ldm_dgemm_tn(ldm_handle h, void* stream, const double* A_d, int64_t lda, con
 
 int ldm_mirror_lower(ldm_handle h, void* stream, double* C_d, int n, int64_t ldc) {
     LDM_CUDA_OK(cudaSetDevice(h->device));
-    int t = (n + 31) / 32;
-    mirror_lower_kernel<<<dim3(t, t), dim3(32, 8), 0, (cudaStream_t)stream>>>(C_d, n, ldc);
+    const long long t = (n + MIRROR_T - 1) / MIRROR_T;
+    mirror_lower_kernel<<<(unsigned)(t * (t + 1) / 2), 256, 0, (cudaStream_t)stream>>>(C_d, n, ldc);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -919,27 +921,9 @@ static int flush_panel(ldm_handle h) {
 
 extern "C" {
 
-int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int neo, int nspin, const void* CT_d,
-                  double* eri_d, int max_group, int kl_group) {
-    LDM_REQUIRE(h && CT_d && eri_d, "null pointer");
-    LDM_REQUIRE(nkpts > 0 && nao > 0 && naux > 0 && neo > 0 && (nspin == 1 || nspin == 2), "shape");
-    LDM_REQUIRE(h->plan == nullptr, "an ERI build is already open on this handle");
-    LDM_REQUIRE((double)naux * nao < 2147483647.0 && (double)naux * neo < 2147483647.0, "naux*nao too large");
-    LDM_CUDA_OK(cudaSetDevice(h->device));
-    EriPlan* p = new EriPlan();
-    h->plan = p;
-    p->st = (cudaStream_t)stream;
+static int eri_begin_body(ldm_handle h, EriPlan* p, int nkpts, int nao, int naux, int neo, int nspin,
+                          const void* CT_d) {
     LDM_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
-    p->nk = nkpts; p->nao = nao; p->naux = naux; p->neo = neo; p->nspin = nspin;
-    p->G = std::max(1, max_group);
-    p->klg = std::max(1, kl_group);
-    p->npair = (long long)neo * (neo + 1) / 2;
-    p->nauxp = naux + (naux & 1);
-    p->ldx = ((long long)p->klg * 2 * p->nauxp + 15) / 16 * 16;
-    p->CT = static_cast<const double2*>(CT_d);
-    p->eri = eri_d;
-    p->cfg = &pick_zconfig(neo, h->zgemm_3m);
-    p->launches0 = h->launches;
     const size_t xt_slice = (size_t)naux * neo * nao;
     const size_t s_elems = (size_t)nspin * naux * neo * neo;
     void* q = nullptr;
@@ -961,10 +945,40 @@ int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int 
         rc = encode_tmap_f64_3d(&p->tmCT, CT_d, 2ull * nao, (uint64_t)neo, (uint64_t)nspin * nkpts, 16ull * nao,
                                 16ull * nao * neo, 8, p->cfg->BN, false);
     if (rc) return rc;
-    rc = encode_tmap_f64_3d(&p->tmXt, p->Xt, 2ull * nao, (uint64_t)naux * neo, (uint64_t)nspin * p->G, 16ull * nao,
-                            16ull * xt_slice, 16, p->cfg->BM, true);
-    if (rc) return rc;
-    return 0;
+    return encode_tmap_f64_3d(&p->tmXt, p->Xt, 2ull * nao, (uint64_t)naux * neo, (uint64_t)nspin * p->G, 16ull * nao,
+                              16ull * xt_slice, 16, p->cfg->BM, true);
+}
+
+int ldm_eri_begin(ldm_handle h, void* stream, int nkpts, int nao, int naux, int neo, int nspin, const void* CT_d,
+                  double* eri_d, int max_group, int kl_group) {
+    LDM_REQUIRE(h && CT_d && eri_d, "null pointer");
+    LDM_REQUIRE(nkpts > 0 && nao > 0 && naux > 0 && neo > 0 && (nspin == 1 || nspin == 2), "shape");
+    LDM_REQUIRE(h->plan == nullptr, "an ERI build is already open on this handle");
+    LDM_REQUIRE((double)naux * nao < 2147483647.0 && (double)naux * neo < 2147483647.0, "naux*nao too large");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    EriPlan* p = new EriPlan();
+    p->st = (cudaStream_t)stream;
+    p->nk = nkpts; p->nao = nao; p->naux = naux; p->neo = neo; p->nspin = nspin;
+    p->G = std::max(1, max_group);
+    p->klg = std::max(1, kl_group);
+    p->npair = (long long)neo * (neo + 1) / 2;
+    p->nauxp = naux + (naux & 1);
+    p->ldx = ((long long)p->klg * 2 * p->nauxp + 15) / 16 * 16;
+    p->CT = static_cast<const double2*>(CT_d);
+    p->eri = eri_d;
+    p->cfg = &pick_zconfig(neo, h->zgemm_3m);
+    p->launches0 = h->launches;
+    h->plan = p;
+    const int rc = eri_begin_body(h, p, nkpts, nao, naux, neo, nspin, CT_d);
+    if (rc) {
+        // a failed allocation (typically cudaMalloc out of memory for a workspace) must not leave the handle with a
+        // half-built plan attached: every later build would be refused.  The error text is kept.
+        const std::string msg = ldm::last_error();
+        cudaGetLastError();
+        ldm_eri_end(h);
+        set_error(msg);
+    }
+    return rc;
 }
 
 int ldm_eri_set_mode(ldm_handle h, int gso) {
@@ -1146,7 +1160,7 @@ int ldm_eri_end_kl(ldm_handle h, int weight) {
     const int t = (p->neo + 15) / 16;
     const size_t s_spin = (size_t)p->naux * p->neo * p->neo;
     if (p->gso) {
-        pack_sym_kernel<<<dim3(t, t, (p->naux + 15) / 16), 256, 16 * 16 * 17 * 16, p->st>>>(
+        pack_sym_kernel<true><<<dim3(t * (t + 1) / 2, (p->naux + 15) / 16), 256, 16 * 16 * 17 * 16, p->st>>>(
             p->sym_init ? p->S_sym : nullptr, p->pln_init ? p->S_pln : nullptr,
             p->sym_init ? p->S_sym + s_spin : nullptr, p->pln_init ? p->S_pln + s_spin : nullptr, p->XT, p->naux,
             p->neo, p->ldx, col_re, col_im);
@@ -1154,7 +1168,7 @@ int ldm_eri_end_kl(ldm_handle h, int weight) {
         h->launches++;
     } else {
         for (int s = 0; s < p->nspin; ++s) {
-            pack_sym_kernel<<<dim3(t, t, (p->naux + 15) / 16), 256, 16 * 16 * 17 * 16, p->st>>>(
+            pack_sym_kernel<false><<<dim3(t * (t + 1) / 2, (p->naux + 15) / 16), 256, 16 * 16 * 17 * 16, p->st>>>(
                 p->sym_init ? p->S_sym + s * s_spin : nullptr, p->pln_init ? p->S_pln + s * s_spin : nullptr, nullptr,
                 nullptr, p->XT + (size_t)s * p->npair * p->ldx, p->naux, p->neo, p->ldx, col_re, col_im);
             LDM_CUDA_OK(cudaGetLastError());
@@ -1202,17 +1216,18 @@ int ldm_eri_end(ldm_handle h) {
     if (!h || !h->plan) return 0;
     EriPlan* p = h->plan;
     cudaSetDevice(h->device);
-    // workspaces stay in the handle's pool and later builds queue behind this one on the same stream; only host
-    // staging through the copy stream needs the compute stream drained before the ring can be overwritten again
-    if (p->h2d_bytes > 0) cudaStreamSynchronize(p->st);
-    cudaStreamSynchronize(p->copy_st);
+    // workspaces stay in the handle's pool; the ring may be overwritten by the next build's copy stream (host
+    // staging) while kernels of this build still read it, so the compute stream is always drained here
+    cudaStreamSynchronize(p->st);
+    if (p->copy_st) cudaStreamSynchronize(p->copy_st);
     for (int k = 0; k < 2; ++k)
         for (auto& e : p->ev[k]) {
             cudaEventDestroy(e.first);
             cudaEventDestroy(e.second);
         }
-    for (auto& e : p->ring_free) cudaEventDestroy(e);
-    cudaStreamDestroy(p->copy_st);
+    for (auto& e : p->ring_free)
+        if (e) cudaEventDestroy(e);
+    if (p->copy_st) cudaStreamDestroy(p->copy_st);
     delete p;
     h->plan = nullptr;
     return 0;

@@ -56,26 +56,74 @@ def sharded_partial(schedule, shape, compute_partial, group=None, all_ranks=Fals
     return part
 
 
+def _blocks_per_launch(kwargs, et):
+    """one name for the blocks-per-launch option on both routes: `group` as in the serial call when it is a number
+    (`group_blocks` is kept as an alias); a ProcessGroup passed as `group` still selects the communicator"""
+    g = kwargs.get("group", None)
+    blocks = kwargs.get("group_blocks", None)
+    pg = None
+    if g is not None and not isinstance(g, (int, np.integer)):
+        pg = g
+    elif g is not None and blocks is None:
+        blocks = int(g)
+    if "process_group" in kwargs:
+        pg = kwargs["process_group"]
+    return (et.DEFAULT_GROUP if blocks is None else blocks), pg
+
+
 def get_emb_eri_sharded(cell, mydf, C_ao_lo=None, basis=None, kscaled_center=None, symmetry=4,
                         kconserv_tol=KPT_DIFF_TOL, unit_eri=False, t_reversal_symm=True, C_ao_eo=None,
-                        return_device=False, all_ranks=False, group=None, **kwargs):
-    """`get_emb_eri(..., use_mpi=True)`: same result layout as the serial call on rank 0 (None elsewhere unless
-    all_ranks)."""
+                        return_device=False, all_ranks=False, gso=False, basis_k=None, incore=True, fout="H2.h5",
+                        feri=None, max_memory=None, swap_idx=None, **kwargs):
+    """`get_emb_eri(..., use_mpi=True)` / `get_emb_eri_gso(..., use_mpi=True)`: same result layout as the serial
+    call on rank 0 (None elsewhere unless all_ranks).  Restricted / unrestricted (eri_transform_mpi.py:57-223) and
+    GSO (:226-388: same k_L sharding, one ERI block from Lambda_a - Lambda_b).  Without an initialised
+    torch.distributed group the call is the serial build (one rank owns every k_L)."""
     from . import eri_transform as et
-    provider = et.as_provider(cell, mydf)
-    CT = et.build_CT(provider, C_ao_lo, basis, C_ao_eo, unit_eri)
+    from .device import get_device
+    if not incore and not t_reversal_symm:
+        raise NotImplementedError                                   # eri_transform_mpi.py:146
+    if gso and not incore:
+        raise NotImplementedError("GSO outcore ERI is not built")
+    blocks, pg = _blocks_per_launch(kwargs, et)
+    if not dist.is_initialized():
+        kw = {k: v for k, v in kwargs.items() if k not in ("group", "group_blocks", "process_group")}
+        if blocks is not None:
+            kw["group"] = blocks
+        common = dict(C_ao_lo=C_ao_lo, basis=basis, feri=feri, kscaled_center=kscaled_center, symmetry=symmetry,
+                      max_memory=max_memory, kconserv_tol=kconserv_tol, unit_eri=unit_eri, swap_idx=swap_idx,
+                      t_reversal_symm=t_reversal_symm, incore=incore, fout=fout, return_device=return_device, **kw)
+        if gso:
+            return et.get_emb_eri_gso(cell, mydf, basis_k=basis_k, **common)
+        return et.get_emb_eri_fast_gdf(cell, mydf, C_ao_eo=C_ao_eo, **common)
+    provider = et.as_provider(cell, mydf, feri=feri)
+    if gso:
+        CT = et.build_CT_gso(provider, C_ao_lo, basis, basis_k, unit_eri)
+    else:
+        CT = et.build_CT(provider, C_ao_lo, basis, C_ao_eo, unit_eri)
     nspin, nkpts, nemb, nao = CT.shape
     schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
+    imag = et._imag_buffer(t_reversal_symm, kwargs, 1 if gso else nspin * (nspin + 1) // 2, nemb)
 
     def compute(items):
         return et.emb_eri_device(provider, CT, schedule=schedule, items=items,
-                                 source=kwargs.get("source", "auto"), group=kwargs.get("group_blocks", et.DEFAULT_GROUP),
-                                 kl_group=kwargs.get("kl_group", et.DEFAULT_KL_GROUP), stats=kwargs.get("stats", None))
+                                 source=kwargs.get("source", "auto"), group=blocks,
+                                 kl_group=kwargs.get("kl_group", et.DEFAULT_KL_GROUP), stats=kwargs.get("stats", None),
+                                 gso=gso, imag=imag)
 
-    eri = sharded_partial(schedule, (nao, provider.naux, nemb, nspin), compute, group=group, all_ranks=all_ranks,
+    eri = sharded_partial(schedule, (nao, provider.naux, nemb, nspin), compute, group=pg, all_ranks=all_ranks,
                           nsplit=kwargs.get("nsplit", None))
-    if dist.get_rank(group) != 0 and not all_ranks:
+    if imag is not None and dist.get_world_size(pg) > 1:
+        # rank 0 reports max|Im| of the complete Lambda^dagger Lambda (eri_transform_mpi.py:205-209)
+        if all_ranks:
+            dist.all_reduce(imag, op=dist.ReduceOp.SUM, group=pg)
+        else:
+            dist.reduce(imag, dst=0, op=dist.ReduceOp.SUM, group=pg)
+    if dist.get_rank(pg) != 0 and not all_ranks:
         return None
-    eri = et.finalize_eri(eri, nemb, symmetry, nspin)
-    from .device import get_device
+    et._report_imag(imag, kwargs)
+    nsp = 1 if gso else nspin
+    if not incore:
+        return et.write_outcore(eri, nemb, nsp, fout)
+    eri = et.finalize_eri(eri, nemb, symmetry, nsp)
     return eri if return_device else get_device().to_host(eri)

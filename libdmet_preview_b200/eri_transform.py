@@ -30,13 +30,15 @@ def auto_groups(nao, naux, nemb, nspin, group=None, kl_group=None):
     """How many blocks share a stage-1 launch and how many momenta share a stage-3 launch.  Small blocks are
     batched until a launch carries ~3e11 flop (about 10 ms) so that tile-wave tails and launch gaps stay below a
     few percent; the staging buffers (X: group * naux * nemb * nao complex, ring: 2 * group blocks) are capped at
-    ~6 GB.  The target shape (nao 200, naux 1000, neo 150) gets 4 and 4."""
+    ~8 GB (a cap below one block still gives group = 1: a cell with 10 GB blocks must not be forced to a 80 GB
+    ring).  The target shape (nao 200, naux 1000, neo 150) gets 4 and 4."""
     if group is None:
         f_block = 8.0 * naux * nao * nemb * (nao + nemb) * nspin
         group = int(np.ceil(3.0e11 / f_block))
         bytes_per_block = 16.0 * naux * nao * (nspin * nemb + 2 * nao)
-        group = max(4, min(group, 32, int(6.0e9 / bytes_per_block)))
-        group = 1 << (max(1, group).bit_length() - 1)          # power of two: units of 32 / 36 blocks split evenly
+        group = max(4, min(group, 32))
+        group = max(1, min(group, int(8.0e9 / bytes_per_block)))            # the memory cap has the last word
+        group = 1 << (group.bit_length() - 1)                  # power of two: units of 32 / 36 blocks split evenly
     if kl_group is None:
         kl_group = max(4, min(16, int(np.ceil(4000.0 / (2.0 * naux)))))
     return int(group), int(kl_group)
@@ -152,12 +154,15 @@ class ResidentGDF(object):
         self.bytes_cached = 0
 
 
-def as_provider(cell, mydf):
+def as_provider(cell, mydf, feri=None):
     """Accept an in-memory provider (duck-typed: .kpts_scaled .kmesh .nao .naux .load), a PySCF GDF, or any object
     carrying the three members of a GDF this path reads -- `_cderi` (path of the cderi file), `kpts`, `cell` --
-    which is served from the file by `gdf_file.GDFFile` (no PySCF needed)."""
+    which is served from the file by `gdf_file.GDFFile` (no PySCF needed).  `feri` names the cderi file of a GDF
+    object that has none yet (eri_transform.py:259-261)."""
     if all(hasattr(mydf, a) for a in ("kpts_scaled", "nao", "naux", "load")):
         return mydf
+    if feri is not None and hasattr(mydf, "_cderi") and mydf._cderi is None:
+        mydf._cderi = feri
     try:
         from pyscf.pbc import df as _pdf
     except ImportError:
@@ -177,7 +182,9 @@ def as_provider(cell, mydf):
                 prov = GDFFile(cderi, cell=cell if cell is not None else getattr(mydf, "cell", None), kpts=mydf.kpts)
                 prov.blockdim = getattr(mydf, "blockdim", prov.blockdim)
                 return prov
-            except h5lite.H5FormatError:
+            except (h5lite.H5FormatError, KeyError, ValueError):
+                # a layout this reader does not serve (e.g. a file holding only the time-reversal-reduced pairs):
+                # PySCF's own loader takes over when it is installed
                 if _pdf is None:
                     raise
     if _pdf is not None:
@@ -193,6 +200,25 @@ def _to_z(a):
     if isinstance(a, torch.Tensor):
         return (a if a.dtype == torch.complex128 else a.to(torch.complex128)).contiguous()
     return dev.to_device(np.asarray(a).astype(np.complex128, copy=False), torch.complex128)
+
+
+def _basis_R2k(provider, bd):
+    """basis_k[s, k] = sum_R basis[s, R] exp(-i k R) (get_basis_k, eri_transform.py:118-126) for a device stack
+    (spin, ncells, nlo, nemb).  The k-points of a GDF object are the mesh's own (make_kpts / fftfreq order) in every
+    use of this path, and then the factorised HBM-bound lattice DFT applies; anything else (shifted or reordered
+    k-points) takes the dense phase-matrix product with the phases of the actual k-points."""
+    dev = get_device()
+    kmesh = [int(x) for x in getattr(provider, "kmesh", [])]
+    ks = np.asarray(provider.kpts_scaled, dtype=float)
+    if len(kmesh) == 3 and max(kmesh) <= 8 and int(np.prod(kmesh)) == len(ks):
+        d = ks - fourier.make_kpts_scaled(kmesh)
+        if np.abs(d - np.round(d)).max() < 1e-9:
+            out, _ = dev.lattice_dft(bd, kmesh, True, want_imag=False)
+            return out
+    phase = fourier.get_phase_R2k_scaled(kmesh, ks)                                   # (R, k)
+    W = dev.to_device(np.ascontiguousarray(phase.T), torch.complex128)
+    out, _ = dev.phase_transform(bd, W)
+    return out
 
 
 def build_CT(provider, C_ao_lo=None, basis=None, C_ao_eo=None, unit_eri=False):
@@ -241,9 +267,7 @@ def build_CT(provider, C_ao_lo=None, basis=None, C_ao_eo=None, unit_eri=False):
         bd = dev.to_device(np.ascontiguousarray(basis), torch.complex128)
     else:
         bd = dev.to_device(np.ascontiguousarray(basis, dtype=np.float64), torch.float64)
-    phase = fourier.get_phase_R2k_scaled(provider.kmesh, provider.kpts_scaled)      # (R, k)
-    W = dev.to_device(np.ascontiguousarray(phase.T), torch.complex128)
-    basis_k, _ = dev.phase_transform(bd, W)                                           # (spin, nk, nlo, nemb)
+    basis_k = _basis_R2k(provider, bd)                                                # (spin, nk, nlo, nemb)
     bkT = dev.ztranspose(basis_k.reshape(-1, nlo, nemb))                              # (spin*nk, nemb, nlo)
     Cz = _to_z(C_ao_lo).reshape(-1, nao, nlo)
     nb = spin * nkpts
@@ -271,14 +295,21 @@ class EriBuild(object):
         self.CT = CT
         self.eri = eri
         self.shape = (nkpts, nao, naux, nemb, spin)
-        check(self.dev.lib.ldm_eri_begin(self.dev.h, self.dev.stream, nkpts, nao, naux, nemb, spin, _ptr(CT),
-                                         _ptr(eri), int(group), int(kl_group)))
-        self.open = True
-        if gso:
-            check(self.dev.lib.ldm_eri_set_mode(self.dev.h, 1))
-        if imag is not None:
-            self._imag = imag
-            check(self.dev.lib.ldm_eri_set_imag(self.dev.h, _ptr(imag)))
+        self.open = False
+        try:
+            check(self.dev.lib.ldm_eri_begin(self.dev.h, self.dev.stream, nkpts, nao, naux, nemb, spin, _ptr(CT),
+                                             _ptr(eri), int(group), int(kl_group)))
+            self.open = True
+            if gso:
+                check(self.dev.lib.ldm_eri_set_mode(self.dev.h, 1))
+            if imag is not None:
+                self._imag = imag
+                check(self.dev.lib.ldm_eri_set_imag(self.dev.h, _ptr(imag)))
+        except BaseException:
+            # the library detaches a half-built plan itself; closing again is harmless and covers set_mode / set_imag
+            self.dev.lib.ldm_eri_end(self.dev.h)
+            self.open = False
+            raise
 
     def __enter__(self):
         return self
@@ -387,7 +418,7 @@ class _Prefetcher(object):
         self.err = None
         self.free = None
         self._lent = {}
-        self.stored = bool(stored) and hasattr(provider, "load_stored")
+        self.stored = bool(stored) and hasattr(provider, "load_stored") and getattr(provider, "fills_out", False)
         if getattr(provider, "fills_out", False):
             self.free = queue.Queue()
             for b in _staging_buffers(provider, depth + 2):      # queued + one being filled + one being copied
@@ -542,6 +573,19 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
     return eri
 
 
+def write_outcore(eri, nemb, nspin, fout):
+    """The reference accumulates the s4 ERI in the dataset "ccdd" of `fout`, spin blocks in the order aa, bb, ab
+    (eri_transform.py:308, 311-320, 486-521), and returns the open file without eri_restore.  Here the build runs
+    on the device as always; the finished tensor is written once and the file handed back for reading."""
+    from . import h5lite
+    host = get_device().to_host(finalize_eri(eri, nemb, 4, nspin))
+    if nspin == 2:
+        host = host[[0, 2, 1]]
+    with h5lite.Writer(fout) as w:
+        w["ccdd"] = host
+    return h5lite.File(fout)
+
+
 def _imag_buffer(t_reversal_symm, kwargs, spin_pair, nemb):
     """without time reversal the reference forms the complex Lambda^dagger Lambda, logs max|imag| and warns above
     ERI_IMAG_TOL before dropping it (eri_transform.py:390-396); `check_imag=False` skips that diagnostic"""
@@ -566,12 +610,12 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
                          t_reversal_symm=True, incore=True, fout="H2.h5", return_device=False, **kwargs):
     """eri_transform.py:235-399.  Same arguments and return layout:
     (spin*(spin+1)/2,) + s4 (npair, npair) / s1 (n,n,n,n) / s8 (npair_pair,), float64, C-contiguous, spin order
-    aa, ab, bb.  `max_memory`, `feri`, `swap_idx` are accepted for compatibility (`max_memory` only chose the
-    auxiliary chunk length in the reference and does not change results).  `incore=False` writes the s4 tensor to the
+    aa, ab, bb.  `max_memory`, `swap_idx` are accepted for compatibility (`max_memory` only chose the auxiliary
+    chunk length in the reference and does not change results); `feri` names the cderi file when `mydf._cderi` is None.  `incore=False` writes the s4 tensor to the
     HDF5 file `fout` (dataset "ccdd", spin order aa, bb, ab) and returns the file opened for reading."""
     if not incore and not t_reversal_symm:
         raise NotImplementedError                                         # l.326-327
-    provider = as_provider(cell, mydf)
+    provider = as_provider(cell, mydf, feri=feri)
     if getattr(cell, "dimension", 3) == 2 and getattr(cell, "low_dim_ft_type", None) != 'inf_vacuum':
         raise NotImplementedError                                         # l.226-227
     assert cell is None or int(cell.nao_nr()) == provider.nao
@@ -585,16 +629,7 @@ def get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscale
                          kl_group=kwargs.get("kl_group", DEFAULT_KL_GROUP), stats=kwargs.get("stats", None), imag=imag)
     _report_imag(imag, kwargs)
     if not incore:
-        # The reference accumulates the s4 ERI in the dataset "ccdd" of `fout`, spin blocks in the order aa, bb, ab
-        # (l.308, 311-320, 486-521), and returns the open file without eri_restore.  Here the build runs on the device
-        # as always; the finished tensor is written once and the file handed back for reading.
-        from . import h5lite
-        host = get_device().to_host(finalize_eri(eri, nemb, 4, spin))
-        if spin == 2:
-            host = host[[0, 2, 1]]
-        with h5lite.Writer(fout) as w:
-            w["ccdd"] = host
-        return h5lite.File(fout)
+        return write_outcore(eri, nemb, spin, fout)
     eri = finalize_eri(eri, nemb, symmetry, spin)
     if return_device:
         return eri
@@ -613,7 +648,8 @@ def get_emb_eri(cell, mydf, C_ao_lo=None, basis=None, unit_eri=False, symmetry=4
         from . import dist
         return dist.get_emb_eri_sharded(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, kscaled_center=kscaled_center,
                                         symmetry=symmetry, kconserv_tol=kconserv_tol, unit_eri=unit_eri,
-                                        t_reversal_symm=t_reversal_symm, **kwargs)
+                                        t_reversal_symm=t_reversal_symm, incore=incore, fout=fout, feri=feri,
+                                        max_memory=max_memory, swap_idx=swap_idx, **kwargs)
     return get_emb_eri_fast_gdf(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, feri=feri,
                                 kscaled_center=kscaled_center, symmetry=symmetry, max_memory=max_memory,
                                 kconserv_tol=kconserv_tol, unit_eri=unit_eri, swap_idx=swap_idx,
@@ -663,10 +699,7 @@ def build_CT_gso(provider, C_ao_lo, basis=None, basis_k=None, unit_eri=False):
             bd = dev.to_device(np.ascontiguousarray(basis), torch.complex128)[None]
         else:
             bd = dev.to_device(np.ascontiguousarray(basis, dtype=np.float64), torch.float64)[None]
-        phase = fourier.get_phase_R2k_scaled(provider.kmesh, provider.kpts_scaled)
-        W = dev.to_device(np.ascontiguousarray(phase.T), torch.complex128)
-        bk, _ = dev.phase_transform(bd, W)
-        bk = bk[0]                                                     # (nk, 2*nlo, nemb)
+        bk = _basis_R2k(provider, bd)[0]                               # (nk, 2*nlo, nemb)
     else:
         bk = _to_z(basis_k)
     if bk.dim() == 3:
@@ -692,9 +725,18 @@ def get_emb_eri_gso(cell, mydf, C_ao_lo=None, basis=None, feri=None, kscaled_cen
     """eri_transform.py:1104-1250: embedding ERI with partial particle-hole transform (generalised spin orbitals).
     Same stage-1 pipeline with two spin flavours; stage 3 is one Gram product of Lambda_a - Lambda_b
     (= the four signed products of `_Lij_s4_to_eri_gso`, l.1252-1284).  Returns (1,) + s4 / s1 / s8 layout."""
-    if not incore and not t_reversal_symm:
-        raise NotImplementedError                                         # l.326-327
-    provider = as_provider(cell, mydf)
+    if kwargs.pop("use_mpi", False):           # eri_transform_mpi.py:226-388
+        from . import dist
+        return dist.get_emb_eri_sharded(cell, mydf, C_ao_lo=C_ao_lo, basis=basis, kscaled_center=kscaled_center,
+                                        symmetry=symmetry, kconserv_tol=kconserv_tol, unit_eri=unit_eri,
+                                        t_reversal_symm=t_reversal_symm, gso=True, basis_k=basis_k, incore=incore,
+                                        fout=fout, feri=feri, max_memory=max_memory, swap_idx=swap_idx,
+                                        return_device=return_device, **kwargs)
+    if not incore:
+        # the reference's outcore GSO branch accumulates into an HDF5 dataset (l.1160-1172); not built here --
+        # say so instead of silently returning an in-memory array
+        raise NotImplementedError("get_emb_eri_gso(incore=False) is not built")
+    provider = as_provider(cell, mydf, feri=feri)
     CT = build_CT_gso(provider, C_ao_lo, basis, basis_k, unit_eri)
     nemb = CT.shape[2]
     schedule = build_schedule(provider.kpts_scaled, t_reversal_symm, kconserv_tol, kscaled_center)
