@@ -53,6 +53,19 @@ class OracleLattice(o_fourier.StripeLattice):
     def getH0(self):
         return self.H0
 
+    # what mfd.HF reads (lattice.py:209-231)
+    def getH1(self, kspace=True):
+        return self.hcore_lo_k if kspace else self.k2R(self.hcore_lo_k)
+
+    def getFock(self, kspace=True):
+        return self.fock_lo_k if kspace else self.k2R(self.fock_lo_k)
+
+    def FFTtoT(self, A):
+        return o_fourier.FFTtoT(A, self.kmesh)
+
+    def FFTtoK(self, A):
+        return o_fourier.FFTtoK(A, self.kmesh)
+
 
 def mean_field(kmesh, nao, nocc, spin=1, seed=0):
     """hcore, ovlp (identity: orthonormal AOs), vhf, rdm1 in the AO basis with time-reversal structure."""
