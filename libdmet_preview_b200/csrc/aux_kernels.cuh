@@ -7,6 +7,18 @@
 
 namespace ldm {
 
+// max over the warp, then one atomicMax per warp -- and only when the value beats what is already there: a plain
+// (L2) read filters almost every warp once the running maximum has settled, so a single address is not hammered
+// by one atomic per warp of a 100k-warp grid (non-negative doubles order like their bit patterns).
+__device__ __forceinline__ void warp_atomic_max_abs(double v, unsigned long long* addr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0.0) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        if (bits > *reinterpret_cast<volatile unsigned long long*>(addr)) atomicMax(addr, bits);
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // Lattice Fourier transform as a dense phase-matrix product (Nk <= a few hundred):
 //     out[b][k][x] = scale * sum_R W[k][R] * in[b][R][x]
@@ -69,11 +81,7 @@ phase_transform_kernel(const double* __restrict__ in, double* __restrict__ out, 
             }
         }
     }
-    if (out_real && imag_max) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) im_max = fmax(im_max, __shfl_xor_sync(0xffffffffu, im_max, o));
-        if ((threadIdx.x & 31) == 0 && im_max > 0.0) atomicMax(imag_max, (unsigned long long)__double_as_longlong(im_max));
-    }
+    if (out_real && imag_max) warp_atomic_max_abs(im_max, imag_max);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -232,12 +240,7 @@ lattice_dft_kernel(const double* __restrict__ in, double* __restrict__ out, cons
     }
     double im_max = 0.0;
     LDM_DFT_SWITCH(n2, im_max = dft_pass_out<ND>(out, tile, tb.w[2], n0 * n1, TX, X, x0, boff, scale, out_real));
-    if (out_real && imag_max) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) im_max = fmax(im_max, __shfl_xor_sync(0xffffffffu, im_max, o));
-        if ((threadIdx.x & 31) == 0 && im_max > 0.0)
-            atomicMax(imag_max, (unsigned long long)__double_as_longlong(im_max));
-    }
+    if (out_real && imag_max) warp_atomic_max_abs(im_max, imag_max);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -870,9 +873,7 @@ __global__ void max_abs_kernel(const double* __restrict__ x, long long n, unsign
     double m = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         m = fmax(m, fabs(x[i]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+    warp_atomic_max_abs(m, out);
 }
 
 // unpack a packed symmetric vector to a full (n, n) matrix
@@ -901,10 +902,7 @@ __global__ void ksum_real_kernel(const double2* __restrict__ in, double* __restr
         out[x] = re * scale;
         im_max = fabs(im);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) im_max = fmax(im_max, __shfl_xor_sync(0xffffffffu, im_max, o));
-    if (imag_max && (threadIdx.x & 31) == 0 && im_max > 0.0)
-        atomicMax(imag_max, (unsigned long long)__double_as_longlong(im_max));
+    if (imag_max) warp_atomic_max_abs(im_max, imag_max);
 }
 
 // ----------------------------------------------------------------------------------------------------------

@@ -1216,9 +1216,11 @@ int ldm_eri_end(ldm_handle h) {
     if (!h || !h->plan) return 0;
     EriPlan* p = h->plan;
     cudaSetDevice(h->device);
-    // workspaces stay in the handle's pool; the ring may be overwritten by the next build's copy stream (host
-    // staging) while kernels of this build still read it, so the compute stream is always drained here
-    cudaStreamSynchronize(p->st);
+    // workspaces stay in the handle's pool and later builds queue behind this one on the same stream.  The staging
+    // ring is the exception: the next build may fill it through its own copy stream (host blocks) while kernels of
+    // this build still read it, so a build that touched the ring -- host OR device-generated blocks -- drains the
+    // compute stream before it goes away.  Builds over a resident store never wait here.
+    if (p->ring) cudaStreamSynchronize(p->st);
     if (p->copy_st) cudaStreamSynchronize(p->copy_st);
     for (int k = 0; k < 2; ++k)
         for (auto& e : p->ev[k]) {

@@ -306,9 +306,11 @@ class EriBuild(object):
                 self._imag = imag
                 check(self.dev.lib.ldm_eri_set_imag(self.dev.h, _ptr(imag)))
         except BaseException:
-            # the library detaches a half-built plan itself; closing again is harmless and covers set_mode / set_imag
-            self.dev.lib.ldm_eri_end(self.dev.h)
-            self.open = False
+            # a failed ldm_eri_begin has detached its half-built plan itself (and must not close a build somebody
+            # else holds open on the handle); a failure after it (set_mode / set_imag) closes the build it opened
+            if self.open:
+                self.open = False
+                self.dev.lib.ldm_eri_end(self.dev.h)
             raise
 
     def __enter__(self):
