@@ -98,6 +98,12 @@ int ldm_restore_s1(ldm_handle h, void* stream, const double* eri4_d, double* out
 int ldm_restore_s8(ldm_handle h, void* stream, const double* eri4_d, double* out_d, int n);
 int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm_d, double* vj_d, double* vk_d,
               int n);
+/* Same result for a SYMMETRIC s4 block (eri4[P][Q] == eri4[Q][P]: the restricted / aa / bb blocks) and a symmetric
+ * density matrix -- what the reference always passes (hermi=1, solver/scf.py:300, 309, 313-316): only the lower
+ * triangle of eri4 is read, half of the tensor crosses HBM.  Shapes outside the kernel's range (n <= 16, n > 160)
+ * are served by ldm_jk_s4.                                                                                     */
+int ldm_jk_s4_symm(ldm_handle h, void* stream, const double* eri4_d, const double* dm_d, double* vj_d, double* vk_d,
+                   int n);
 
 /* DMET energy weights, in place (reference: get_H2_scaled, libdmet/routine/slater.py:1734-1778).
  * symmetry 4: eri (npair, npair) *= (w[P] + w[Q]) / 4 with weights_d[npair] = impurity count of each pair (0,1,2);

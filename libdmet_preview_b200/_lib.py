@@ -44,6 +44,7 @@ SIGNATURES = {
     "ldm_restore_s1": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "ldm_restore_s8": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "ldm_jk_s4": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
+    "ldm_jk_s4_symm": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
     "ldm_scale_eri": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp]),
     "ldm_synth_block": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_uint32, C.c_double]),

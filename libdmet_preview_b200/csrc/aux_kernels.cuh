@@ -819,6 +819,182 @@ jk_rows_bulk_kernel(const double* __restrict__ eri4, const double* __restrict__ 
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// J/K from the LOWER TRIANGLE of a symmetric s4 ERI (eri4[P][Q] == eri4[Q][P]: the restricted / aa / bb blocks, which
+// are Gram matrices) and a symmetric density matrix (the reference always passes hermi=1, solver/scf.py:300-326):
+// only the words Q <= P of row P are read, i.e. half of the tensor crosses HBM.
+//   J:  vj[P] = sum_{Q <= P} E[P][Q] dd[Q]  (row part, kept per row)
+//             + sum_{Q >  P} E[Q][P] dd[Q]  (column part: every row P' adds dd[P'] E[P'][Q] to the columns Q < P';
+//                                            accumulated in registers over the rows of a CTA, one partial vector
+//                                            per CTA, summed in a fixed order afterwards)
+//   K:  with M_P the symmetric matrix packed in row P, truncated to the words Q <= P (the word Q = P halved),
+//       S[j][:] += M_P D[i][:],  S[i][:] += M_P D[j][:] (i != j),   K = S + S^T.
+// One CTA walks JKT_ROWS consecutive rows (heaviest row blocks are scheduled first); a row arrives in shared memory
+// by cp.async.bulk into one of two buffers, so the next row streams in while the current one is used.  Per word: one
+// conflict-free LDS + one cached load of dd for J; the K walk of the bulk kernel above on the truncated matrix (the
+// unused tail of packed row i is zero-filled, so the walk needs no predicates).  Deterministic: no atomics.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int JKT_ROWS = 32;
+
+template <int NP>
+__global__ void __launch_bounds__(2 * NP, 1)
+jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, const double* __restrict__ dd,
+              double* __restrict__ vj_row, double* __restrict__ jpart, double* __restrict__ kpart, int n,
+              long long npair, int with_k, int rowbuf_words) {
+    constexpr int T = 2 * NP;
+    constexpr int NCMAX = (NP * (NP + 1) / 2 + T - 1) / T;
+    extern __shared__ __align__(16) double jkt_rows[];         // 2 buffers of rowbuf_words
+    __shared__ double2 sD[NP];                                 // (D[i][l], D[j][l])
+    __shared__ double sY[2][2][NP];
+    __shared__ double sJ[T / 32];
+    __shared__ __align__(8) unsigned long long bars[2];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const long long nblk = (npair + JKT_ROWS - 1) / JKT_ROWS;
+    const long long B = nblk - 1 - blockIdx.x;                  // heaviest blocks first
+    const long long Phi = min(npair, (B + 1) * JKT_ROWS) - 1, Plo = B * JKT_ROWS;
+    const int nrows = (int)(Phi - Plo + 1);
+    const long long total = npair * npair;
+    if (t == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // bring the words 0..P of row P into buffer b (16-byte aligned enclosing range by bulk copy, a tail that would
+    // cross the end of the tensor by plain loads)
+    auto issue = [&](long long P, int b) {
+        const long long off = P * npair, a0 = off & ~1LL;
+        const int head = (int)(off - a0);
+        long long cnt = ((long long)head + P + 2) & ~1LL;
+        if (a0 + cnt > total) cnt -= 2;
+        double* buf = jkt_rows + (size_t)b * rowbuf_words;
+        if (t == 0) {
+            fence_proxy_async_smem();
+            const uint32_t bar = smem_u32(&bars[b]);
+            mbar_expect_tx(bar, (uint32_t)(cnt * 8));
+            const uint32_t dst = smem_u32(buf);
+            for (long long c = 0; c < cnt; c += 4096)
+                bulk_load_1d(dst + (uint32_t)(c * 8), eri4 + a0 + c, (uint32_t)(min(4096LL, cnt - c) * 8), bar);
+        }
+        for (long long q = cnt - head + t; q <= P; q += T) buf[head + q] = eri4[off + q];
+    };
+
+    double colacc[NCMAX];
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c) colacc[c] = 0.0;
+
+    issue(Phi, 0);
+    __syncthreads();                                                // plain-load tail of the very last row
+    for (int r = 0; r < nrows; ++r) {
+        const long long P = Phi - r;
+        const int b = r & 1;
+        if (r + 1 < nrows) issue(P - 1, b ^ 1);
+        int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+        while ((long long)(i + 1) * (i + 2) / 2 <= P) ++i;
+        while ((long long)i * (i + 1) / 2 > P) --i;
+        const int j = (int)(P - (long long)i * (i + 1) / 2);
+        for (int l = t; l < NP; l += T)
+            sD[l] = l < n ? make_double2(D[(size_t)i * n + l], D[(size_t)j * n + l]) : make_double2(0.0, 0.0);
+        double* srow = jkt_rows + (size_t)b * rowbuf_words + (int)((P * npair) & 1LL);
+        mbar_wait(smem_u32(&bars[b]), (uint32_t)((r >> 1) & 1));
+        // ---- J: row dot product and column updates ----
+        const double ddP = dd[P];
+        double racc = 0.0;
+#pragma unroll
+        for (int c = 0; c < NCMAX; ++c) {
+            const long long q = t + (long long)c * T;
+            if (q <= P) {
+                const double e = srow[q];
+                racc = fma(e, __ldg(dd + q), racc);
+                if (q < P) colacc[c] = fma(e, ddP, colacc[c]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+        if (lane == 0) sJ[w] = racc;
+        __syncthreads();
+        if (t == 0) {
+            double sj = 0.0;
+            for (int x = 0; x < T / 32; ++x) sj += sJ[x];
+            vj_row[P] = sj;
+        }
+        if (with_k) {
+            // the rest of packed row i is not part of the truncated matrix; the word Q = P counts half
+            const int rowend = (i + 1) * (i + 2) / 2;
+            for (long long q = P + 1 + t; q < rowend; q += T) srow[q] = 0.0;
+            if (t == T - 1) srow[P] *= 0.5;
+            __syncthreads();
+            const int ne = i + 1;
+            const int g = t >= NP, k = t - g * NP;
+            const int half = (ne + 1) >> 1;
+            const int l0 = g * half, l1 = min(ne, l0 + half);
+            double y1 = 0.0, y2 = 0.0, z1 = 0.0, z2 = 0.0;
+            if (k < ne) {
+                int offA = k * (k + 1) / 2 + l0;                    // M[k][l], l <= k
+                int offB = l0 * (l0 + 1) / 2 + k;                   // M[l][k], l > k
+                int l = l0;
+                for (; l + 1 < l1; l += 2) {
+                    const double m0 = srow[l <= k ? offA : offB];
+                    const double m1 = srow[l + 1 <= k ? offA + 1 : offB + l + 1];
+                    const double2 d0 = sD[l], d1 = sD[l + 1];
+                    y1 = fma(m0, d0.x, y1);
+                    y2 = fma(m0, d0.y, y2);
+                    z1 = fma(m1, d1.x, z1);
+                    z2 = fma(m1, d1.y, z2);
+                    offA += 2;
+                    offB += 2 * l + 3;
+                }
+                if (l < l1) {
+                    const double m0 = srow[l <= k ? offA : offB];
+                    const double2 d0 = sD[l];
+                    y1 = fma(m0, d0.x, y1);
+                    y2 = fma(m0, d0.y, y2);
+                }
+            }
+            sY[g][0][k] = y1 + z1;
+            sY[g][1][k] = y2 + z2;
+            __syncthreads();
+            for (int x = t; x < 2 * n; x += T) {
+                const int v = x >= n, kk = x - v * n;
+                kpart[(P * 2 + v) * n + kk] = sY[0][v][kk] + sY[1][v][kk];
+            }
+        }
+        fence_proxy_async_smem();        // generic writes to this buffer (zero fill, halving) before the next bulk copy
+        __syncthreads();                                            // buffers, sD, sY, sJ free for the next row
+    }
+    // column partials of this block: every column below the block's last row
+    double* jp = jpart + (size_t)B * npair;
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c) {
+        const long long q = t + (long long)c * T;
+        if (q < Phi) jp[q] = colacc[c];
+    }
+}
+
+// vj_packed[q] = vj_row[q] + sum over the row blocks B >= q / JKT_ROWS of their column partials (fixed order)
+__global__ void jk_tri_jsum_kernel(const double* __restrict__ vj_row, const double* __restrict__ jpart,
+                                   double* __restrict__ vj_packed, long long npair) {
+    const long long nblk = (npair + JKT_ROWS - 1) / JKT_ROWS;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npair;
+         q += (long long)gridDim.x * blockDim.x) {
+        double s = vj_row[q];
+        for (long long B = q / JKT_ROWS; B < nblk; ++B) {
+            const long long Phi = min(npair, (B + 1) * JKT_ROWS) - 1;
+            if (q < Phi) s += jpart[B * npair + q];
+        }
+        vj_packed[q] = s;
+    }
+}
+
+// K = S + S^T
+__global__ void symmetrise_add_kernel(const double* __restrict__ S, double* __restrict__ K, int n) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+        const int a = idx / n, b = idx - a * n;
+        K[idx] = S[idx] + S[(size_t)b * n + a];
+    }
+}
+
 // K[a][k] = sum_{i >= a} y1(P(i, a))[k] + sum_{j < a} y2(P(a, j))[k], terms dealt to the 8 warps and summed in a
 // fixed order (deterministic)
 __global__ void __launch_bounds__(256)

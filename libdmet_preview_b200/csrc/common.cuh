@@ -88,6 +88,10 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// order earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy / TMA) writes
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -671,6 +671,8 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
     size_t need = (size_t)npair * 16 + (size_t)npair * 2 * n * 8;
     if (h->jk_part_bytes < need) {
         if (h->jk_part_d) LDM_CUDA_OK(cudaFree(h->jk_part_d));
+        h->jk_part_d = nullptr;
+        h->jk_part_bytes = 0;
         LDM_CUDA_OK(cudaMalloc(&h->jk_part_d, need));
         h->jk_part_bytes = need;
     }
@@ -712,6 +714,75 @@ int ldm_jk_s4(ldm_handle h, void* stream, const double* eri4_d, const double* dm
         jk_reduce_kernel<<<n, 256, (size_t)8 * n * 8, st>>>(kpart, vk_d, n);
         LDM_CUDA_OK(cudaGetLastError());
         h->launches++;
+    }
+    return 0;
+}
+
+int ldm_jk_s4_symm(ldm_handle h, void* stream, const double* eri4_d, const double* dm_d, double* vj_d, double* vk_d,
+                   int n) {
+    LDM_REQUIRE(h && eri4_d && dm_d && vj_d, "null pointer");
+    LDM_REQUIRE(n > 0 && n <= 3200, "orbital count out of range");
+    const long long npair = (long long)n * (n + 1) / 2;
+    const int rowbuf_words = (int)((npair + 4) & ~1LL);
+    const size_t smem = (size_t)2 * rowbuf_words * 8;
+    // two row buffers must fit beside ~10 KB of static shared memory; otherwise the general kernels serve the call
+    if (n <= 16 || n > 160 || smem > 214 * 1024) return ldm_jk_s4(h, stream, eri4_d, dm_d, vj_d, vk_d, n);
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nblk = (npair + JKT_ROWS - 1) / JKT_ROWS;
+    // workspace: vj_packed | dd | vj_row | S (n*n) | kpart (npair * 2n) | jpart (nblk * npair)
+    const size_t need = ((size_t)npair * 3 + (size_t)n * n + (size_t)npair * 2 * n + (size_t)nblk * npair) * 8;
+    if (h->jk_part_bytes < need) {
+        if (h->jk_part_d) {
+            LDM_CUDA_OK(cudaDeviceSynchronize());
+            LDM_CUDA_OK(cudaFree(h->jk_part_d));
+            h->jk_part_d = nullptr;
+            h->jk_part_bytes = 0;
+        }
+        LDM_CUDA_OK(cudaMalloc(&h->jk_part_d, need));
+        h->jk_part_bytes = need;
+    }
+    double* vj_packed = static_cast<double*>(h->jk_part_d);
+    double* dd = vj_packed + npair;
+    double* vj_row = dd + npair;
+    double* S = vj_row + npair;
+    double* kpart = S + (size_t)n * n;
+    double* jpart = kpart + (size_t)npair * 2 * n;
+    jk_pack_dm_kernel<<<(unsigned)std::min<long long>((npair + 255) / 256, 1024), 256, 0, st>>>(dm_d, dd, n);
+    LDM_CUDA_OK(cudaGetLastError());
+    const int wk = vk_d != nullptr;
+    static bool attr = false;
+    if (!attr) {
+        LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_tri_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         214 * 1024));
+        LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_tri_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         214 * 1024));
+        LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_tri_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         214 * 1024));
+        attr = true;
+    }
+    if (n <= 64)
+        jk_tri_kernel<64><<<(unsigned)nblk, 128, smem, st>>>(eri4_d, dm_d, dd, vj_row, jpart, kpart, n, npair, wk,
+                                                            rowbuf_words);
+    else if (n <= 128)
+        jk_tri_kernel<128><<<(unsigned)nblk, 256, smem, st>>>(eri4_d, dm_d, dd, vj_row, jpart, kpart, n, npair, wk,
+                                                             rowbuf_words);
+    else
+        jk_tri_kernel<160><<<(unsigned)nblk, 320, smem, st>>>(eri4_d, dm_d, dd, vj_row, jpart, kpart, n, npair, wk,
+                                                             rowbuf_words);
+    LDM_CUDA_OK(cudaGetLastError());
+    jk_tri_jsum_kernel<<<(unsigned)std::min<long long>((npair + 127) / 128, 4096), 128, 0, st>>>(vj_row, jpart,
+                                                                                                  vj_packed, npair);
+    LDM_CUDA_OK(cudaGetLastError());
+    unpack_sym_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(vj_packed, vj_d, n);
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches += 4;
+    if (vk_d) {
+        jk_reduce_kernel<<<n, 256, (size_t)8 * n * 8, st>>>(kpart, S, n);
+        LDM_CUDA_OK(cudaGetLastError());
+        symmetrise_add_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(S, vk_d, n);
+        LDM_CUDA_OK(cudaGetLastError());
+        h->launches += 2;
     }
     return 0;
 }

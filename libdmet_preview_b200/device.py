@@ -198,13 +198,16 @@ class Device(object):
         check(self.lib.ldm_restore_s8(self.h, self.stream, _ptr(eri4), _ptr(out), n))
         return out
 
-    def jk_s4(self, eri4, dm, with_k=True):
+    def jk_s4(self, eri4, dm, with_k=True, symmetric=False):
+        """J, K of one s4 ERI block and one density matrix.  symmetric=True: `eri4` is a symmetric matrix AND `dm` is
+        symmetric (the reference's hermi=1 calls on the restricted / aa / bb blocks) -- only the lower triangle of
+        `eri4` is read."""
         n = dm.shape[-1]
         assert eri4.dtype == torch.float64 and eri4.is_contiguous() and dm.is_contiguous()
         vj = self.empty((n, n))
         vk = self.empty((n, n)) if with_k else None
-        check(self.lib.ldm_jk_s4(self.h, self.stream, _ptr(eri4), _ptr(dm), _ptr(vj), _ptr(vk) if with_k else None,
-                                 n))
+        fn = self.lib.ldm_jk_s4_symm if symmetric else self.lib.ldm_jk_s4
+        check(fn(self.h, self.stream, _ptr(eri4), _ptr(dm), _ptr(vj), _ptr(vk) if with_k else None, n))
         return vj, vk
 
     def scale_eri(self, eri, n, symmetry, weights):

@@ -257,16 +257,18 @@ def get_veff_dev(rdm1_emb, eri4_blocks):
     dev = get_device()
     spin = rdm1_emb.shape[0]
     dm = rdm1_emb.contiguous()
+    # the density matrices are symmetric (the reference passes hermi=1 throughout) and the restricted / aa / bb
+    # blocks are symmetric matrices: those calls read only the lower triangle of the block
     if spin == 1:
-        vj, vk = dev.jk_s4(eri4_blocks[0], dm[0])
+        vj, vk = dev.jk_s4(eri4_blocks[0], dm[0], symmetric=True)
         return (vj - vk * 0.5)[None]                                    # scf.py:347-348
     if len(eri4_blocks) == 1:                                            # UHF with a spin-free ERI (scf.py:303-309)
-        vj0, vk0 = dev.jk_s4(eri4_blocks[0], dm[0])
-        vj1, vk1 = dev.jk_s4(eri4_blocks[0], dm[1])
+        vj0, vk0 = dev.jk_s4(eri4_blocks[0], dm[0], symmetric=True)
+        vj1, vk1 = dev.jk_s4(eri4_blocks[0], dm[1], symmetric=True)
         return torch.stack([vj0 + vj1 - vk0, vj0 + vj1 - vk1])
     assert len(eri4_blocks) == 3 and spin == 2                          # UIHF (scf.py:310-331)
-    vj00, vk00 = dev.jk_s4(eri4_blocks[0], dm[0])
-    vj11, vk11 = dev.jk_s4(eri4_blocks[1], dm[1])
+    vj00, vk00 = dev.jk_s4(eri4_blocks[0], dm[0], symmetric=True)
+    vj11, vk11 = dev.jk_s4(eri4_blocks[1], dm[1], symmetric=True)
     vj01, _ = dev.jk_s4(eri4_blocks[2], dm[1], with_k=False)            # J on alpha from beta density
     eri_ba = eri4_blocks[2].t().contiguous()
     vj10, _ = dev.jk_s4(eri_ba, dm[0], with_k=False)                    # J on beta from alpha density

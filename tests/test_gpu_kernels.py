@@ -195,6 +195,34 @@ def test_jk_streaming_variants(dev, n):
     assert torch.equal(again[0], vj) and torch.equal(again[1], vk)          # fixed summation order
 
 
+@pytest.mark.parametrize("n", [17, 31, 64, 65, 100, 128, 129, 150, 160])
+def test_jk_lower_triangle_kernel(dev, n):
+    """`ldm_jk_s4_symm`: symmetric ERI block and symmetric density, only the lower triangle of the block is read
+    (the upper triangle is poisoned here to prove it) -- against PySCF's dot_eri_dm convention (scf.py:269-271) and
+    bit-for-bit reproducible"""
+    from oracle import pyscf_lib as olib
+    rng = np.random.default_rng(1000 + n)
+    npair = n * (n + 1) // 2
+    x = rng.standard_normal((npair, npair))
+    e4 = x + x.T
+    d = rng.standard_normal((n, n))
+    d = d + d.T
+    rj, rk = olib.dot_eri_dm(e4, d, hermi=1)
+    poisoned = np.tril(e4) + np.triu(np.full_like(e4, 1e30), 1)
+    e4d, dd = dev.to_device(poisoned, torch.float64), dev.to_device(d, torch.float64)
+    vj, vk = dev.jk_s4(e4d, dd, symmetric=True)
+    assert np.abs(vj.cpu().numpy() - rj).max() < 1e-11 * np.abs(rj).max()
+    assert np.abs(vk.cpu().numpy() - rk).max() < 1e-11 * np.abs(rk).max()
+    vj2, none = dev.jk_s4(e4d, dd, with_k=False, symmetric=True)
+    assert none is None and torch.equal(vj2, vj)
+    again = dev.jk_s4(e4d, dd, symmetric=True)
+    assert torch.equal(again[0], vj) and torch.equal(again[1], vk)          # fixed summation order
+    # agrees with the general kernel on the full symmetric block
+    gj, gk = dev.jk_s4(dev.to_device(e4, torch.float64), dd)
+    assert np.abs((gj - vj).cpu().numpy()).max() < 1e-11 * np.abs(rj).max()
+    assert np.abs((gk - vk).cpu().numpy()).max() < 1e-11 * np.abs(rk).max()
+
+
 def test_synth_block_bit_exact(dev):
     from libdmet_preview_b200 import synthetic
     g = synthetic.SyntheticGDF([2, 1, 3], 9, 14, seed=77)

@@ -55,7 +55,11 @@ t = timeit(lambda i: dev.restore_s8(E[i], neo), 2, reps=5)
 report("restore s4->s8", 8 * npair * npair // 2 * 2, t)
 D = torch.randn(neo, neo, dtype=torch.float64, device="cuda"); D = (D + D.T).contiguous()
 t = timeit(lambda i: dev.jk_s4(E[i], D), 2, reps=5)
-report("J/K from s4 ERI (neo=150)", 8 * npair * npair, t)
+report("J/K from s4 ERI (neo=150), general kernel", 8 * npair * npair, t)
+t = timeit(lambda i: dev.jk_s4(E[i], D, symmetric=True), 2, reps=5)
+report("J/K from s4 ERI (neo=150), lower triangle", 8 * npair * npair, t)
+t = timeit(lambda i: dev.jk_s4(E[i], D, with_k=False, symmetric=True), 2, reps=5)
+report("J only, lower triangle", 8 * npair * npair, t)
 blk = torch.empty(1000, 200, 200, dtype=torch.complex128, device="cuda")
 t = timeit(lambda i: dev.synth_block(blk, 1000, 200, (1, 2, 3, 4), 0.25), 1, reps=5)
 report("synth_block (1000,200,200) generator", 16 * 1000 * 200 * 200, t)

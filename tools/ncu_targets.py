@@ -20,6 +20,7 @@ E = (E + E.T).contiguous()
 D = torch.randn(neo, neo, dtype=torch.float64, device="cuda"); D = (D + D.T).contiguous()
 for _ in range(2):
     dev.jk_s4(E, D)
+    dev.jk_s4(E, D, symmetric=True)
 # pack_sym: one transfer momentum of a 1x1x2 mesh at the target block shape
 gdf = synthetic.SyntheticGDF([1, 1, 2], 200, 1000, seed=3)
 C = synthetic.make_C_ao_lo([1, 1, 2], 200, seed=1)

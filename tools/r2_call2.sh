@@ -10,7 +10,7 @@ for sp in 1 0; do
 done
 BENCH_DEBUG=1 timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu --no-dmet --no-peak 2>$O/r2b_bench.err | tail -1 | tee $O/r2b_bench_dev.json
 LDM_ZGEMM_SKIP_PAD=0 timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu --no-dmet --no-peak --no-parity 2>/dev/null | tail -1 | tee $O/r2b_bench_dev_nopadskip.json
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:'lattice_dft|pack_sym|jk_rows_bulk' -c 12 \
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:'lattice_dft|pack_sym|jk_rows_bulk|jk_tri_kernel' -c 14 \
     -o $O/r2b_hbm_full python tools/ncu_targets.py > $O/r2b_ncu_targets.log 2>&1
 ncu -i $O/r2b_hbm_full.ncu-rep --page raw --csv > $O/r2b_hbm_full_raw.csv 2>/dev/null
 timeout 300 python bench.py --workload c3_nio_uhf --gdf-file --steps 2 --warmup 1 --no-e2e --no-cpu --no-dmet --no-peak 2>/dev/null | tail -1 | tee $O/r2b_bench_c3_gdffile.json
