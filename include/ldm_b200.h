@@ -89,6 +89,11 @@ int ldm_d2z(ldm_handle h, void* stream, const double* in_d, void* out_d, int64_t
  * transform_trans_inv_k (libdmet/routine/slater_helper.py:37-50).                                            */
 int ldm_ksum_real(ldm_handle h, void* stream, const void* in_d, double* out_d, int nk, int64_t X, double scale,
                   double* imag_max_h);
+/* out[L][m(m+1)/2 + c] = in[L][m][c], c <= m, for a stack of `rows` complex (n, n) matrices: PySCF lib.pack_tril
+ * as transform_gdf_to_lo applies it to the blocks it stores (eri_transform.py:1386-1390).  out_real: keep the real
+ * part only (double output) and report max|imag| (both k-points Gamma).                                          */
+int ldm_pack_tril(ldm_handle h, void* stream, const void* in_d, void* out_d, int rows, int n, int out_real,
+                  double* imag_max_h);
 
 /* ---- ERI re-layouts and J/K ------------------------------------------------------------------------------
  * restore: s4 (npair, npair) -> s1 (n,n,n,n) or s8 (npair(npair+1)/2)   (pyscf ao2mo.restore; call sites
@@ -159,6 +164,7 @@ int ldm_eri_block_host(ldm_handle h, int ki, int kj, int sym, const void* L_h);
  * raw bytes cross PCIe once and are widened / unpacked / transposed on the device (ldm_unpack_stored).        */
 #define LDM_STORED_SWAPPED 1
 #define LDM_STORED_REAL 2
+#define LDM_STORED_CONJ 4      /* the entry is the one of the time-reversed pair (-k_i, -k_j): plain conjugate */
 int ldm_eri_block_stored(ldm_handle h, int ki, int kj, int sym, const void* src_h, int rows, int64_t ncols,
                          int flags);
 /* device -> device form of the same conversion: src_d (rows, ncols) -> out_d (naux, nao, nao) complex128 */

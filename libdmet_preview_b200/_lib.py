@@ -41,6 +41,7 @@ SIGNATURES = {
     "ldm_ztranspose": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "ldm_d2z": (C.c_int, [vp, vp, vp, vp, C.c_int64]),
     "ldm_ksum_real": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int64, C.c_double, c_f64p]),
+    "ldm_pack_tril": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, c_f64p]),
     "ldm_restore_s1": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "ldm_restore_s8": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "ldm_jk_s4": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
@@ -87,6 +88,12 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class UnsupportedBranch(NotImplementedError):
+    """a branch of the reference this package does not mirror (model Hamiltonians, DFT / QSGW one-body terms, the
+    non-interacting bath, ...).  `patch.install()` routes exactly these calls to the reference's own function; any
+    other error -- including a NotImplementedError raised inside torch or CUDA -- propagates."""
 
 
 class LdmError(RuntimeError):

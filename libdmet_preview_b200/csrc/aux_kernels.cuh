@@ -275,6 +275,8 @@ ztranspose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int
 //         ncols = nao*nao (full) or nao*(nao+1)/2 (`packed`: Hermitian lower triangle, row-major pack_tril)
 //   out   (naux, nao, nao) complex128; aux rows >= rows are zero ("aux basis drop")
 //   swapped: the entry belongs to the pair (k_j, k_i): out[L][p][q] = conj(src[L][q][p])
+//   conj_all: the entry belongs to the time-reversed pair (-k_i, -k_j) [or, with swapped, (-k_j, -k_i)]: the
+//         result is conjugated once more (files that keep only one member of each time-reversal pair)
 // One CTA per 32x32 output tile of one auxiliary row: the source tile (the mirrored one for swapped entries and for
 // the upper triangle of packed entries) is read with its fast index along threadIdx.x, parked in shared memory and
 // written out transposed / conjugated as needed, so that both the loads and the stores are coalesced.  HBM-bound:
@@ -289,7 +291,7 @@ __device__ __forceinline__ double2 stored_elem(const void* __restrict__ src, siz
 template <bool REAL>
 __global__ void __launch_bounds__(256)
 unpack_stored_kernel(const void* __restrict__ src, double2* __restrict__ out, int naux, int rows, int nao,
-                     long long ncols, int packed, int swapped) {
+                     long long ncols, int packed, int swapped, int conj_all) {
     __shared__ double2 tile[32][33];
     const int p0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
     // source tile: rows r0.., columns c0.. of the (nao x nao) matrix the entry describes
@@ -330,6 +332,7 @@ unpack_stored_kernel(const void* __restrict__ src, double2* __restrict__ out, in
                 } else {
                     v = tile[dy][threadIdx.x];
                 }
+                if (conj_all) v.y = -v.y;                  // entry of the time-reversed pair (-k_i, -k_j)
                 o[(size_t)p * nao + q] = v;
             }
         }
@@ -358,6 +361,32 @@ __global__ void zforms_kernel(const double2* __restrict__ B, double* __restrict_
         f[3 * ps] = -sum;
         f[4 * ps] = -dif;
     }
+}
+
+// Lower-triangular packing of a stack of square complex matrices, out[L][m(m+1)/2 + n] = in[L][m][n] (n <= m) --
+// PySCF `lib.pack_tril` as `transform_gdf_to_lo` applies it to the LO-basis GDF blocks it stores
+// (eri_transform.py:1386-1390): complex for k_i == k_j, real part only (with max|imag| reported) when both k-points
+// are Gamma.  One CTA per matrix; reads run along n, writes are contiguous.
+template <bool OUT_REAL>
+__global__ void __launch_bounds__(256)
+pack_tril_kernel(const double2* __restrict__ in, void* __restrict__ out, int n, long long npair,
+                 unsigned long long* imag_max) {
+    const double2* src = in + (size_t)blockIdx.x * n * n;
+    double im_max = 0.0;
+    for (long long P = threadIdx.x; P < npair; P += blockDim.x) {
+        int m = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+        while ((long long)(m + 1) * (m + 2) / 2 <= P) ++m;
+        while ((long long)m * (m + 1) / 2 > P) --m;
+        const int c = (int)(P - (long long)m * (m + 1) / 2);
+        const double2 v = src[(size_t)m * n + c];
+        if (OUT_REAL) {
+            static_cast<double*>(out)[(size_t)blockIdx.x * npair + P] = v.x;
+            im_max = fmax(im_max, fabs(v.y));
+        } else {
+            static_cast<double2*>(out)[(size_t)blockIdx.x * npair + P] = v;
+        }
+    }
+    if (OUT_REAL && imag_max) warp_atomic_max_abs(im_max, imag_max);
 }
 
 // real -> complex widening copy (basis in R-space is real; the GEMM operands are complex)

@@ -580,7 +580,7 @@ int ldm_ztranspose(ldm_handle h, void* stream, const void* in_d, void* out_d, in
 
 static int check_stored_shape(int naux, int rows, int nao, int64_t ncols, int flags, int* packed) {
     LDM_REQUIRE(naux > 0 && nao > 0 && rows >= 0 && rows <= naux, "stored entry: rows must lie in [0, naux]");
-    LDM_REQUIRE((flags & ~(LDM_STORED_SWAPPED | LDM_STORED_REAL)) == 0, "stored entry: unknown flags");
+    LDM_REQUIRE((flags & ~(LDM_STORED_SWAPPED | LDM_STORED_REAL | LDM_STORED_CONJ)) == 0, "stored entry: unknown flags");
     const int64_t full = (int64_t)nao * nao, tri = (int64_t)nao * (nao + 1) / 2;
     LDM_REQUIRE(ncols == full || ncols == tri, "stored entry: ncols must be nao*nao or nao*(nao+1)/2");
     *packed = (ncols != full) ? 1 : 0;
@@ -597,14 +597,40 @@ int ldm_unpack_stored(ldm_handle h, void* stream, const void* src_d, void* out_d
     const int nt = (nao + 31) / 32;
     dim3 grid(nt, nt, std::min(naux, 32768));
     const int swapped = (flags & LDM_STORED_SWAPPED) ? 1 : 0;
+    const int conj = (flags & LDM_STORED_CONJ) ? 1 : 0;
     if (flags & LDM_STORED_REAL)
         unpack_stored_kernel<true><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
-            src_d, static_cast<double2*>(out_d), naux, rows, nao, (long long)ncols, packed, swapped);
+            src_d, static_cast<double2*>(out_d), naux, rows, nao, (long long)ncols, packed, swapped, conj);
     else
         unpack_stored_kernel<false><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
-            src_d, static_cast<double2*>(out_d), naux, rows, nao, (long long)ncols, packed, swapped);
+            src_d, static_cast<double2*>(out_d), naux, rows, nao, (long long)ncols, packed, swapped, conj);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
+    return 0;
+}
+
+int ldm_pack_tril(ldm_handle h, void* stream, const void* in_d, void* out_d, int rows, int n, int out_real,
+                  double* imag_max_h) {
+    LDM_REQUIRE(h && in_d && out_d && rows > 0 && n > 0, "arguments");
+    LDM_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long npair = (long long)n * (n + 1) / 2;
+    if (out_real) {
+        LDM_CUDA_OK(cudaMemsetAsync(h->imag_d, 0, sizeof(unsigned long long), st));
+        pack_tril_kernel<true><<<rows, 256, 0, st>>>(static_cast<const double2*>(in_d), out_d, n, npair, h->imag_d);
+    } else {
+        pack_tril_kernel<false><<<rows, 256, 0, st>>>(static_cast<const double2*>(in_d), out_d, n, npair, nullptr);
+    }
+    LDM_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    if (out_real && imag_max_h) {
+        unsigned long long bits = 0;
+        LDM_CUDA_OK(cudaMemcpyAsync(&bits, h->imag_d, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        LDM_CUDA_OK(cudaStreamSynchronize(st));
+        double v;
+        std::memcpy(&v, &bits, sizeof(v));
+        *imag_max_h = v;
+    }
     return 0;
 }
 

@@ -172,6 +172,16 @@ class Device(object):
                                       int(bool(conj)), float(scale)))
         return out
 
+    def pack_tril(self, x, out_real=False):
+        """(rows, n, n) complex128 -> (rows, n(n+1)/2) lower triangles, complex or (out_real) real part + max|imag|"""
+        assert x.dtype == torch.complex128 and x.is_contiguous() and x.dim() == 3 and x.shape[1] == x.shape[2]
+        rows, n = x.shape[0], x.shape[1]
+        out = self.empty((rows, n * (n + 1) // 2), torch.float64 if out_real else torch.complex128)
+        imag = C.c_double(0.0)
+        check(self.lib.ldm_pack_tril(self.h, self.stream, _ptr(x), _ptr(out), rows, n, int(bool(out_real)),
+                                     C.byref(imag) if out_real else None))
+        return out, (imag.value if out_real else None)
+
     def d2z(self, x):
         assert x.dtype == torch.float64 and x.is_contiguous()
         out = self.empty(tuple(x.shape), torch.complex128)

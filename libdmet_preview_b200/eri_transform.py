@@ -892,15 +892,16 @@ def transform_gdf_to_lo(mydf, C_ao_lo, fname="gdf_ints_lo.h5", t_reversal_symm=T
         # S[L][m][n] = sum_p conj(C_i[p][m]) XT[L][n][p]
         dev.zgemm_tn(XT.reshape(1, naux * nlo, nao), CT, [[0, i, 0, 1]], S, rdiv=nlo, s_outer=nlo * nlo,
                      s_inner=1, s_col=nlo)
-        Lij = dev.to_host(S)
+        # storage rules of the reference, packed on the device so that only what is stored crosses PCIe
         both_gamma = max(np.abs(ks[i]).max(), np.abs(ks[j]).max()) < KPT_DIFF_TOL
-        if both_gamma:               # l.1386-1388
-            assert np.abs(Lij.imag).max() < ERI_IMAG_TOL
-            stored = _pack_rows(Lij.real)
-        elif i == j:                 # l.1389-1390
-            stored = _pack_rows(Lij)
+        if both_gamma:               # l.1386-1388: real lower triangles
+            packed, imag_max = dev.pack_tril(S, out_real=True)
+            assert imag_max < ERI_IMAG_TOL
+            stored = dev.to_host(packed).copy()
+        elif i == j:                 # l.1389-1390: complex lower triangles
+            stored = dev.to_host(dev.pack_tril(S)[0]).copy()
         else:
-            stored = Lij.reshape(naux, nlo * nlo).copy()
+            stored = dev.to_host(S).reshape(naux, nlo * nlo).copy()
         j3c[pos] = stored
         if mask[pos] != -1:          # l.1395-1396
             j3c[int(mask[pos])] = stored.conj()

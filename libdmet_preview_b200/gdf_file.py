@@ -30,6 +30,7 @@ _KPT_FILE_TOL = 1e-6     # PySCF kpts_helper.member tolerance (KPT_DIFF_TOL)
 
 STORED_SWAPPED = 1       # include/ldm_b200.h: LDM_STORED_SWAPPED
 STORED_REAL = 2          # LDM_STORED_REAL
+STORED_CONJ = 4          # LDM_STORED_CONJ: entry of the time-reversed pair (-k_i, -k_j), plain conjugate
 
 
 class StoredEntry(object):
@@ -55,6 +56,8 @@ class StoredEntry(object):
         if self.flags & STORED_SWAPPED:
             # full entry of the pair (k_j, k_i): conjugate transpose; packed one: plain conjugate (PySCF _load3c)
             full = full.conj().transpose(0, 2, 1) if a.shape[1] == nao * nao else full.conj()
+        if self.flags & STORED_CONJ:
+            full = full.conj()
         out[:rows] = full
         return out
 
@@ -139,6 +142,7 @@ class GDFFile(object):
         self.nkpts = len(kpts)
         self.kptij_idx = idx
         self._key = dict(zip(idx, keys))
+        self._minus = None
         # -- geometry
         if lattice_vectors is None:
             if cell is None:
@@ -167,6 +171,29 @@ class GDFFile(object):
             n2 = int(round(np.sqrt(ncol)))
             self.nao = n2 if n2 * n2 == ncol else int(round((np.sqrt(8 * ncol + 1) - 1) / 2))
         self._tril = None
+
+    def _resolve(self, ki, kj):
+        """(stored pair, flags) serving block (k_i, k_j): the pair itself; the swapped pair (conjugate transpose,
+        PySCF `_load3c`); or -- files that keep only one member of each time-reversal pair, as recent PySCF writes
+        them -- the pair (-k_i, -k_j) (plain conjugate, L(-k_i, -k_j) = conj L(k_i, k_j)) or (-k_j, -k_i)."""
+        if (ki, kj) in self._key:
+            return (ki, kj), 0
+        if (kj, ki) in self._key:
+            return (kj, ki), STORED_SWAPPED
+        if self._minus is None:
+            ks = np.asarray(self.kpts_scaled)
+            self._minus = []
+            for k in ks:
+                d = ks + k[None]
+                hit = np.flatnonzero(np.abs(d - np.round(d)).max(axis=1) < KPT_DIFF_TOL)
+                self._minus.append(int(hit[0]) if len(hit) else -1)
+        mi, mj = self._minus[ki], self._minus[kj]
+        if mi >= 0 and mj >= 0:
+            if (mi, mj) in self._key:
+                return (mi, mj), STORED_CONJ
+            if (mj, mi) in self._key:
+                return (mj, mi), STORED_SWAPPED | STORED_CONJ
+        raise KeyError("k-point pair (%d, %d) is not stored in %s" % (ki, kj, self.path))
 
     # -- block assembly (PySCF _load3c / _KPair3CLoader + sr_loop's unpack and cast) ---------------------------
     def _stored(self, key, out):
@@ -207,12 +234,8 @@ class GDFFile(object):
         `StoredEntry` whose `.data` is the (rows, ncols) view and `.flags` say how the device has to interpret it
         (`ldm_eri_block_stored`).  Single-segment entries are one positioned read; column segments are read one
         after the other into their column ranges."""
-        if (ki, kj) in self._key:
-            key, flags = self._key[(ki, kj)], 0
-        elif (kj, ki) in self._key:
-            key, flags = self._key[(kj, ki)], STORED_SWAPPED
-        else:
-            raise KeyError("k-point pair (%d, %d) is not stored in %s" % (ki, kj, self.path))
+        pair, flags = self._resolve(ki, kj)
+        key = self._key[pair]
         segs = _segments(self._f[self.label][key])
         dtype = np.dtype(segs[0].dtype)
         if dtype not in (np.dtype(np.complex128), np.dtype(np.float64)):
@@ -245,14 +268,15 @@ class GDFFile(object):
         nao = self.nao
         if out is None:
             out = np.empty((self.naux, nao, nao), dtype=np.complex128)
-        if (ki, kj) in self._key:
-            rows, _ = self._stored(self._key[(ki, kj)], out)
-        elif (kj, ki) in self._key:
-            tmp = np.empty((self.naux_of[(kj, ki)], nao, nao), dtype=np.complex128)
-            rows, _ = self._stored(self._key[(kj, ki)], tmp)
-            np.conjugate(tmp.transpose(0, 2, 1), out=out[:rows])
+        pair, flags = self._resolve(ki, kj)
+        if not flags & STORED_SWAPPED:
+            rows, _ = self._stored(self._key[pair], out)
         else:
-            raise KeyError("k-point pair (%d, %d) is not stored in %s" % (ki, kj, self.path))
+            tmp = np.empty((self.naux_of[pair], nao, nao), dtype=np.complex128)
+            rows, _ = self._stored(self._key[pair], tmp)
+            np.conjugate(tmp.transpose(0, 2, 1), out=out[:rows])
+        if flags & STORED_CONJ:
+            np.conjugate(out[:rows], out=out[:rows])
         if rows < out.shape[0]:
             out[rows:] = 0.0
         return out

@@ -16,21 +16,25 @@ rebinds the names the reference's callers actually resolve (SURVEY.md section 8b
   * `libdmet.routine.spinless.get_emb_basis / embBasis / get_emb_Ham / embHam / get_H_dmet / transformResults` and
     `libdmet.basis_transform.eri_transform.get_emb_eri_gso` (resolved inside `spinless.__embHam2e` at call time)
 Non-GDF density-fitting objects keep going to the reference's own drivers, and every branch this package does not
-mirror (it raises `NotImplementedError` before doing any work of consequence) falls through to the reference's
-function.  `uninstall()` restores the originals.
+mirror falls through to the reference's function: those branches raise `UnsupportedBranch` (a NotImplementedError
+subclass) from argument checks at the top of the call, before the embedding ERI or anything else of consequence has
+been computed.  Only that exception triggers the fallback -- a NotImplementedError from torch or CUDA is a real
+failure and propagates.  `uninstall()` restores the originals.
 """
 import functools
+
+from ._lib import UnsupportedBranch
 
 _saved = {}
 
 
 def _with_fallback(ours, ref):
-    """`ours`, except that a branch we do not mirror (NotImplementedError) is served by the reference's function"""
+    """`ours`, except that a branch we do not mirror (UnsupportedBranch) is served by the reference's function"""
     @functools.wraps(ours)
     def call(*args, **kwargs):
         try:
             return ours(*args, **kwargs)
-        except NotImplementedError:
+        except UnsupportedBranch:
             return ref(*args, **kwargs)
     return call
 

@@ -13,6 +13,7 @@ import numpy as np
 import scipy.linalg as la
 import torch
 
+from ._lib import UnsupportedBranch
 from .device import get_device
 from . import eri_transform
 from .eri_transform import get_emb_eri, get_unit_eri
@@ -44,7 +45,7 @@ def get_emb_basis(lattice, rho=None, local=True, kind='svd', **kwargs):
     if rho is None:
         rho = lattice.rdm1_lo_R
     if not local:
-        raise NotImplementedError("non-local (particle-hole symmetric model) bath is outside the ab-initio path")
+        raise UnsupportedBranch("non-local (particle-hole symmetric model) bath is outside the ab-initio path")
     rho = rho.cpu().numpy() if isinstance(rho, torch.Tensor) else np.asarray(rho)
     if kind == 'svd':
         return _get_emb_basis_svd(lattice, rho.real, **kwargs)
@@ -67,7 +68,7 @@ def _get_emb_basis_svd(lattice, rdm1, **kwargs):
                nbath=None, localize_bath=None)
     opt.update({k: v for k, v in kwargs.items() if k in opt})
     if opt["localize_bath"] is not None:
-        raise NotImplementedError("bath localisation is only defined for model Hamiltonians in the reference")
+        raise UnsupportedBranch("bath localisation is only defined for model Hamiltonians in the reference")
     imp_idx, val_idx = list(opt["imp_idx"]), list(opt["val_idx"])
     ncells, nlo = int(lattice.ncells), int(lattice.nscsites)
     ntot = ncells * nlo
@@ -117,7 +118,7 @@ def _get_emb_basis_eig(lattice, rdm1, **kwargs):
                localize_bath=None)
     opt.update({k: v for k, v in kwargs.items() if k in opt})
     if opt["localize_bath"] is not None:
-        raise NotImplementedError("bath localisation is only defined for model Hamiltonians in the reference")
+        raise UnsupportedBranch("bath localisation is only defined for model Hamiltonians in the reference")
     imp_idx, val_idx = list(opt["imp_idx"]), list(opt["val_idx"])
     ncells, nlo = int(lattice.ncells), int(lattice.nscsites)
     ntot = ncells * nlo
@@ -278,7 +279,7 @@ def get_veff_dev(rdm1_emb, eri4_blocks):
 def get_veff(rdm1, eri, hyb=1.0):
     """slater.py:478-523 (HF branch), numpy in / numpy out."""
     if hyb != 1.0:
-        raise NotImplementedError("DFT / hybrid branches are outside the hot path")
+        raise UnsupportedBranch("DFT / hybrid branches are outside the hot path")
     rdm1 = np.asarray(rdm1, dtype=np.double)
     if rdm1.ndim == 2:
         rdm1 = rdm1[None]
@@ -307,7 +308,7 @@ def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwar
     """slater.py:372-476, ab-initio branch (438-472).  Returns (H2 numpy in the requested symmetry,
     s4 device blocks for the J/K step)."""
     if getattr(lattice, "is_model", False):
-        raise NotImplementedError("model Hamiltonians are outside the ab-initio hot path")
+        raise UnsupportedBranch("model Hamiltonians are outside the ab-initio hot path")
     nbasis = basis.shape[-1]
     eri_symmetry = lattice.eri_symmetry
     cell, mydf, C_ao_lo = lattice.cell, lattice.df, lattice.C_ao_lo
@@ -344,11 +345,11 @@ def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwar
 def _embHam1e(lattice, basis, vcor, H2_emb, eri4_blocks, int_bath=True, add_vcor=False, **kwargs):
     """slater.py:525-688, interacting-bath HF branch (590-605, 639-643).  Side effect: lattice.JK_core."""
     if not int_bath:
-        raise NotImplementedError("the non-interacting-bath one-body branch is outside the hot path "
+        raise UnsupportedBranch("the non-interacting-bath one-body branch is outside the hot path "
                                   "(its ERI is available through get_unit_eri / unit2emb)")
     for flag in ("dft", "qsgw"):
         if kwargs.get(flag, False):
-            raise NotImplementedError("%s branch is outside the hot path" % flag)
+            raise UnsupportedBranch("%s branch is outside the hot path" % flag)
     spin = basis.shape[0]
     nbasis = basis.shape[-1]
     bk = _BasisK(lattice.R2k_basis(basis))                               # l.533
@@ -377,17 +378,41 @@ def _embHam1e(lattice, basis, vcor, H2_emb, eri4_blocks, int_bath=True, add_vcor
     return H1, ovlp_emb
 
 
+def _check_supported(lattice, kwargs):
+    """branches `get_emb_Ham` does not mirror are refused HERE, before any ERI work, so that `patch.install()` can
+    hand the call to the reference without the embedding ERI having been built twice"""
+    if getattr(lattice, "is_model", False) and kwargs.get("H2_given", None) is None \
+            and kwargs.get("H2_fname", None) is None:
+        raise UnsupportedBranch("model Hamiltonians are outside the ab-initio hot path")
+    if not kwargs.get("int_bath", True):
+        raise UnsupportedBranch("the non-interacting-bath one-body branch is outside the hot path "
+                                "(its ERI is available through get_unit_eri / unit2emb)")
+    for flag in ("dft", "qsgw"):
+        if kwargs.get(flag, False):
+            raise UnsupportedBranch("%s branch is outside the hot path" % flag)
+
+
+def load_H2(fname):
+    """the embedding ERI a previous run stored in an HDF5 file, dataset 'emb_eri' (slater.py:349-355)"""
+    from . import h5lite
+    with h5lite.File(fname) as f:
+        return np.asarray(f["emb_eri"][...])
+
+
 def get_emb_Ham(lattice, basis, vcor, local=True, **kwargs):
-    """slater.py:320-370.  Returns (Integral, None); H2 blocks come in the order aa, bb, ab (l.461-462)."""
+    """slater.py:320-370.  Returns (Integral, None); H2 blocks come in the order aa, bb, ab (l.461-462).
+    `H2_given` / `H2_fname` supply the two-electron integrals instead of building them (l.346-358)."""
     basis = np.asarray(basis)
     spin = basis.shape[0]
     nbasis = basis.shape[-1]
+    _check_supported(lattice, kwargs)
     H2_given = kwargs.get("H2_given", None)
     blocks = None
     if H2_given is None:
         if kwargs.get("H2_fname", None) is not None:
-            raise NotImplementedError("loading H2 from HDF5 needs h5py, which this build does not depend on")
-        H2, blocks = _embHam2e(lattice, basis, vcor, local, **kwargs)
+            H2 = load_H2(kwargs["H2_fname"])
+        else:
+            H2, blocks = _embHam2e(lattice, basis, vcor, local, **kwargs)
     else:
         H2 = H2_given
     kw1 = {k: v for k, v in kwargs.items() if k != "last_aabb"}
@@ -457,7 +482,7 @@ def get_H_dmet(basis, lattice, ImpHam, last_dmu, imp_idx=None, dmu_idx=None, add
     is the fragment energy.  The branches that rebuild J/K from a global density matrix through the lattice
     mean-field object (`veff`, `rebuild_veff`) stay with the reference."""
     if veff is not None or rebuild_veff:
-        raise NotImplementedError("rebuilding JK_core from the global density needs the lattice mean-field object")
+        raise UnsupportedBranch("rebuilding JK_core from the global density needs the lattice mean-field object")
     basis = np.asarray(basis)
     spin = basis.shape[0]
     nbasis = basis.shape[-1]
@@ -548,7 +573,7 @@ def get_rho_glob_R(basis, lattice, rho_emb, symmetric=True, compact=True, sign=N
     else:
         frags = [(basis, lattice, rho_emb)]
     if sign is not None or not compact:
-        raise NotImplementedError("full-shape / signed global density matrices (particle-hole fragments) are "
+        raise UnsupportedBranch("full-shape / signed global density matrices (particle-hole fragments) are "
                                   "outside the ab-initio path")
     left, right, blocks = [], [], []
     spin = ncells = nlo = None
@@ -562,7 +587,7 @@ def get_rho_glob_R(basis, lattice, rho_emb, symmetric=True, compact=True, sign=N
         rho = add_spin_dim(rho, spin, non_spin_dim=2)
         imp = np.asarray(lat_f.imp_idx, dtype=int)
         if imp.size and (imp.min() < 0 or imp.max() >= nlo):
-            raise NotImplementedError("impurity orbitals outside the first cell")
+            raise UnsupportedBranch("impurity orbitals outside the first cell")
         mask = np.zeros(nlo)
         mask[imp] = 0.5
         half = np.broadcast_to((mask[None, :, None] * b[:, 0])[:, None], b.shape)         # 1/2 M C_0 for every cell

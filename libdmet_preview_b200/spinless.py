@@ -13,6 +13,7 @@ import warnings
 import numpy as np
 import torch
 
+from ._lib import UnsupportedBranch
 from .device import get_device
 from .eri_transform import get_emb_eri_gso, separate_basis
 from .fourier import IMAG_DISCARD_TOL
@@ -48,7 +49,7 @@ def _gso_finish(lattice, bath, imp, env, env_is_imp, env_is_alpha, orth, kwargs)
     """shared tail of both constructions: virtual rows zeroed + Loewdin, columns ordered by decreasing alpha
     (particle) weight, identity on the impurity rows (spinless.py:124-162 / 240-271)"""
     if kwargs.get("localize_bath") is not None:
-        raise NotImplementedError("bath localisation is only defined for model Hamiltonians in the reference")
+        raise UnsupportedBranch("bath localisation is only defined for model Hamiltonians in the reference")
     if not orth:
         raise NotImplementedError                                   # l.129-131
     ncells, nso = int(lattice.ncells), 2 * int(lattice.nscsites)
@@ -73,7 +74,7 @@ def get_emb_basis(lattice, GRho, local=True, kind='svd', **kwargs):
     if not local:
         raise NotImplementedError
     if kwargs.get("bath_opt", False):
-        raise NotImplementedError("bath optimisation (get_emb_basis_opt) is outside the path")
+        raise UnsupportedBranch("bath optimisation (get_emb_basis_opt) is outside the path")
     rdm1 = np.asarray(GRho.cpu() if isinstance(GRho, torch.Tensor) else GRho).real
     ncells, nso = int(lattice.ncells), 2 * int(lattice.nscsites)
     assert rdm1.shape == (ncells, nso, nso)
@@ -94,7 +95,7 @@ def get_emb_basis(lattice, GRho, local=True, kind='svd', **kwargs):
         occ, vec = la.eigh(lattice.expand(rdm1)[env][:, env])
         bath = vec[:, (np.abs(occ) > tol_bath) & (np.abs(1.0 - occ) > tol_bath)]
     elif kind == 'ph':
-        raise NotImplementedError("particle-hole bath (model Hamiltonians) is outside the ab-initio path")
+        raise UnsupportedBranch("particle-hole bath (model Hamiltonians) is outside the ab-initio path")
     else:
         raise ValueError("get_emb_basis: Unknown kind %s" % kind)
     return _gso_finish(lattice, np.array(bath), imp, env, env_is_imp, env_is_alpha, orth, kwargs)
@@ -175,9 +176,9 @@ def foldRho_k(GRho_k, basis_k):
 def _embHam2e(lattice, basis, vcor, local, int_bath=True, last_aabb=True, **kwargs):
     """spinless.py:464-558, ab-initio interacting bath: one GSO ERI block, built in s4 on the device"""
     if getattr(lattice, "is_model", False):
-        raise NotImplementedError("model Hamiltonians are outside the ab-initio hot path")
+        raise UnsupportedBranch("model Hamiltonians are outside the ab-initio hot path")
     if not int_bath:
-        raise NotImplementedError("the reference's non-interacting-bath GSO branch feeds a (1, npair, npair) unit ERI "
+        raise UnsupportedBranch("the reference's non-interacting-bath GSO branch feeds a (1, npair, npair) unit ERI "
                                   "to a 3-block unit2emb (spinless_helper.py:288-313) and cannot run; not mirrored")
     nb = basis.shape[-1]
     eri4 = get_emb_eri_gso(lattice.cell, lattice.df, C_ao_lo=lattice.C_ao_lo, basis=basis,
@@ -201,7 +202,7 @@ def _embHam1e(lattice, basis, vcor, mu, H2_emb, eri4_blocks, int_bath=True, add_
     """spinless.py:560-726, interacting bath, Hartree-Fock: H1 = T[fock_hf] - (J - K)[folded density] - mu N
     (+ optional local terms); side effect lattice.JK_core.  Returns (H1 (1, nbasis, nbasis), ovlp_emb)."""
     if not int_bath or kwargs.get("dft", False):
-        raise NotImplementedError("only the interacting-bath Hartree-Fock branch is mirrored")
+        raise UnsupportedBranch("only the interacting-bath Hartree-Fock branch is mirrored")
     if vcor is not None and hasattr(vcor, "islocal") and not vcor.islocal():
         raise Exception("nonlocal correlation potential cannot be treated in this routine")
     basis = np.asarray(basis)
@@ -246,10 +247,16 @@ def get_emb_Ham(lattice, basis, vcor, mu, local=True, **kwargs):
     nb = basis.shape[-1]
     H2_given = kwargs.get("H2_given", None)
     blocks = None
+    # unsupported branches are refused before any ERI work (see slater._check_supported)
+    if getattr(lattice, "is_model", False) and H2_given is None and kwargs.get("H2_fname", None) is None:
+        raise UnsupportedBranch("model Hamiltonians are outside the ab-initio hot path")
+    if not kwargs.get("int_bath", True) or kwargs.get("dft", False):
+        raise UnsupportedBranch("only the interacting-bath Hartree-Fock branch is mirrored")
     if H2_given is None:
         if kwargs.get("H2_fname", None) is not None:
-            raise NotImplementedError("loading H2 from HDF5 needs h5py, which this build does not depend on")
-        H2, blocks = _embHam2e(lattice, basis, vcor, local, **kwargs)
+            H2 = slater.load_H2(kwargs["H2_fname"])                      # spinless.py:446-449
+        else:
+            H2, blocks = _embHam2e(lattice, basis, vcor, local, **kwargs)
     else:
         H2 = H2_given
     kw1 = {k: v for k, v in kwargs.items() if k != "last_aabb"}
@@ -275,7 +282,7 @@ def transformResults(GRhoEmb, E, lattice, basis, ImpHam, H1e, mu, fit_ghf=False,
     re-evaluated with the chemical potentials added back, half of JK_core removed and the impurity weights
     applied."""
     if fit_ghf:
-        raise NotImplementedError("fit_ghf (several bases) belongs to the correlation-potential fitting")
+        raise UnsupportedBranch("fit_ghf (several bases) belongs to the correlation-potential fitting")
     basis = np.asarray(basis)
     ncells, nso, nbasis = basis.shape
     nao = nso // 2
@@ -319,7 +326,7 @@ def get_H_dmet(basis, lattice, ImpHam, last_dmu=None, mu=None, imp_idx=None, dmu
     the device (`transform_trans_inv_k`), two-body weights by `ldm_scale_eri`; the branches that rebuild J/K from a
     global density matrix through the lattice mean-field object stay with the reference."""
     if veff is not None or rebuild_veff:
-        raise NotImplementedError("rebuilding JK_core from the global density needs the lattice mean-field object")
+        raise UnsupportedBranch("rebuilding JK_core from the global density needs the lattice mean-field object")
     basis = np.asarray(basis)
     nbasis = basis.shape[-1]
     basis_Ra, basis_Rb = separate_basis(basis)

@@ -64,3 +64,49 @@ def test_header_is_plain_c_and_links_from_c(built_lib, tmp_path):
                            str(src), "-o", exe, "-L", libdir, "-l:libldm_b200.so", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe]).decode().split()
     assert int(out[0]) >= 100 and out[1] == "ok"
+
+
+def test_unsupported_branches_are_refused_before_any_work():
+    """`patch.install()` hands branches this package does not mirror to the reference; they must be refused by an
+    argument check (no device, no ERI build) with the dedicated exception -- a plain NotImplementedError from torch
+    or CUDA must NOT trigger that fallback"""
+    import types
+    import numpy as np
+    from libdmet_preview_b200 import slater, spinless, patch
+    from libdmet_preview_b200._lib import UnsupportedBranch
+    assert issubclass(UnsupportedBranch, NotImplementedError)
+    lat = types.SimpleNamespace(is_model=False)
+    basis = np.zeros((1, 2, 3, 4))
+    for kw in (dict(int_bath=False), dict(dft=True), dict(qsgw=True)):
+        try:
+            slater.get_emb_Ham(lat, basis, None, **kw)
+            raise AssertionError("not refused: %s" % kw)
+        except UnsupportedBranch:
+            pass
+    try:
+        slater.get_emb_Ham(types.SimpleNamespace(is_model=True), basis, None)
+        raise AssertionError("model Hamiltonian not refused")
+    except UnsupportedBranch:
+        pass
+    try:
+        spinless.get_emb_Ham(lat, basis[0], None, 0.0, int_bath=False)
+        raise AssertionError("GSO non-interacting bath not refused")
+    except UnsupportedBranch:
+        pass
+    calls = []
+
+    def ours(x):
+        if x == 0:
+            raise UnsupportedBranch("not mirrored")
+        raise NotImplementedError("a real failure")
+
+    f = patch._with_fallback(ours, lambda x: calls.append(x) or "reference")
+    assert f(0) == "reference" and calls == [0]
+    try:
+        f(1)
+        raise AssertionError("a plain NotImplementedError must propagate")
+    except UnsupportedBranch:
+        raise AssertionError("wrong exception type")
+    except NotImplementedError:
+        pass
+    assert calls == [0]

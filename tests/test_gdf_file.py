@@ -235,3 +235,45 @@ def test_run_items_ships_stored_entries_when_the_build_can_unpack(tmp_path):
                     full[7:] = 0
                 assert np.array_equal(L, full[l0:l1])
             assert rec.bytes < len(want) * (l1 - l0) * 16 * 16       # packed / real / dropped rows: fewer bytes
+
+
+def _trs_reduced_pairs(gdf):
+    """one member of every time-reversal class {(i, j), (j, i), (-i, -j), (-j, -i)} of k-point pairs"""
+    nk = len(gdf.kpts_scaled)
+    seen, keep = set(), []
+    for i in range(nk):
+        for j in range(nk):
+            if (i, j) in seen:
+                continue
+            mi, mj = gdf.minus[i], gdf.minus[j]
+            seen.update({(i, j), (j, i), (mi, mj), (mj, mi)})
+            keep.append((i, j))
+    return keep
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+def test_time_reversal_reduced_file(tmp_path, version):
+    """a cderi file that keeps one member of each time-reversal class of pairs (what recent PySCF writes): a missing
+    pair is served as the conjugate of (-k_i, -k_j), or the transpose of (-k_j, -k_i) -- on the host route (`load`) and
+    as a stored entry + flags for the device unpacker (`load_stored` / `StoredEntry.expand`)"""
+    gdf = synthetic.SyntheticGDF([2, 1, 3], 5, 9, seed=21)
+    pairs = _trs_reduced_pairs(gdf)
+    nk = len(gdf.kpts_scaled)
+    assert len(pairs) < nk * (nk + 1) // 2
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, version=version, pairs=pairs, nsegments=2)
+    f = GDFFile(path, cell=gdf.cell, kpts=gdf.kpts)
+    buf = np.empty((gdf.naux, gdf.nao, gdf.nao), dtype=np.complex128)
+    flags_seen = set()
+    for i in range(nk):
+        for j in range(nk):
+            want = gdf.load(i, j)
+            assert np.array_equal(f.load(i, j), want)
+            e = f.load_stored(i, j, 0, gdf.naux, buf)
+            flags_seen.add(e.flags & 5)
+            assert np.array_equal(e.expand(gdf.naux, gdf.nao), want)
+    assert flags_seen == {0, 1, 4, 5}
+    # the whole pipeline's host logic over such a file (oracle arithmetic)
+    C = synthetic.make_C_ao_lo(gdf.kmesh, gdf.nao, seed=3)
+    basis = synthetic.make_emb_basis(gdf.kmesh, gdf.nao, 4, seed=4)
+    assert np.abs(oe.get_emb_eri(gdf.cell, f, C_ao_lo=C, basis=basis) -
+                  oe.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis)).max() < 1e-13

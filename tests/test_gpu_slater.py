@@ -76,6 +76,23 @@ def test_embham(dev, spin, sym):
     # H2_given re-entry
     Ham2, _ = slater.embHam(L, basis, None, H2_given=Ref.H2["ccdd"])
     assert np.abs(Ham2.H1["cd"] - Ref.H1["cd"]).max() < TOL
+    # H2_fname re-entry: integrals stored by an earlier run in the dataset 'emb_eri' (slater.py:349-355)
+    import tempfile, os
+    from libdmet_preview_b200 import h5lite
+    with tempfile.TemporaryDirectory() as d:
+        fn = os.path.join(d, "emb_eri.h5")
+        with h5lite.Writer(fn) as w:
+            w["emb_eri"] = Ham.H2["ccdd"]
+        Ham3, _ = slater.embHam(L, basis, None, H2_fname=fn)
+    assert np.array_equal(Ham3.H2["ccdd"], Ham.H2["ccdd"])
+    assert np.abs(Ham3.H1["cd"] - Ham.H1["cd"]).max() < 1e-12
+    # branches that are not mirrored are refused before any ERI work (UnsupportedBranch <: NotImplementedError)
+    from libdmet_preview_b200._lib import UnsupportedBranch
+    n0 = dev.launch_count()
+    for kw in (dict(int_bath=False), dict(dft=True), dict(qsgw=True)):
+        with pytest.raises(UnsupportedBranch):
+            slater.embHam(L, basis, None, **kw)
+    assert dev.launch_count() == n0
     # non-interacting bath ERI: unit ERI zero-padded (slater.py:464-472)
     H2u, _ = slater._embHam2e(L, basis, None, True, int_bath=False)
     Ru = osl._embHam2e(O, basis, None, True, int_bath=False)

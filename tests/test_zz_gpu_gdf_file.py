@@ -89,14 +89,14 @@ def test_unpack_stored_kernel(dev, nao, naux, rows):
     """ldm_unpack_stored against its host twin (gdf_file.StoredEntry.expand): full / Hermitian-packed, complex /
     real, stored / swapped pair, fewer stored rows than naux -- bit for bit (pure data movement + sign flips)"""
     import torch
-    from libdmet_preview_b200.gdf_file import StoredEntry, STORED_SWAPPED
+    from libdmet_preview_b200.gdf_file import StoredEntry, STORED_SWAPPED, STORED_CONJ
     rng = np.random.default_rng(nao)
     for ncols in (nao * nao, nao * (nao + 1) // 2):
         for real in (False, True):
             a = rng.standard_normal((rows, ncols))
             if not real:
                 a = a + 1j * rng.standard_normal((rows, ncols))
-            for flags in (0, STORED_SWAPPED):
+            for flags in (0, STORED_SWAPPED, STORED_CONJ, STORED_SWAPPED | STORED_CONJ):
                 want = StoredEntry(a, flags | (2 if real else 0)).expand(naux, nao)
                 out = dev.empty((naux, nao, nao), torch.complex128)
                 out.fill_(float("nan"))
@@ -120,6 +120,31 @@ def test_host_and_device_unpack_agree(dev, tmp_path, monkeypatch):
     e_host = et.get_emb_eri(gdf.cell, f, C_ao_lo=C, basis=basis, stats=st_host)
     assert np.array_equal(e_dev, e_host) and np.abs(e_split - e_host).max() < TOL
     assert 0 < st_dev["h2d_bytes"] < st_host["h2d_bytes"]
+
+
+def test_time_reversal_reduced_file_on_the_device(dev, tmp_path):
+    """a cderi file holding one member of each time-reversal class of pairs: missing pairs are served from
+    (-k_i, -k_j) / (-k_j, -k_i) with LDM_STORED_CONJ, unpacked on the device -- same ERI as from memory"""
+    from libdmet_preview_b200 import eri_transform as et
+    from libdmet_preview_b200.gdf_file import GDFFile, write_gdf_file
+    gdf, C, basis = problem([2, 1, 3], 7, 12, 6)
+    nk = len(gdf.kpts_scaled)
+    seen, pairs = set(), []
+    for i in range(nk):
+        for j in range(nk):
+            if (i, j) not in seen:
+                mi, mj = gdf.minus[i], gdf.minus[j]
+                seen.update({(i, j), (j, i), (mi, mj), (mj, mi)})
+                pairs.append((i, j))
+    path = write_gdf_file(str(tmp_path / "cderi.h5"), gdf, pairs=pairs)
+    f = GDFFile(path, cell=gdf.cell, kpts=gdf.kpts)
+    ref = et.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, source="host")
+    for trs in (True, False):
+        got = et.get_emb_eri(gdf.cell, f, C_ao_lo=C, basis=basis, t_reversal_symm=trs)
+        assert np.abs(got - ref).max() < TOL
+    res = et.ResidentGDF(f)
+    assert np.abs(et.get_emb_eri(gdf.cell, res, C_ao_lo=C, basis=basis) - ref).max() < TOL
+    f.close()
 
 
 def test_rho_glob_vs_reference_python(dev):
