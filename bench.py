@@ -820,6 +820,8 @@ def gdf_file_leg(args):
                 "cold_seconds": t_cold, "warm_seconds": t_warm, "resident_seconds": t_res,
                 "device_generated_seconds": t_mem, "cold_tflops": (F1 + F3) / t_cold / 1e12,
                 "cold_file_gbs": size / t_cold / 1e9, "h2d_bytes": st_cold.get("h2d_bytes"),
+                "cold_wait_for_file_s": st_cold.get("provider_wait_s"), "cold_block_calls_s": st_cold.get("block_call_s"),
+                "warm_wait_for_file_s": st_warm.get("provider_wait_s"), "warm_block_calls_s": st_warm.get("block_call_s"),
                 "page_cache_fraction_before_cold_run": frac,
                 "cold_equals_warm_bitwise": bool(np.array_equal(e_cold, e_warm)),
                 "max_abs_vs_device_generated": float(np.abs(e_cold - e_mem).max()),

@@ -33,8 +33,8 @@ const char* ldm_last_error(void);
 int ldm_create(int device, ldm_handle* out);
 int ldm_destroy(ldm_handle h);
 /* run-time options of a handle.  "zgemm_3m": 1 (default; environment LDM_ZGEMM_3M=0 changes the default) evaluates
- * complex products on the tensor cores with three real multiplications (P1 = ArBr, P2 = AiBi, P3 = (Ar+Ai)(Br+Bi)),
- * 0 with the classical four.  Takes effect for the next ldm_zgemm_tn / ldm_eri_begin.  Returns the previous value in
+ * complex products on the tensor cores with three real multiplications -- k1 = (Ar + Ai) Br, k2 = Ar (Bi - Br),
+ * k3 = Ai (Br + Bi), Re = k1 - k3, Im = k1 + k2, as in csrc/zgemm_tn.cuh -- 0 with the classical four.  Takes effect for the next ldm_zgemm_tn / ldm_eri_begin.  Returns the previous value in
  * *old_value when that pointer is not NULL. */
 int ldm_set_option(ldm_handle h, const char* name, int value, int* old_value);
 /* pinned host memory for staging GDF blocks (cudaHostAlloc / cudaFreeHost) */

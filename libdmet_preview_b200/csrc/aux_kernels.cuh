@@ -930,13 +930,15 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
         // ---- J: row dot product and column updates ----
         const double ddP = dd[P];
         double racc = 0.0;
+        const int Pi = (int)P;
 #pragma unroll
         for (int c = 0; c < NCMAX; ++c) {
-            const long long q = t + (long long)c * T;
-            if (q <= P) {
+            if (c * T > Pi) break;                                  // warp-uniform: the row ends before this chunk
+            const int q = t + c * T;
+            if (q <= Pi) {
                 const double e = srow[q];
                 racc = fma(e, __ldg(dd + q), racc);
-                if (q < P) colacc[c] = fma(e, ddP, colacc[c]);
+                colacc[c] = fma(q < Pi ? e : 0.0, ddP, colacc[c]);
             }
         }
 #pragma unroll
@@ -960,22 +962,38 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
             const int l0 = g * half, l1 = min(ne, l0 + half);
             double y1 = 0.0, y2 = 0.0, z1 = 0.0, z2 = 0.0;
             if (k < ne) {
-                int offA = k * (k + 1) / 2 + l0;                    // M[k][l], l <= k
-                int offB = l0 * (l0 + 1) / 2 + k;                   // M[l][k], l > k
-                int l = l0;
-                for (; l + 1 < l1; l += 2) {
-                    const double m0 = srow[l <= k ? offA : offB];
-                    const double m1 = srow[l + 1 <= k ? offA + 1 : offB + l + 1];
+                // l <= k: consecutive words of packed row k
+                const int la = l0, lb = min(l1, k + 1);
+                const double* ra = srow + k * (k + 1) / 2;
+                int l = la;
+                for (; l + 1 < lb; l += 2) {
+                    const double m0 = ra[l], m1 = ra[l + 1];
                     const double2 d0 = sD[l], d1 = sD[l + 1];
                     y1 = fma(m0, d0.x, y1);
                     y2 = fma(m0, d0.y, y2);
                     z1 = fma(m1, d1.x, z1);
                     z2 = fma(m1, d1.y, z2);
-                    offA += 2;
-                    offB += 2 * l + 3;
+                }
+                if (l < lb) {
+                    const double m0 = ra[l];
+                    const double2 d0 = sD[l];
+                    y1 = fma(m0, d0.x, y1);
+                    y2 = fma(m0, d0.y, y2);
+                }
+                // l > k: column k, word l(l+1)/2 + k
+                l = max(l0, k + 1);
+                int off = l * (l + 1) / 2 + k;
+                for (; l + 1 < l1; l += 2) {
+                    const double m0 = srow[off], m1 = srow[off + l + 1];
+                    const double2 d0 = sD[l], d1 = sD[l + 1];
+                    y1 = fma(m0, d0.x, y1);
+                    y2 = fma(m0, d0.y, y2);
+                    z1 = fma(m1, d1.x, z1);
+                    z2 = fma(m1, d1.y, z2);
+                    off += 2 * l + 3;
                 }
                 if (l < l1) {
-                    const double m0 = srow[l <= k ? offA : offB];
+                    const double m0 = srow[off];
                     const double2 d0 = sD[l];
                     y1 = fma(m0, d0.x, y1);
                     y2 = fma(m0, d0.y, y2);
@@ -1002,16 +1020,36 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
 }
 
 // vj_packed[q] = vj_row[q] + sum over the row blocks B >= q / JKT_ROWS of their column partials (fixed order)
-__global__ void jk_tri_jsum_kernel(const double* __restrict__ vj_row, const double* __restrict__ jpart,
-                                   double* __restrict__ vj_packed, long long npair) {
+__global__ void __launch_bounds__(256)
+jk_tri_jsum_kernel(const double* __restrict__ vj_row, const double* __restrict__ jpart,
+                   double* __restrict__ vj_packed, long long npair) {
+    // 32 consecutive columns per CTA (threadIdx.x), the row blocks dealt to the 8 warps (threadIdx.y) with four
+    // independent loads in flight each; the eight partial sums are added in a fixed order
+    __shared__ double part[8][33];
     const long long nblk = (npair + JKT_ROWS - 1) / JKT_ROWS;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npair;
-         q += (long long)gridDim.x * blockDim.x) {
-        double s = vj_row[q];
-        for (long long B = q / JKT_ROWS; B < nblk; ++B) {
-            const long long Phi = min(npair, (B + 1) * JKT_ROWS) - 1;
-            if (q < Phi) s += jpart[B * npair + q];
+    const long long q = (long long)blockIdx.x * 32 + threadIdx.x;
+    const int w = threadIdx.y;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (q < npair) {
+        // block B holds a value for column q iff q < (last row of B) ; B >= q / JKT_ROWS, and for B == q / JKT_ROWS
+        // only if q is not that block's last row
+        long long B = q / JKT_ROWS;
+        if (q >= min(npair, (B + 1) * JKT_ROWS) - 1) ++B;
+        B += w;
+        for (; B + 24 < nblk; B += 32) {
+            s0 += jpart[B * npair + q];
+            s1 += jpart[(B + 8) * npair + q];
+            s2 += jpart[(B + 16) * npair + q];
+            s3 += jpart[(B + 24) * npair + q];
         }
+        for (; B < nblk; B += 8) s0 += jpart[B * npair + q];
+    }
+    part[w][threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && q < npair) {
+        double s = vj_row[q];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) s += part[x][threadIdx.x];
         vj_packed[q] = s;
     }
 }

@@ -797,8 +797,7 @@ int ldm_jk_s4_symm(ldm_handle h, void* stream, const double* eri4_d, const doubl
         jk_tri_kernel<160><<<(unsigned)nblk, 320, smem, st>>>(eri4_d, dm_d, dd, vj_row, jpart, kpart, n, npair, wk,
                                                              rowbuf_words);
     LDM_CUDA_OK(cudaGetLastError());
-    jk_tri_jsum_kernel<<<(unsigned)std::min<long long>((npair + 127) / 128, 4096), 128, 0, st>>>(vj_row, jpart,
-                                                                                                  vj_packed, npair);
+    jk_tri_jsum_kernel<<<(unsigned)((npair + 31) / 32), dim3(32, 8), 0, st>>>(vj_row, jpart, vj_packed, npair);
     LDM_CUDA_OK(cudaGetLastError());
     unpack_sym_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(vj_packed, vj_d, n);
     LDM_CUDA_OK(cudaGetLastError());

@@ -9,6 +9,7 @@ What runs where
 There is no CPU fallback; the module raises if the CUDA library is missing.
 """
 import ctypes as C
+import time
 import warnings
 
 import numpy as np
@@ -381,12 +382,18 @@ def _host_block(provider, ki, kj, l0, l1, naux_full):
     return L[l0:l1]                      # leading-index slice of a C-contiguous block: still contiguous
 
 
+_STAGING_POOL = {}          # shape -> (shape, buffers, tensors): page-locking ~100 MB costs tens of ms, so the buffers of
+                            # a provider that has gone away (a cderi file reopened per call) serve the next one
+
+
 def _staging_buffers(provider, count):
     """`count` host buffers of one GDF block each, page-locked when a CUDA device is present (so that the H2D copy in
     `ldm_eri_block_host` is a single DMA transfer instead of a staged pageable copy); kept on the provider and
     reused by later calls"""
     shape = (int(provider.naux), int(provider.nao), int(provider.nao))
     have = getattr(provider, "_staging", None)
+    if have is None:
+        have = _STAGING_POOL.get(shape)
     if have is None or have[0] != shape or len(have[1]) < count:
         pin = torch.cuda.is_available()
         keep = []
@@ -396,6 +403,9 @@ def _staging_buffers(provider, count):
             keep.append(t)
             bufs.append(t.numpy())
         have = (shape, bufs, keep)
+        _STAGING_POOL.clear()                       # one shape at a time: the pool must not pin memory without bound
+        _STAGING_POOL[shape] = have
+    if getattr(provider, "_staging", None) is not have:
         try:
             provider._staging = have
         except AttributeError:
@@ -464,7 +474,7 @@ class _Prefetcher(object):
             self.free.put(None)
 
 
-def run_items(build, provider, schedule, items, source="auto", store_map=None, prefetch=2):
+def run_items(build, provider, schedule, items, source="auto", store_map=None, prefetch=3, timing=None):
     """Feed the (k_i, k_j) blocks of `items` -- (unit index, l0, l1) with one common aux range -- to an open build.
     source: "host"      provider.load(ki, kj)[l0:l1] -> host array -> H2D inside the call (blocks are loaded
                         `prefetch` ahead on a background thread)
@@ -492,13 +502,18 @@ def run_items(build, provider, schedule, items, source="auto", store_map=None, p
                     else:
                         build.block_host(ki, kj, sym, _host_block(provider, ki, kj, l0, l1, provider.naux))
                 elif source == "host":
+                    t0 = time.perf_counter()
                     blk = pre.next() if pre is not None else _host_block(provider, ki, kj, l0, l1, provider.naux)
+                    t1 = time.perf_counter()
                     if pre is not None and pre.stored:
                         build.block_stored(ki, kj, sym, blk)
                     else:
                         build.block_host(ki, kj, sym, blk)
                     if pre is not None:
                         pre.done(blk)
+                    if timing is not None:       # where a host-fed build spends its wall time
+                        timing["provider_wait_s"] = timing.get("provider_wait_s", 0.0) + (t1 - t0)
+                        timing["block_call_s"] = timing.get("block_call_s", 0.0) + (time.perf_counter() - t1)
                 elif source == "synth":
                     build.block_synth(ki, kj, sym, provider.keys(ki, kj), provider.scale, l0)
                 elif source == "store":
@@ -561,7 +576,7 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
                 t, _ = provider.store_for(l0, l1, nwant)
                 if t is not None:
                     b.set_store(t)
-            run_items(b, provider, schedule, sub, source, store_map)
+            run_items(b, provider, schedule, sub, source, store_map, timing=stats)
             if stats is not None:
                 st = b.stats()
                 tot["launches"] += st["launches"]

@@ -19,10 +19,13 @@ from oracle import pyscf_lib as olib
 
 
 def gapped_hcore(kmesh, nao, nocc, seed=0, gap=3.0, hop=0.35):
-    """Hermitian hcore[k] with time-reversal structure: `nocc` levels near -gap/2, the rest near +gap/2, coupled by a
-    random Hermitian matrix -- a band insulator, so plain SCF iterations converge to machine precision"""
+    """Hermitian hcore[k] with time-reversal structure and a gap at the Fermi level of BOTH spin channels: with
+    nocc = (n_a, n_b) occupied bands per k-point, n_b levels sit near -gap, n_a - n_b near 0 and the rest near +gap,
+    coupled by a random Hermitian matrix -- a (magnetic) band insulator, so SCF iterations converge to machine
+    precision and filling the lowest levels per k-point equals filling them over the whole zone"""
+    na, nb = (max(nocc), min(nocc)) if np.ndim(nocc) else (nocc, nocc)
     h = synthetic.make_hermitian_k(kmesh, nao, seed=900 + seed, scale=hop)
-    level = np.diag([-0.5 * gap] * nocc + [0.5 * gap] * (nao - nocc)).astype(np.complex128)
+    level = np.diag([-gap] * nb + [0.0] * (na - nb) + [gap] * (nao - na)).astype(np.complex128)
     return h + level[None]
 
 
@@ -46,11 +49,19 @@ def lattice_scf(gdf, hcore_k, nocc, tol=1e-13, max_iter=200):
         return np.asarray([o_fourier.FFTtoK(lat.extract_stripe(v[s]), kmesh) for s in range(spin)])
 
     def density(fock):
+        """lowest occ[s] * nk levels of the whole zone per spin channel (what mfd.HF's assignocc fills)"""
         rho = np.zeros((spin, nk, nao, nao), dtype=np.complex128)
         for s in range(spin):
+            ec = [np.linalg.eigh(fock[s, k]) for k in range(nk)]
+            levels = np.sort(np.concatenate([e for e, _ in ec]))
+            nel = occ[s] * nk
+            if nel < len(levels) and levels[nel] - levels[nel - 1] < 1e-6:
+                raise RuntimeError("synthetic mean field is not gapped: choose other parameters")
+            mu = 0.5 * (levels[nel - 1] + levels[min(nel, len(levels) - 1)])
             for k in range(nk):
-                e, c = np.linalg.eigh(fock[s, k])
-                rho[s, k] = c[:, :occ[s]].dot(c[:, :occ[s]].conj().T)
+                e, c = ec[k]
+                co = c[:, e < mu]
+                rho[s, k] = co.dot(co.conj().T)
         return rho
 
     rho = density(np.asarray([hcore_k] * spin))

@@ -97,6 +97,15 @@ class _HostStandIn(object):
     def to_host(self, t):
         return t.numpy().copy()
 
+    def pack_tril(self, x, out_real=False):
+        """ldm_pack_tril: out[L][m(m+1)/2 + c] = x[L][m][c], c <= m; real part + max|imag| when out_real"""
+        import torch
+        r, c = np.tril_indices(x.shape[-1])
+        p = x.numpy()[:, r, c]
+        if out_real:
+            return torch.from_numpy(np.ascontiguousarray(p.real)), float(np.abs(p.imag).max())
+        return torch.from_numpy(np.ascontiguousarray(p)), None
+
     def unpack_stored(self, src, naux, nao, flags=0, out=None):
         import torch
         from libdmet_preview_b200.gdf_file import StoredEntry

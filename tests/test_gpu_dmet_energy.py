@@ -30,7 +30,7 @@ def test_converged_dmet_energy(dev, kmesh, nao, naux, nocc, sym):
     gdf = synthetic.SyntheticGDF(kmesh, nao, naux, seed=61)
     spin = 2 if np.ndim(nocc) else 1
     restricted = spin == 1
-    hcore = hd.gapped_hcore(kmesh, nao, max(nocc) if spin == 2 else nocc, seed=3)
+    hcore = hd.gapped_hcore(kmesh, nao, nocc, seed=3)
     mf = hd.lattice_scf(gdf, hcore, nocc)
     C = synthetic.make_C_ao_lo(kmesh, nao, seed=62, spin=(2 if spin == 2 else None))
     ovlp = np.asarray([np.eye(nao, dtype=np.complex128)] * len(gdf.kpts_scaled))

@@ -16,8 +16,7 @@ from oracle import mfd as o_mfd
 def build(kmesh, nao, naux, nocc, seed=0, sym=4):
     gdf = synthetic.SyntheticGDF(kmesh, nao, naux, seed=40 + seed)
     spin = 2 if np.ndim(nocc) else 1
-    n_lo = max(nocc) if spin == 2 else nocc
-    hcore = hd.gapped_hcore(kmesh, nao, n_lo, seed=seed)
+    hcore = hd.gapped_hcore(kmesh, nao, nocc, seed=seed)
     mf = hd.lattice_scf(gdf, hcore, nocc)
     C = synthetic.make_C_ao_lo(kmesh, nao, seed=50 + seed, spin=(2 if spin == 2 else None))
     nk = len(gdf.kpts_scaled)
