@@ -119,3 +119,91 @@ def test_rank_items_balance_and_coverage():
             assert r[0][0] == 0 and r[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
         loads = [sum(costs[u] * (l1 - l0) / 1000.0 for (u, l0, l1) in p) for p in parts]
         assert max(loads) <= 1.03 * sum(loads) / world       # 8 GPUs: 8.0x ideal instead of 7.2x with whole kL units
+
+
+def _sharded_worker(rank, world, port, out):
+    """`dist.get_emb_eri_sharded` end to end over gloo with the device entry points it drives (`build_CT`,
+    `build_CT_gso`, `emb_eri_device`, `finalize_eri`, `to_host`) restated with the oracle: exercises the argument
+    handling, the GSO route, the blocks-per-launch keyword, the reduction and what the non-root ranks return"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        from libdmet_preview_b200 import dist as ldist, eri_transform as et, device
+        from oracle import eri_transform as oe
+        from helpers import gso_basis
+        seen = {}
+
+        def build_CT(provider, C_ao_lo=None, basis=None, C_ao_eo=None, unit_eri=False):
+            Cemb = oe.build_C_ao_emb(provider, C_ao_lo, basis, C_ao_eo, unit_eri)
+            return torch.from_numpy(np.ascontiguousarray(Cemb.transpose(0, 1, 3, 2)))
+
+        def build_CT_gso(provider, C_ao_lo, basis=None, basis_k=None, unit_eri=False):
+            from oracle.make_basis import add_spin_dim, multiply_basis
+            from oracle.fourier import get_phase_R2k_scaled
+            C2 = add_spin_dim(np.asarray(C_ao_lo), 2)
+            bk = oe.get_basis_k(basis[None], get_phase_R2k_scaled(provider.kmesh, provider.kpts_scaled))[0]
+            half = bk.shape[1] // 2
+            bk = np.asarray((bk[:, :half], bk[:, half:]))
+            Cemb = multiply_basis(C2, bk) / (len(provider.kpts_scaled) ** 0.75)
+            return torch.from_numpy(np.ascontiguousarray(Cemb.transpose(0, 1, 3, 2)))
+
+        def emb_eri_device(provider, CT, schedule=None, items=None, source="auto", group=None, kl_group=None,
+                           stats=None, gso=False, imag=None, **kw):
+            seen["group"] = group
+            nk = CT.shape[1]
+            C_ao_eo = CT.numpy().transpose(0, 1, 3, 2) * nk ** 0.75
+            npair = CT.shape[2] * (CT.shape[2] + 1) // 2
+            nsp = CT.shape[0]
+            eri = np.zeros((1 if gso else nsp * (nsp + 1) // 2, npair, npair))
+            for (u, l0, l1) in items:
+                kL = schedule.units[u][0]
+                sl = SlicedProvider(provider, l0, l1)
+                if gso:
+                    w = oe.get_weights_t_reversal(provider.kpts_scaled)
+                    L = oe._accumulate_Lij_s4(sl, C_ao_eo / nk ** 0.75, kL, np.asarray(provider.kpts_scaled, float),
+                                              1e-6, True, 240)
+                    oe._Lij_s4_to_eri_gso(L, eri, weight=w[kL], t_reversal_symm=True)
+                else:
+                    eri += oe.get_emb_eri_fast_gdf(None, sl, C_ao_eo=C_ao_eo, kL_subset={kL}, restore=False)
+            return torch.from_numpy(eri)
+
+        et.build_CT, et.build_CT_gso, et.emb_eri_device = build_CT, build_CT_gso, emb_eri_device
+        et.finalize_eri = lambda eri, nemb, sym, nsp: torch.from_numpy(oe.eri_restore(eri.numpy(), sym, nemb))
+        device.get_device = lambda *a: types.SimpleNamespace(to_host=lambda t: t.numpy())
+        gdf, C, basis = problem([1, 2, 2], 5, 12, 6, spin=2)
+        got = ldist.get_emb_eri_sharded(gdf.cell, gdf, C_ao_lo=C, basis=basis, symmetry=1, group=3, nsplit=2)
+        assert seen["group"] == 3                            # the serial keyword names the blocks per launch here too
+        gb = gso_basis([1, 2, 2], 5, 7, seed=1)
+        got_gso = ldist.get_emb_eri_sharded(gdf.cell, gdf, C_ao_lo=C, basis=gb, gso=True)
+        try:
+            ldist.get_emb_eri_sharded(gdf.cell, gdf, C_ao_lo=C, basis=gb, gso=True, incore=False)
+            raise AssertionError("GSO outcore must be refused")
+        except NotImplementedError:
+            pass
+        if rank == 0:
+            ref = oe.get_emb_eri(gdf.cell, gdf, C_ao_lo=C, basis=basis, symmetry=1)
+            ref_gso = oe.get_emb_eri_gso(gdf.cell, gdf, C_ao_lo=C, basis=gb)
+            out.put((float(np.abs(got - ref).max()), float(np.abs(got_gso - ref_gso).max())))
+        else:
+            assert got is None and got_gso is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_entry_point_host_logic_incl_gso():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    e1, e2 = out.get(timeout=5)
+    assert e1 < 1e-10 and e2 < 1e-10
