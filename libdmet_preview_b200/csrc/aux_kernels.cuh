@@ -864,40 +864,45 @@ jk_rows_bulk_kernel(const double* __restrict__ eri4, const double* __restrict__ 
 // unused tail of packed row i is zero-filled, so the walk needs no predicates).  Deterministic: no atomics.
 // ----------------------------------------------------------------------------------------------------------
 constexpr int JKT_ROWS = 32;
+constexpr int JKT_MAXBUF = 8;
 
 template <int NP>
 __global__ void __launch_bounds__(2 * NP, 1)
 jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, const double* __restrict__ dd,
               double* __restrict__ vj_row, double* __restrict__ jpart, double* __restrict__ kpart, int n,
-              long long npair, int with_k, int rowbuf_words) {
+              long long npair, int with_k, int arena_words) {
     constexpr int T = 2 * NP;
     constexpr int NCMAX = (NP * (NP + 1) / 2 + T - 1) / T;
-    extern __shared__ __align__(16) double jkt_rows[];         // 2 buffers of rowbuf_words
+    extern __shared__ __align__(16) double jkt_rows[];         // arena_words doubles: a ring of row slots
     __shared__ double2 sD[NP];                                 // (D[i][l], D[j][l])
     __shared__ double sY[2][2][NP];
     __shared__ double sJ[T / 32];
-    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ __align__(8) unsigned long long bars[JKT_MAXBUF];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const long long nblk = (npair + JKT_ROWS - 1) / JKT_ROWS;
     const long long B = nblk - 1 - blockIdx.x;                  // heaviest blocks first
     const long long Phi = min(npair, (B + 1) * JKT_ROWS) - 1, Plo = B * JKT_ROWS;
     const int nrows = (int)(Phi - Plo + 1);
     const long long total = npair * npair;
+    // Ring of row slots sized for the longest row of this block (packed row i of the truncated matrix may be zero
+    // filled up to its end, hence the extra i + 1 words).  Short rows get a deep ring: a row costs at least one DRAM
+    // round trip, so enough of them must be in flight to keep the SM's share of the bandwidth busy.
+    const int slot_words = (int)((Phi + 2 * NP + 6) & ~1LL);
+    const int nbuf = max(2, min(JKT_MAXBUF, arena_words / slot_words));
     if (t == 0) {
-        mbar_init(smem_u32(&bars[0]), 1);
-        mbar_init(smem_u32(&bars[1]), 1);
+        for (int x = 0; x < JKT_MAXBUF; ++x) mbar_init(smem_u32(&bars[x]), 1);
         mbar_fence_init();
     }
     __syncthreads();
 
-    // bring the words 0..P of row P into buffer b (16-byte aligned enclosing range by bulk copy, a tail that would
+    // bring the words 0..P of row P into slot b (16-byte aligned enclosing range by bulk copy, a tail that would
     // cross the end of the tensor by plain loads)
     auto issue = [&](long long P, int b) {
         const long long off = P * npair, a0 = off & ~1LL;
         const int head = (int)(off - a0);
         long long cnt = ((long long)head + P + 2) & ~1LL;
         if (a0 + cnt > total) cnt -= 2;
-        double* buf = jkt_rows + (size_t)b * rowbuf_words;
+        double* buf = jkt_rows + (size_t)b * slot_words;
         if (t == 0) {
             fence_proxy_async_smem();
             const uint32_t bar = smem_u32(&bars[b]);
@@ -913,20 +918,20 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
 #pragma unroll
     for (int c = 0; c < NCMAX; ++c) colacc[c] = 0.0;
 
-    issue(Phi, 0);
+    for (int r = 0; r < min(nbuf - 1, nrows); ++r) issue(Phi - r, r);
     __syncthreads();                                                // plain-load tail of the very last row
     for (int r = 0; r < nrows; ++r) {
         const long long P = Phi - r;
-        const int b = r & 1;
-        if (r + 1 < nrows) issue(P - 1, b ^ 1);
+        const int b = r % nbuf;
+        if (r + nbuf - 1 < nrows) issue(P - (nbuf - 1), (r + nbuf - 1) % nbuf);   // the slot row r - 1 has just left
         int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
         while ((long long)(i + 1) * (i + 2) / 2 <= P) ++i;
         while ((long long)i * (i + 1) / 2 > P) --i;
         const int j = (int)(P - (long long)i * (i + 1) / 2);
         for (int l = t; l < NP; l += T)
             sD[l] = l < n ? make_double2(D[(size_t)i * n + l], D[(size_t)j * n + l]) : make_double2(0.0, 0.0);
-        double* srow = jkt_rows + (size_t)b * rowbuf_words + (int)((P * npair) & 1LL);
-        mbar_wait(smem_u32(&bars[b]), (uint32_t)((r >> 1) & 1));
+        double* srow = jkt_rows + (size_t)b * slot_words + (int)((P * npair) & 1LL);
+        mbar_wait(smem_u32(&bars[b]), (uint32_t)((r / nbuf) & 1));
         // ---- J: row dot product and column updates ----
         const double ddP = dd[P];
         double racc = 0.0;
@@ -953,7 +958,7 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
         if (with_k) {
             // the rest of packed row i is not part of the truncated matrix; the word Q = P counts half
             const int rowend = (i + 1) * (i + 2) / 2;
-            for (long long q = P + 1 + t; q < rowend; q += T) srow[q] = 0.0;
+            for (int q = Pi + 1 + t; q < rowend; q += T) srow[q] = 0.0;
             if (t == T - 1) srow[P] *= 0.5;
             __syncthreads();
             const int ne = i + 1;
@@ -962,38 +967,22 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
             const int l0 = g * half, l1 = min(ne, l0 + half);
             double y1 = 0.0, y2 = 0.0, z1 = 0.0, z2 = 0.0;
             if (k < ne) {
-                // l <= k: consecutive words of packed row k
-                const int la = l0, lb = min(l1, k + 1);
-                const double* ra = srow + k * (k + 1) / 2;
-                int l = la;
-                for (; l + 1 < lb; l += 2) {
-                    const double m0 = ra[l], m1 = ra[l + 1];
-                    const double2 d0 = sD[l], d1 = sD[l + 1];
-                    y1 = fma(m0, d0.x, y1);
-                    y2 = fma(m0, d0.y, y2);
-                    z1 = fma(m1, d1.x, z1);
-                    z2 = fma(m1, d1.y, z2);
-                }
-                if (l < lb) {
-                    const double m0 = ra[l];
-                    const double2 d0 = sD[l];
-                    y1 = fma(m0, d0.x, y1);
-                    y2 = fma(m0, d0.y, y2);
-                }
-                // l > k: column k, word l(l+1)/2 + k
-                l = max(l0, k + 1);
-                int off = l * (l + 1) / 2 + k;
+                int offA = k * (k + 1) / 2 + l0;                    // M[k][l], l <= k
+                int offB = l0 * (l0 + 1) / 2 + k;                   // M[l][k], l > k
+                int l = l0;
                 for (; l + 1 < l1; l += 2) {
-                    const double m0 = srow[off], m1 = srow[off + l + 1];
+                    const double m0 = srow[l <= k ? offA : offB];
+                    const double m1 = srow[l + 1 <= k ? offA + 1 : offB + l + 1];
                     const double2 d0 = sD[l], d1 = sD[l + 1];
                     y1 = fma(m0, d0.x, y1);
                     y2 = fma(m0, d0.y, y2);
                     z1 = fma(m1, d1.x, z1);
                     z2 = fma(m1, d1.y, z2);
-                    off += 2 * l + 3;
+                    offA += 2;
+                    offB += 2 * l + 3;
                 }
                 if (l < l1) {
-                    const double m0 = srow[off];
+                    const double m0 = srow[l <= k ? offA : offB];
                     const double2 d0 = sD[l];
                     y1 = fma(m0, d0.x, y1);
                     y2 = fma(m0, d0.y, y2);
@@ -1007,8 +996,8 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
                 kpart[(P * 2 + v) * n + kk] = sY[0][v][kk] + sY[1][v][kk];
             }
         }
-        fence_proxy_async_smem();        // generic writes to this buffer (zero fill, halving) before the next bulk copy
-        __syncthreads();                                            // buffers, sD, sY, sJ free for the next row
+        fence_proxy_async_smem();        // generic writes to this slot (zero fill, halving) before the next bulk copy
+        __syncthreads();                                            // slot, sD, sY, sJ free for the next row
     }
     // column partials of this block: every column below the block's last row
     double* jp = jpart + (size_t)B * npair;

@@ -373,6 +373,10 @@ static int launch_zgemm(ldm_handle h, cudaStream_t st, const ZConfig& cfg, const
     static const bool skip_pad = getenv("LDM_ZGEMM_SKIP_PAD") ? atoi(getenv("LDM_ZGEMM_SKIP_PAD")) != 0 : true;
     if (!skip_pad) a.fb_last = fb_full;
     a.rotate = (cfg.m3 && a.fb_last < fb_full && a.tiles_n > 1 && grid % a.tiles_n == 0) ? 1 : 0;
+    // stagger of the two consumer warps of each SM sub-partition (zgemm_tn.cuh); only worth it when a CTA has a few
+    // tiles to work through
+    static const int skew = getenv("LDM_ZGEMM_SKEW") ? atoi(getenv("LDM_ZGEMM_SKEW")) : 4000;
+    a.skew_clocks = (ntiles >= 4LL * grid) ? skew : 0;
     cfg.kernel<<<grid, cfg.threads, cfg.smem, st>>>(tmA, tmB, a);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
@@ -749,10 +753,14 @@ int ldm_jk_s4_symm(ldm_handle h, void* stream, const double* eri4_d, const doubl
     LDM_REQUIRE(h && eri4_d && dm_d && vj_d, "null pointer");
     LDM_REQUIRE(n > 0 && n <= 3200, "orbital count out of range");
     const long long npair = (long long)n * (n + 1) / 2;
-    const int rowbuf_words = (int)((npair + 4) & ~1LL);
-    const size_t smem = (size_t)2 * rowbuf_words * 8;
-    // two row buffers must fit beside ~10 KB of static shared memory; otherwise the general kernels serve the call
-    if (n <= 16 || n > 160 || smem > 214 * 1024) return ldm_jk_s4(h, stream, eri4_d, dm_d, vj_d, vk_d, n);
+    // ring of row slots in shared memory: at least two slots of the longest row (+ its zero-filled tail) must fit
+    // beside ~10 KB of static shared memory; otherwise the general kernels serve the call
+    const int NPt = n <= 64 ? 64 : (n <= 128 ? 128 : 160);
+    const int slot_max = (int)((npair - 1 + 2 * NPt + 6) & ~1LL);
+    const int rowbuf_words = 214 * 1024 / 8;          // the whole arena: short rows get a deeper ring
+    const size_t smem = (size_t)rowbuf_words * 8;
+    if (n <= 16 || n > 160 || 2LL * slot_max * 8 > 214 * 1024)
+        return ldm_jk_s4(h, stream, eri4_d, dm_d, vj_d, vk_d, n);
     LDM_CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long long nblk = (npair + JKT_ROWS - 1) / JKT_ROWS;

@@ -59,6 +59,7 @@ struct ZGemmArgs {
     int fb_last;                 // 3M: column fragments (8 columns each) of the LAST n-tile that hold columns < N;
                                  // the others are all padding and their MMAs are skipped (N = 150 as 80 + 72)
     int rotate;                  // 1: the n-tile a CTA takes alternates from wave to wave (see tile_coords)
+    int skew_clocks;             // head start (SM clocks) of the first consumer warp of every SM sub-partition
 };
 
 // tile index -> (batch entry, m-tile, n-tile).  n runs fastest, so the tiles_n CTAs that share an A tile run side
@@ -155,6 +156,19 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     // ===================== MMA consumers =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // Warps w and w + 4 share an SM sub-partition and its FP64 tensor pipe.  One warp alone can issue a DMMA every
+    // 16 clocks, i.e. keep that pipe full; started together, the two run in lockstep for the whole kernel and reach
+    // every k-step boundary, stage hand-over and -- above all -- every epilogue at the same time, leaving the pipe
+    // idle (ncu: 83 % active, the per-tile code is 6 % of the consumers' time, k-step and stage boundaries 8 %).  A
+    // one-off head start for one warp of each pair makes them alternate like a ping-pong schedule: while one
+    // writes its tile out the other has the pipe to itself, so the idle phases of one are filled by the other.
+    // Nothing re-synchronises the two (each waits only on TMA barriers), so the stagger persists; the stage ring
+    // bounds it.
+    if (args.skew_clocks > 0 && T::NCONS == 8 && warp >= 4) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < args.skew_clocks) {
+        }
+    }
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
     const int pg = (g >> 1) | ((g & 1) << 2);
