@@ -794,12 +794,23 @@ jk_rows_bulk_kernel(const double* __restrict__ eri4, const double* __restrict__ 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double jacc = 0.0, jacc2 = 0.0;
     {
-        long long q = threadIdx.x;
-        for (; q + blockDim.x < npair; q += 2 * blockDim.x) {
-            jacc = fma(srow[q], dd[q], jacc);
-            jacc2 = fma(srow[q + blockDim.x], dd[q + blockDim.x], jacc2);
+        // eight independent dd loads (L2) in flight per thread; a two-way unrolled chain exposed their latency
+        constexpr int CH = 8;
+        for (long long q0 = threadIdx.x; q0 < npair; q0 += (long long)CH * blockDim.x) {
+            double e[CH], gq[CH];
+#pragma unroll
+            for (int x = 0; x < CH; ++x) {
+                const long long q = q0 + (long long)x * blockDim.x;
+                const bool in = q < npair;
+                e[x] = in ? srow[q] : 0.0;
+                gq[x] = in ? __ldg(dd + q) : 0.0;
+            }
+#pragma unroll
+            for (int x = 0; x < CH; x += 2) {
+                jacc = fma(e[x], gq[x], jacc);
+                jacc2 = fma(e[x + 1], gq[x + 1], jacc2);
+            }
         }
-        if (q < npair) jacc = fma(srow[q], dd[q], jacc);
         jacc += jacc2;
     }
 #pragma unroll
@@ -936,14 +947,27 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
         const double ddP = dd[P];
         double racc = 0.0;
         const int Pi = (int)P;
+        // eight independent (row word, dd) load pairs are issued before their first use: a load / FMA chain per
+        // word would expose one L2 round trip per word (dd does not fit beside the row slots in L1)
+        constexpr int CH = 8;
 #pragma unroll
-        for (int c = 0; c < NCMAX; ++c) {
-            if (c * T > Pi) break;                                  // warp-uniform: the row ends before this chunk
-            const int q = t + c * T;
-            if (q <= Pi) {
-                const double e = srow[q];
-                racc = fma(e, __ldg(dd + q), racc);
-                colacc[c] = fma(q < Pi ? e : 0.0, ddP, colacc[c]);
+        for (int c0 = 0; c0 < NCMAX; c0 += CH) {
+            if (c0 * T > Pi) break;                                 // warp-uniform: the row ends before this chunk
+            double e[CH], gq[CH];
+#pragma unroll
+            for (int x = 0; x < CH; ++x) {
+                const int q = t + (c0 + x) * T;
+                const bool in = (c0 + x < NCMAX) && q <= Pi;
+                e[x] = in ? srow[q] : 0.0;
+                gq[x] = in ? __ldg(dd + q) : 0.0;
+            }
+#pragma unroll
+            for (int x = 0; x < CH; ++x) {
+                if (c0 + x < NCMAX) {
+                    const int q = t + (c0 + x) * T;
+                    racc = fma(e[x], gq[x], racc);
+                    colacc[c0 + x] = fma(q < Pi ? e[x] : 0.0, ddP, colacc[c0 + x]);
+                }
             }
         }
 #pragma unroll

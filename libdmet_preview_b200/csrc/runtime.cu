@@ -366,17 +366,6 @@ static int launch_zgemm(ldm_handle h, cudaStream_t st, const ZConfig& cfg, const
     long long ntiles = (long long)a.tiles_m * a.tiles_n * nbatch;
     LDM_REQUIRE(ntiles < (1ll << 31), "too many tiles");
     int grid = (int)std::min<long long>(ntiles, h->num_sms);
-    // last n-tile: fragments that carry real columns; rotate the n index per wave when that tile is shorter and the
-    // groups of tiles_n neighbouring tiles never straddle two waves
-    const int fb_full = cfg.BN / 8;
-    a.fb_last = (N - (a.tiles_n - 1) * cfg.BN + 7) / 8;
-    static const bool skip_pad = getenv("LDM_ZGEMM_SKIP_PAD") ? atoi(getenv("LDM_ZGEMM_SKIP_PAD")) != 0 : true;
-    if (!skip_pad) a.fb_last = fb_full;
-    a.rotate = (cfg.m3 && a.fb_last < fb_full && a.tiles_n > 1 && grid % a.tiles_n == 0) ? 1 : 0;
-    // stagger of the two consumer warps of each SM sub-partition (zgemm_tn.cuh); only worth it when a CTA has a few
-    // tiles to work through
-    static const int skew = getenv("LDM_ZGEMM_SKEW") ? atoi(getenv("LDM_ZGEMM_SKEW")) : 4000;
-    a.skew_clocks = (ntiles >= 4LL * grid) ? skew : 0;
     cfg.kernel<<<grid, cfg.threads, cfg.smem, st>>>(tmA, tmB, a);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;

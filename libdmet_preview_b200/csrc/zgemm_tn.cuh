@@ -56,24 +56,7 @@ struct ZGemmArgs {
     double alpha;
     int accumulate;              // 1: C += result
     int tiles_m, tiles_n;
-    int fb_last;                 // 3M: column fragments (8 columns each) of the LAST n-tile that hold columns < N;
-                                 // the others are all padding and their MMAs are skipped (N = 150 as 80 + 72)
-    int rotate;                  // 1: the n-tile a CTA takes alternates from wave to wave (see tile_coords)
-    int skew_clocks;             // head start (SM clocks) of the first consumer warp of every SM sub-partition
 };
-
-// tile index -> (batch entry, m-tile, n-tile).  n runs fastest, so the tiles_n CTAs that share an A tile run side
-// by side and the second reader finds it in L2.  When the last n-tile is shorter than the others (fb_last) a fixed
-// assignment would give some CTAs only short tiles (gridDim.x is a multiple of tiles_n); with `rotate` the n index
-// is shifted by the wave number, which keeps the sharing and evens out the work.
-__device__ __forceinline__ void tile_coords(const ZGemmArgs& a, int tile, int tiles_per_batch, int& b, int& tm,
-                                            int& tn) {
-    b = tile / tiles_per_batch;
-    const int rem = tile - b * tiles_per_batch;
-    tm = rem / a.tiles_n;
-    tn = rem - tm * a.tiles_n;
-    if (a.rotate) tn = (tn + tile / (int)gridDim.x) % a.tiles_n;
-}
 
 constexpr int ZFORM_PLANES = 5;      // Br, D, S, -S, -D
 
@@ -125,8 +108,10 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                int b, tm, tn;
-                tile_coords(args, tile, tiles_per_batch, b, tm, tn);
+                const int b = tile / tiles_per_batch;
+                const int rem = tile - b * tiles_per_batch;
+                const int tm = rem / args.tiles_n;
+                const int tn = rem - tm * args.tiles_n;
                 const ZSeg* segs = args.segs + (size_t)b * args.nseg;
                 for (int s = 0; s < args.nseg; ++s) {
                     const int az = segs[s].az, bz = segs[s].bz;
@@ -156,19 +141,6 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     // ===================== MMA consumers =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // Warps w and w + 4 share an SM sub-partition and its FP64 tensor pipe.  One warp alone can issue a DMMA every
-    // 16 clocks, i.e. keep that pipe full; started together, the two run in lockstep for the whole kernel and reach
-    // every k-step boundary, stage hand-over and -- above all -- every epilogue at the same time, leaving the pipe
-    // idle (ncu: 83 % active, the per-tile code is 6 % of the consumers' time, k-step and stage boundaries 8 %).  A
-    // one-off head start for one warp of each pair makes them alternate like a ping-pong schedule: while one
-    // writes its tile out the other has the pipe to itself, so the idle phases of one are filled by the other.
-    // Nothing re-synchronises the two (each waits only on TMA barriers), so the stagger persists; the stage ring
-    // bounds it.
-    if (args.skew_clocks > 0 && T::NCONS == 8 && warp >= 4) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < args.skew_clocks) {
-        }
-    }
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
     const int pg = (g >> 1) | ((g & 1) << 2);
@@ -192,11 +164,11 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0, prev_stage = -1;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int b, tm, tn;
-        tile_coords(args, tile, tiles_per_batch, b, tm, tn);
+        const int b = tile / tiles_per_batch;
+        const int rem = tile - b * tiles_per_batch;
+        const int tm = rem / args.tiles_n;
+        const int tn = rem - tm * args.tiles_n;
         const ZSeg* segs = args.segs + (size_t)b * args.nseg;
-        // column fragments of this tile that are not all padding (warp-uniform)
-        const int fbe = (M3 && tn == args.tiles_n - 1) ? args.fb_last : FB;
 
         // 4M: cr = Re, ci = Im.   3M: cr = k1, ci = k2, cs = k3.
         double cr[FA][FB][2], ci[FA][FB][2], cs[M3 ? FA : 1][M3 ? FB : 1][2];
@@ -239,7 +211,6 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
                         for (int j = 0; j < FB; ++j) {
-                            if (j >= fbe) break;             // the remaining fragments are padding columns
                             if (j + 1 < FB) {
                                 g0 = lds64(b_addr + (j + 1) * 512);
                                 g1 = lds64(b_addr + (j + 1) * 512 + T::B_SLAB);
