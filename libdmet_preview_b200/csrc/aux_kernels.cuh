@@ -342,18 +342,21 @@ unpack_stored_kernel(const void* __restrict__ src, double2* __restrict__ out, in
 
 // The five real planes of the B operand that the 3-multiplication complex GEMM reads (zgemm_tn.cuh):
 //   F[5 z + 0] = Br, [5 z + 1] = Bi - Br, [5 z + 2] = Br + Bi, [5 z + 3] = -(Br + Bi), [5 z + 4] = Br - Bi
-// for every slice z of B (zb, N, K) complex; rows padded to Kp (even) doubles for the 16-byte TMA stride rule.
+// for every slice z of B (zb, N, K) complex.  Rows are Kp = K rounded up to a multiple of 8 doubles, zero padded, and
+// within every group of 8 the words are stored in the order k = 0,4,1,5,2,6,3,7, so that the two k the MMA lane
+// t needs in the two k-steps of a pipeline stage (t and t + 4) are one aligned 16-byte chunk.
 __global__ void zforms_kernel(const double2* __restrict__ B, double* __restrict__ F, long long rows, int K, int Kp,
                               long long N) {
-    const long long total = rows * K;
+    const long long total = rows * Kp;
     const long long ps = N * Kp;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const long long r = idx / K;
-        const int k = (int)(idx - r * K);
+        const long long r = idx / Kp;
+        const int k = (int)(idx - r * Kp);
         const long long z = r / N, n = r - z * N;
-        const double2 b = B[idx];
-        double* f = F + (5 * z * N + n) * Kp + k;
+        const double2 b = k < K ? B[r * K + k] : make_double2(0.0, 0.0);
+        const int kpos = (k & ~7) + 2 * (k & 3) + ((k >> 2) & 1);
+        double* f = F + (5 * z * N + n) * Kp + kpos;
         const double sum = b.x + b.y, dif = b.y - b.x;
         f[0] = b.x;
         f[ps] = dif;

@@ -166,6 +166,7 @@ struct ldm_context {
     void* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t ws_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t bforms_ev = nullptr;   // last use of the WS_BFORMS planes (ldm_zgemm_tn may be called on any stream)
+    cudaStream_t copy_st = nullptr;    // host -> device staging stream of the ERI pipeline, created once per handle
 };
 
 enum { WS_XT = 0, WS_SSYM = 1, WS_SPLN = 2, WS_PANEL = 3, WS_RING = 4, WS_BFORMS = 5, WS_CTFORMS = 6, WS_STORED = 7,
@@ -283,6 +284,7 @@ int ldm_destroy(ldm_handle h) {
     if (h->scratch_h) cudaFreeHost(h->scratch_h);
     if (h->imag_d) cudaFree(h->imag_d);
     if (h->bforms_ev) cudaEventDestroy(h->bforms_ev);
+    if (h->copy_st) cudaStreamDestroy(h->copy_st);
     if (h->jk_part_d) cudaFree(h->jk_part_d);
     delete h;
     return 0;
@@ -375,17 +377,17 @@ static int launch_zgemm(ldm_handle h, cudaStream_t st, const ZConfig& cfg, const
 // B operand of a 3M launch: build the five real planes in workspace `slot` and encode their tensor map
 static int make_bforms(ldm_handle h, cudaStream_t st, int slot, const void* B_d, int zb_count, int N, int K, int BN,
                        CUtensorMap* tm) {
-    const int Kp = K + (K & 1);
+    const int Kp = (K + 7) & ~7;        // zero-padded rows of whole 8-k groups (permuted order, see zforms_kernel)
     void* F = nullptr;
     int rc = ws_get(h, slot, (size_t)ZFORM_PLANES * zb_count * N * Kp * 8, &F);
     if (rc) return rc;
     const long long rows = (long long)zb_count * N;
-    const long long total = rows * K;
+    const long long total = rows * Kp;
     const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16);
     zforms_kernel<<<grid, 256, 0, st>>>(static_cast<const double2*>(B_d), static_cast<double*>(F), rows, K, Kp, N);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
-    return encode_tmap_f64_3d(tm, F, (uint64_t)K, (uint64_t)N, (uint64_t)ZFORM_PLANES * zb_count, 8ull * Kp,
+    return encode_tmap_f64_3d(tm, F, (uint64_t)Kp, (uint64_t)N, (uint64_t)ZFORM_PLANES * zb_count, 8ull * Kp,
                               8ull * Kp * N, 8, BN, 2);
 }
 
@@ -1023,7 +1025,8 @@ extern "C" {
 
 static int eri_begin_body(ldm_handle h, EriPlan* p, int nkpts, int nao, int naux, int neo, int nspin,
                           const void* CT_d) {
-    LDM_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
+    if (!h->copy_st) LDM_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
+    p->copy_st = h->copy_st;            // a small build must not pay for a stream creation
     const size_t xt_slice = (size_t)naux * neo * nao;
     const size_t s_elems = (size_t)nspin * naux * neo * neo;
     void* q = nullptr;
@@ -1329,7 +1332,6 @@ int ldm_eri_end(ldm_handle h) {
         }
     for (auto& e : p->ring_free)
         if (e) cudaEventDestroy(e);
-    if (p->copy_st) cudaStreamDestroy(p->copy_st);
     delete p;
     h->plan = nullptr;
     return 0;

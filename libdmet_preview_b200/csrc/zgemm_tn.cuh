@@ -30,8 +30,8 @@
 // (`zforms_kernel`: five real planes Br, D = Bi - Br, S = Br + Bi, -S, -D per slice; conj(B) uses Br, -S, -D), so
 // the producer just picks three planes per segment and the only extra arithmetic in the loop is one DADD per A
 // fragment -- DADDs share the FP64 pipe with the DMMAs and each one costs tensor issue slots.
-// 3M stage: A tile as above; B = 3 planes of BN rows x 64 B (8 real k), 64-byte swizzled by TMA so that the
-// LDS.64 fragment loads of 8 rows x 4 k are bank-conflict free.
+// 3M stage: A tile as above; B = 3 planes of BN rows x 64 B (8 real k in the order 0,4,1,5,2,6,3,7), 64-byte
+// swizzled by TMA; one LDS.128 per plane and column fragment delivers the words of both k-steps of the stage.
 #pragma once
 #include "common.cuh"
 
@@ -148,13 +148,15 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t a_row_off = (uint32_t)((wm * FA * 8 + pg) * 128);
     const uint32_t a_c0 = (uint32_t)((t ^ pg) * 16);       // k-step 0 ; k-step 1 is a_c0 ^ 64
     // 4M: (re, im) of k = 4 kk + t in slab kk.
-    // 3M: real word k = 4 kk + t of a 64-byte-swizzled row (16-byte chunk index xor ((row >> 1) & 3)).  64-bit
-    // shared loads are served per half-warp (MMA rows g = 0..3 / 4..7), so MMA column g reads tile row
-    // permB(g) = g with bits 1 and 2 swapped: rows {0,1,4,5} / {2,3,6,7} then fall into four different 32-byte bank
-    // groups.  The epilogue applies the same permutation to the output column.  kk = 1 is b_off ^ 32.
+    // 3M: the planes are stored with the 8 k of a stage in the order 0,4,1,5,2,6,3,7 (zforms_kernel), so the 16-byte
+    // chunk t of a 64-byte-swizzled row (chunk index xor ((row >> 1) & 3)) holds the words k = t and k = t + 4: ONE
+    // 128-bit load per plane and fragment serves both k-steps of the stage (half the shared-load instructions of a
+    // load per k-step -- every instruction a consumer warp issues between its DMMAs costs tensor-pipe time).  A
+    // quarter-warp covers tile rows 2r, 2r + 1 = 128 contiguous bytes: conflict free.  MMA column g reads tile row
+    // permB(g) = g with bits 1 and 2 swapped (kept from the 64-bit version; the epilogue applies the same
+    // permutation to the output column).
     const int pgb = (g & 1) | ((g & 2) << 1) | ((g & 4) >> 1);
-    const uint32_t b_off = M3 ? (uint32_t)(T::A_BYTES + (wn * FB * 8 + pgb) * 64 +
-                                           (((t >> 1) ^ ((pgb >> 1) & 3)) << 4) + (t & 1) * 8)
+    const uint32_t b_off = M3 ? (uint32_t)(T::A_BYTES + (wn * FB * 8 + pgb) * 64 + ((t ^ ((pgb >> 1) & 3)) << 4))
                               : (uint32_t)(T::A_BYTES + (wn * FB * 8 + g) * 64 + t * 16);
 
     // A stage is handed back to the producer one iteration late, right after the wait for the NEXT stage: the
@@ -191,42 +193,63 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (lane == 0) mbar_arrive(bar_base + 8 * (T::STAGES + prev_stage));
                 }
                 const uint32_t sbase = smem_base + stage * T::STAGE_BYTES;
+                if constexpr (M3) {
+                    // both k-steps of the stage: A fragments (re, im) of k = t and k = t + 4, then per column fragment
+                    // three 128-bit loads (one per plane) and six DMMAs.  Fragment j + 1 is in flight while the
+                    // MMAs of j issue.
+                    double ar[2][FA], aip[2][FA], ain[2][FA];
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    double ar[FA], aip[FA], ain[FA];
-                    const uint32_t a_addr = sbase + a_row_off + (a_c0 ^ (kk * 64));
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint32_t a_addr = sbase + a_row_off + (a_c0 ^ (kk * 64));
 #pragma unroll
-                    for (int i = 0; i < FA; ++i) {
-                        double x, y;
-                        lds128(a_addr + i * 1024, x, y);
-                        ar[i] = x;
-                        aip[i] = xor_hi(y, mA);               //  sa * Ai
-                        if constexpr (M3) ain[i] = x + aip[i];            // Ar + sa * Ai
-                        else ain[i] = xor_hi(y, mA ^ 0x80000000u);        // -sa * Ai
+                        for (int i = 0; i < FA; ++i) {
+                            double x, y;
+                            lds128(a_addr + i * 1024, x, y);
+                            ar[kk][i] = x;
+                            aip[kk][i] = xor_hi(y, mA);               //  sa * Ai
+                            ain[kk][i] = x + aip[kk][i];              // Ar + sa * Ai
+                        }
                     }
-                    if constexpr (M3) {
-                        // ain[i] holds Ar + sa Ai.  Fragment j+1 is in flight while the MMAs of j issue.
-                        const uint32_t b_addr = sbase + (b_off ^ (kk * 32));
-                        double f0 = lds64(b_addr), f1 = lds64(b_addr + T::B_SLAB), f2 = lds64(b_addr + 2 * T::B_SLAB);
-                        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+                    const uint32_t b_addr = sbase + b_off;
+                    double f0[2], f1[2], f2[2], g0[2] = {0.0, 0.0}, g1[2] = {0.0, 0.0}, g2[2] = {0.0, 0.0};
+                    lds128(b_addr, f0[0], f0[1]);
+                    lds128(b_addr + T::B_SLAB, f1[0], f1[1]);
+                    lds128(b_addr + 2 * T::B_SLAB, f2[0], f2[1]);
 #pragma unroll
-                        for (int j = 0; j < FB; ++j) {
-                            if (j + 1 < FB) {
-                                g0 = lds64(b_addr + (j + 1) * 512);
-                                g1 = lds64(b_addr + (j + 1) * 512 + T::B_SLAB);
-                                g2 = lds64(b_addr + (j + 1) * 512 + 2 * T::B_SLAB);
-                            }
+                    for (int j = 0; j < FB; ++j) {
+                        if (j + 1 < FB) {
+                            lds128(b_addr + (j + 1) * 512, g0[0], g0[1]);
+                            lds128(b_addr + (j + 1) * 512 + T::B_SLAB, g1[0], g1[1]);
+                            lds128(b_addr + (j + 1) * 512 + 2 * T::B_SLAB, g2[0], g2[1]);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
                             for (int i = 0; i < FA; ++i) {
-                                dmma884(cr[i][j][0], cr[i][j][1], ain[i], f0);     // k1 = (Ar + Ai) Br
-                                dmma884(ci[i][j][0], ci[i][j][1], ar[i], f1);      // k2 = Ar (Bi - Br)
-                                dmma884(cs[i][j][0], cs[i][j][1], aip[i], f2);     // k3 = Ai (Br + Bi)
+                                dmma884(cr[i][j][0], cr[i][j][1], ain[kk][i], f0[kk]);     // k1 = (Ar + Ai) Br
+                                dmma884(ci[i][j][0], ci[i][j][1], ar[kk][i], f1[kk]);      // k2 = Ar (Bi - Br)
+                                dmma884(cs[i][j][0], cs[i][j][1], aip[kk][i], f2[kk]);     // k3 = Ai (Br + Bi)
                             }
-                            f0 = g0;
-                            f1 = g1;
-                            f2 = g2;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            f0[kk] = g0[kk];
+                            f1[kk] = g1[kk];
+                            f2[kk] = g2[kk];
                         }
-                    } else {
+                    }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        double ar[FA], aip[FA], ain[FA];
+                        const uint32_t a_addr = sbase + a_row_off + (a_c0 ^ (kk * 64));
+#pragma unroll
+                        for (int i = 0; i < FA; ++i) {
+                            double x, y;
+                            lds128(a_addr + i * 1024, x, y);
+                            ar[i] = x;
+                            aip[i] = xor_hi(y, mA);                   //  sa * Ai
+                            ain[i] = xor_hi(y, mA ^ 0x80000000u);     // -sa * Ai
+                        }
                         const uint32_t b_addr = sbase + b_off + kk * T::B_SLAB;
                         // software pipeline over the B fragments: fragment j+1 is in flight while the MMAs of j issue
                         double br, bi, br_n = 0.0, bi_n = 0.0;

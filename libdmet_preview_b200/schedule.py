@@ -83,11 +83,28 @@ class EriSchedule(object):
         return [flop_block * len(u[2]) + flop_gram * (1 if u[1] == 1 else 2) for u in self.units]
 
 
+_SCHEDULES = {}
+
+
 def build_schedule(kpts_scaled, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL, kscaled_center=None):
     """Replay of eri_transform.py:308-382.  `kpts_scaled` are the unshifted scaled k-points (what
     cell.get_scaled_kpts(mydf.kpts) returns); the optional centre shift only enters the conservation test and the
-    partner lookup, as in the reference (l.266-268 vs l.309)."""
+    partner lookup, as in the reference (l.266-268 vs l.309).  The schedule is a pure function of its arguments and
+    a DMET loop asks for the same one every iteration, so the last few are kept (an EriSchedule is read-only)."""
     k0 = np.array(kpts_scaled, dtype=float)
+    key = (k0.tobytes(), k0.shape, bool(t_reversal_symm), float(kconserv_tol),
+           None if kscaled_center is None else np.asarray(kscaled_center, dtype=float).tobytes())
+    hit = _SCHEDULES.get(key)
+    if hit is not None:
+        return hit
+    sch = _build_schedule(k0, t_reversal_symm, kconserv_tol, kscaled_center)
+    if len(_SCHEDULES) >= 8:
+        _SCHEDULES.pop(next(iter(_SCHEDULES)))
+    _SCHEDULES[key] = sch
+    return sch
+
+
+def _build_schedule(k0, t_reversal_symm, kconserv_tol, kscaled_center):
     nk = len(k0)
     ks = k0 - kscaled_center if kscaled_center is not None else k0
     if t_reversal_symm:

@@ -89,6 +89,7 @@ class SyntheticGDF(object):
         self.max_memory = 4000
         self._cderi = "<synthetic>"
         self.minus = [int(kpt_member(-k, self.kpts_scaled)[0]) for k in self.kpts_scaled]
+        self._keys = {}
         assert 2 * self.naux * self.nao * self.nao < 2 ** 32
 
     def pair_key(self, a, b):
@@ -96,8 +97,12 @@ class SyntheticGDF(object):
         return int(lowbias32(np.uint64(self.seed ^ inner)))
 
     def keys(self, ki, kj):
-        mi, mj = self.minus[ki], self.minus[kj]
-        return (self.pair_key(ki, kj), self.pair_key(kj, ki), self.pair_key(mi, mj), self.pair_key(mj, mi))
+        k = self._keys.get((ki, kj))
+        if k is None:
+            mi, mj = self.minus[ki], self.minus[kj]
+            k = (self.pair_key(ki, kj), self.pair_key(kj, ki), self.pair_key(mi, mj), self.pair_key(mj, mi))
+            self._keys[(ki, kj)] = k
+        return k
 
     def load(self, ki, kj, aux_slice=None):
         """(naux, nao, nao) complex128 block L(k_i, k_j) (host twin of the device generator; 32-bit wrapping
