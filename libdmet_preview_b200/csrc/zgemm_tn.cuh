@@ -283,11 +283,18 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         auto col_in_frag = [](int q) { return M3 ? ((q & 1) | ((q & 2) << 1) | ((q & 4) >> 1)) : q; };
         constexpr int JB = FB > 23 ? 1 : (FB > 20 ? 2 : 4);   // the widest tiles have no registers to spare
         constexpr bool kBatch = FB <= 23;
+        // addresses: one division per row, then pointer steps only (the epilogue is ~5 % of a consumer warp's time
+        // at K = 200 and was dominated by 64-bit index arithmetic per stored element)
+        const long long sc = args.s_col, step = 8 * sc;
+        const int c_base = tn * T::BN + wn * FB * 8;
+        const int ce0 = c_base + col_in_frag(2 * t), ce1 = c_base + col_in_frag(2 * t + 1);
 #pragma unroll
         for (int i = 0; i < FA; ++i) {
             const int r = tm * T::BM + wm * FA * 8 + i * 8 + pg;
             if (r >= args.M) continue;
             const long long roff = (long long)(r / args.rdiv) * args.s_outer + (long long)(r % args.rdiv) * args.s_inner;
+            double2* const pe0 = Cb + roff + (long long)ce0 * sc;
+            double2* const pe1 = Cb + roff + (long long)ce1 * sc;
 #pragma unroll
             for (int j0 = 0; j0 < FB; j0 += JB) {
                 double2 old[JB][2];
@@ -296,9 +303,10 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int jj = 0; jj < JB; ++jj)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const int c = tn * T::BN + wn * FB * 8 + (j0 + jj) * 8 + col_in_frag(2 * t + e);
-                            old[jj][e] = (j0 + jj < FB && c < args.N) ? Cb[roff + (long long)c * args.s_col]
-                                                                      : make_double2(0.0, 0.0);
+                            const int j = j0 + jj;
+                            const int c = (e ? ce1 : ce0) + 8 * j;
+                            const double2* src = (e ? pe1 : pe0) + (long long)j * step;
+                            old[jj][e] = (j < FB && c < args.N) ? *src : make_double2(0.0, 0.0);
                         }
                 }
 #pragma unroll
@@ -307,8 +315,9 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int j = j0 + jj;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int c = tn * T::BN + wn * FB * 8 + j * 8 + col_in_frag(2 * t + e);
+                        const int c = (e ? ce1 : ce0) + 8 * j;
                         if (c >= args.N) continue;
+                        double2* dst = (e ? pe1 : pe0) + (long long)j * step;
                         double2 v;
                         if constexpr (M3)
                             v = make_double2(alpha * (cr[i][j][e] - cs[i][j][e]),
@@ -316,11 +325,11 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         else
                             v = make_double2(alpha * cr[i][j][e], alpha * ci[i][j][e]);
                         if (args.accumulate) {
-                            const double2 o = kBatch ? old[jj][e] : Cb[roff + (long long)c * args.s_col];
+                            const double2 o = kBatch ? old[jj][e] : *dst;
                             v.x += o.x;
                             v.y += o.y;
                         }
-                        Cb[roff + (long long)c * args.s_col] = v;
+                        *dst = v;
                     }
                 }
             }
