@@ -24,20 +24,53 @@ def unit_costs(schedule, nao, naux, nemb, nspin):
     return schedule.unit_cost(f_block, f_gram)
 
 
-def rank_items(schedule, nao, naux, nemb, nspin, world_size, nsplit=None):
+def rank_items(schedule, nao, naux, nemb, nspin, world_size, nsplit=None, speeds=None):
     """work items (unit, l0, l1) per rank -- deterministic, identical on every rank.  When the transfer momenta do
     not divide evenly over the ranks (36 units on 8 GPUs at 4x4x4 would cap the speed-up at 7.2x) each unit is
-    split along the auxiliary index into `nsplit` independent, additive pieces."""
+    split along the auxiliary index into `nsplit` independent, additive pieces.  `speeds`: relative throughput of
+    the ranks (identical list on every rank), used when the build is bound by each rank's own host link."""
     costs = unit_costs(schedule, nao, naux, nemb, nspin)
     if nsplit is None:
-        nsplit = choose_split(costs, world_size)
+        nsplit = choose_split(costs, world_size, speeds=speeds, max_split=4 if speeds is None else 8)
     items = work_items(schedule, naux, nsplit)
     icost = [costs[u] * (l1 - l0) / float(naux) for (u, l0, l1) in items]
-    parts = assign_units(icost, world_size)
+    parts = assign_units(icost, world_size, speeds)
     return [[items[i] for i in p] for p in parts]
 
 
-def sharded_partial(schedule, shape, compute_partial, group=None, all_ranks=False, nsplit=None):
+_H2D_SPEEDS = {}
+
+
+def measure_h2d_speeds(group=None, nbytes=256 << 20, reps=3):
+    """Pinned host -> device bandwidth of every rank with ALL ranks copying at the same time, in GB/s (identical
+    list on every rank).  On a multi-GPU box the ranks' links are not equal (the 8-GPU boxes of this pool deliver
+    23-35 GB/s per rank when all copy at once, profiles/probe_h2d_r02_8gpu.json) and a build that streams the GDF
+    tensor from host memory finishes when the slowest link has moved its share -- so the shares are made
+    proportional to these rates."""
+    world = dist.get_world_size(group)
+    key = (id(group), world)
+    if key in _H2D_SPEEDS:                       # the links do not change during the life of the process group
+        return _H2D_SPEEDS[key]
+    src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    src.fill_(1)
+    dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dist.barrier(group)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    e1.synchronize()
+    mine = torch.tensor([reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9], dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine, group=group)
+    _H2D_SPEEDS[key] = [float(x.item()) for x in allr]
+    return _H2D_SPEEDS[key]
+
+
+def sharded_partial(schedule, shape, compute_partial, group=None, all_ranks=False, nsplit=None, speeds=None):
     """Each rank computes its items with `compute_partial(items) -> tensor`, then the partials are summed onto
     rank 0 (or all ranks).  shape = (nao, naux, nemb, nspin).  Returns the reduced tensor on rank 0 (all ranks if
     all_ranks) and the local partial elsewhere."""
@@ -46,7 +79,7 @@ def sharded_partial(schedule, shape, compute_partial, group=None, all_ranks=Fals
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     nao, naux, nemb, nspin = shape
-    mine = rank_items(schedule, nao, naux, nemb, nspin, world, nsplit)[rank]
+    mine = rank_items(schedule, nao, naux, nemb, nspin, world, nsplit, speeds)[rank]
     part = compute_partial(mine)
     if world > 1:
         if all_ranks:
@@ -111,8 +144,18 @@ def get_emb_eri_sharded(cell, mydf, C_ao_lo=None, basis=None, kscaled_center=Non
                                  kl_group=kwargs.get("kl_group", et.DEFAULT_KL_GROUP), stats=kwargs.get("stats", None),
                                  gso=gso, imag=imag)
 
+    # a build that streams its blocks from host memory is bound by each rank's own host link: shares proportional to
+    # the measured rates (device-generated and resident tensors: equal shares)
+    speeds = kwargs.get("rank_speeds", None)
+    host_fed = kwargs.get("source", "auto") == "host" or not (
+        isinstance(provider, et.ResidentGDF) or (hasattr(provider, "keys") and hasattr(provider, "scale")))
+    if speeds is None and host_fed and kwargs.get("balance_h2d", True) and dist.get_world_size(pg) > 1 \
+            and torch.cuda.is_available() and dist.get_backend(pg) == "nccl":
+        speeds = measure_h2d_speeds(pg)
+    if isinstance(kwargs.get("stats", None), dict):
+        kwargs["stats"]["rank_speeds"] = speeds
     eri = sharded_partial(schedule, (nao, provider.naux, nemb, nspin), compute, group=pg, all_ranks=all_ranks,
-                          nsplit=kwargs.get("nsplit", None))
+                          nsplit=kwargs.get("nsplit", None), speeds=speeds)
     if imag is not None and dist.get_world_size(pg) > 1:
         # rank 0 reports max|Im| of the complete Lambda^dagger Lambda (eri_transform_mpi.py:205-209)
         if all_ranks:

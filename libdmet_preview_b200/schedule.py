@@ -153,28 +153,33 @@ def work_items(schedule, naux, nsplit=1, units=None):
     return [(u, cuts[s], cuts[s + 1]) for u in idx for s in range(nsplit) if cuts[s + 1] > cuts[s]]
 
 
-def choose_split(costs, nranks, max_split=4, tol=0.03):
-    """smallest aux split whose LPT assignment is balanced to `tol` (1 when the units already divide evenly)."""
+def choose_split(costs, nranks, max_split=4, tol=0.03, speeds=None):
+    """smallest aux split whose LPT assignment is balanced to `tol` (1 when the units already divide evenly).
+    `speeds`: relative throughput of the ranks (see assign_units)."""
+    sp = [1.0] * nranks if speeds is None else [float(x) for x in speeds]
     best = 1
     for ns in range(1, max_split + 1):
         c = [x / ns for x in costs for _ in range(ns)]
-        parts = assign_units(c, nranks)
-        loads = [sum(c[u] for u in p) for p in parts]
-        if max(loads) <= (1.0 + tol) * sum(loads) / nranks:
+        parts = assign_units(c, nranks, speeds)
+        times = [sum(c[u] for u in p) / sp[r] for r, p in enumerate(parts)]
+        if max(times) <= (1.0 + tol) * sum(c) / sum(sp):
             return ns
         best = ns
     return best
 
 
-def assign_units(costs, nranks):
+def assign_units(costs, nranks, speeds=None):
     """Longest-processing-time assignment of schedule units to ranks (the reference's MPI variant deals the units
-    out round-robin, eri_transform_mpi.py:35-55; LPT balances unequal block counts better).  Returns a list of
-    unit-index lists, deterministic."""
+    out round-robin, eri_transform_mpi.py:35-55; LPT balances unequal block counts better).  With `speeds` (relative
+    throughput per rank, e.g. the host->device bandwidth each rank measured for a host-streamed build) a unit goes to
+    the rank that would finish it first.  Returns a list of unit-index lists, deterministic."""
+    sp = [1.0] * nranks if speeds is None else [float(x) for x in speeds]
+    assert len(sp) == nranks and min(sp) > 0.0
     order = sorted(range(len(costs)), key=lambda u: (-costs[u], u))
     load = [0.0] * nranks
     out = [[] for _ in range(nranks)]
     for u in order:
-        r = min(range(nranks), key=lambda x: (load[x], x))
+        r = min(range(nranks), key=lambda x: ((load[x] + costs[u]) / sp[x], x))
         out[r].append(u)
         load[r] += costs[u]
     for r in range(nranks):
