@@ -126,7 +126,10 @@ static const ZConfig& pick_zconfig(int N, bool m3) {
     double best_cost = 0.0;
     for (size_t i = 0; i < v.size(); ++i) {
         if (v[i].m3 != m3) continue;
-        const double pad = (double)((N + v[i].BN - 1) / v[i].BN) * v[i].BN;
+        const int tiles = (N + v[i].BN - 1) / v[i].BN;
+        double pad = (double)tiles * v[i].BN;
+        // 3M tiles run their last n-tile with one column fragment less when that fragment would be all padding
+        if (v[i].m3 && tiles > 1 && v[i].BN > 8 && (N - (tiles - 1) * v[i].BN + 7) / 8 == v[i].BN / 8 - 1) pad -= 8.0;
         const double cost = pad * (1.0 + 24.0 / v[i].BN);
         if (best < 0 || cost < best_cost) {
             best = (int)i;
@@ -368,6 +371,11 @@ static int launch_zgemm(ldm_handle h, cudaStream_t st, const ZConfig& cfg, const
     long long ntiles = (long long)a.tiles_m * a.tiles_n * nbatch;
     LDM_REQUIRE(ntiles < (1ll << 31), "too many tiles");
     int grid = (int)std::min<long long>(ntiles, h->num_sms);
+    // the last n-tile needs one column fragment less than the others: run it with FB - 1 fragments (zgemm_tn.cuh)
+    const int fb_full = cfg.BN / 8, fb_last = (N - (a.tiles_n - 1) * cfg.BN + 7) / 8;
+    static const bool allow_short = getenv("LDM_ZGEMM_SHORT_LAST") ? atoi(getenv("LDM_ZGEMM_SHORT_LAST")) != 0 : true;
+    a.short_last = (allow_short && cfg.m3 && fb_full > 1 && fb_last == fb_full - 1 && a.tiles_n > 1 &&
+                    grid % a.tiles_n == 0) ? 1 : 0;
     cfg.kernel<<<grid, cfg.threads, cfg.smem, st>>>(tmA, tmB, a);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;

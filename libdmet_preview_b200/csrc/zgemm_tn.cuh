@@ -33,6 +33,8 @@
 // 3M stage: A tile as above; B = 3 planes of BN rows x 64 B (8 real k in the order 0,4,1,5,2,6,3,7), 64-byte
 // swizzled by TMA; one LDS.128 per plane and column fragment delivers the words of both k-steps of the stage.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ldm {
@@ -56,7 +58,22 @@ struct ZGemmArgs {
     double alpha;
     int accumulate;              // 1: C += result
     int tiles_m, tiles_n;
+    int short_last;              // 3M: the LAST n-tile runs with FB - 1 column fragments (its last fragment would be all
+                                 // padding: N = 150 as 80 + 72 instead of 80 + 80); the n index is then rotated by the
+                                 // wave number so that every CTA gets long and short tiles in turn
 };
+
+// tile index -> (batch entry, m-tile, n-tile).  n runs fastest, so the tiles_n CTAs that share an A tile run side by
+// side and the second reader finds it in L2; with `short_last` the n index is shifted by the wave number (the grid
+// is a multiple of tiles_n then, so the tiles of one A tile stay in one wave and the map stays one-to-one).
+__device__ __forceinline__ void tile_coords(const ZGemmArgs& a, int tile, int tiles_per_batch, int& b, int& tm,
+                                            int& tn) {
+    b = tile / tiles_per_batch;
+    const int rem = tile - b * tiles_per_batch;
+    tm = rem / a.tiles_n;
+    tn = rem - tm * a.tiles_n;
+    if (a.short_last) tn = (tn + tile / (int)gridDim.x) % a.tiles_n;
+}
 
 constexpr int ZFORM_PLANES = 5;      // Br, D, S, -S, -D
 
@@ -108,10 +125,8 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int b = tile / tiles_per_batch;
-                const int rem = tile - b * tiles_per_batch;
-                const int tm = rem / args.tiles_n;
-                const int tn = rem - tm * args.tiles_n;
+                int b, tm, tn;
+                tile_coords(args, tile, tiles_per_batch, b, tm, tn);
                 const ZSeg* segs = args.segs + (size_t)b * args.nseg;
                 for (int s = 0; s < args.nseg; ++s) {
                     const int az = segs[s].az, bz = segs[s].bz;
@@ -165,19 +180,19 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // Releasing directly after the last fragment loads is not safe: the arrive does not wait for LDS in flight.
     int stage = 0, prev_stage = -1;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_batch;
-        const int rem = tile - b * tiles_per_batch;
-        const int tm = rem / args.tiles_n;
-        const int tn = rem - tm * args.tiles_n;
+    // One tile, with FBE <= FB column fragments per warp (a compile-time count: the short last n-tile is a second
+    // instance of the same code, chosen once per tile -- a run-time test per fragment costs more than the skipped
+    // MMAs save, measured).
+    auto run_tile = [&](auto fbe_tag, const int b, const int tm, const int tn) {
+        constexpr int FBE = decltype(fbe_tag)::value;
         const ZSeg* segs = args.segs + (size_t)b * args.nseg;
 
         // 4M: cr = Re, ci = Im.   3M: cr = k1, ci = k2, cs = k3.
-        double cr[FA][FB][2], ci[FA][FB][2], cs[M3 ? FA : 1][M3 ? FB : 1][2];
+        double cr[FA][FBE][2], ci[FA][FBE][2], cs[M3 ? FA : 1][M3 ? FBE : 1][2];
 #pragma unroll
         for (int i = 0; i < FA; ++i)
 #pragma unroll
-            for (int j = 0; j < FB; ++j) {
+            for (int j = 0; j < FBE; ++j) {
                 cr[i][j][0] = cr[i][j][1] = 0.0;
                 ci[i][j][0] = ci[i][j][1] = 0.0;
                 if constexpr (M3) cs[i][j][0] = cs[i][j][1] = 0.0;
@@ -216,8 +231,8 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     lds128(b_addr + T::B_SLAB, f1[0], f1[1]);
                     lds128(b_addr + 2 * T::B_SLAB, f2[0], f2[1]);
 #pragma unroll
-                    for (int j = 0; j < FB; ++j) {
-                        if (j + 1 < FB) {
+                    for (int j = 0; j < FBE; ++j) {
+                        if (j + 1 < FBE) {
                             lds128(b_addr + (j + 1) * 512, g0[0], g0[1]);
                             lds128(b_addr + (j + 1) * 512 + T::B_SLAB, g1[0], g1[1]);
                             lds128(b_addr + (j + 1) * 512 + 2 * T::B_SLAB, g2[0], g2[1]);
@@ -255,8 +270,8 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         double br, bi, br_n = 0.0, bi_n = 0.0;
                         lds128(b_addr, br, bi);
 #pragma unroll
-                        for (int j = 0; j < FB; ++j) {
-                            if (j + 1 < FB) lds128(b_addr + (j + 1) * 512, br_n, bi_n);
+                        for (int j = 0; j < FBE; ++j) {
+                            if (j + 1 < FBE) lds128(b_addr + (j + 1) * 512, br_n, bi_n);
                             bi = xor_hi(bi, mB);                  //  sb * Bi
 #pragma unroll
                             for (int i = 0; i < FA; ++i) {
@@ -296,7 +311,7 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             double2* const pe0 = Cb + roff + (long long)ce0 * sc;
             double2* const pe1 = Cb + roff + (long long)ce1 * sc;
 #pragma unroll
-            for (int j0 = 0; j0 < FB; j0 += JB) {
+            for (int j0 = 0; j0 < FBE; j0 += JB) {
                 double2 old[JB][2];
                 if (kBatch && args.accumulate) {
 #pragma unroll
@@ -306,12 +321,12 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const int j = j0 + jj;
                             const int c = (e ? ce1 : ce0) + 8 * j;
                             const double2* src = (e ? pe1 : pe0) + (long long)j * step;
-                            old[jj][e] = (j < FB && c < args.N) ? *src : make_double2(0.0, 0.0);
+                            old[jj][e] = (j < FBE && c < args.N) ? *src : make_double2(0.0, 0.0);
                         }
                 }
 #pragma unroll
                 for (int jj = 0; jj < JB; ++jj) {
-                    if (j0 + jj >= FB) continue;
+                    if (j0 + jj >= FBE) continue;
                     const int j = j0 + jj;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -334,6 +349,18 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
         }
+    };
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int b, tm, tn;
+        tile_coords(args, tile, tiles_per_batch, b, tm, tn);
+        if constexpr (M3 && FB > 1) {
+            if (args.short_last && tn == args.tiles_n - 1) {
+                run_tile(std::integral_constant<int, FB - 1>{}, b, tm, tn);
+                continue;
+            }
+        }
+        run_tile(std::integral_constant<int, FB>{}, b, tm, tn);
     }
 }
 
