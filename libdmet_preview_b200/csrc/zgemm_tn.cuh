@@ -87,8 +87,18 @@ struct ZTile {
     static constexpr int STAGE_BYTES = (TX_BYTES + 1023) / 1024 * 1024;     // stages stay 1024-byte aligned (swizzle)
     static constexpr int NCONS = WM * WN;
     static constexpr int THREADS = (NCONS + 4) * 32;   // + one producer warpgroup
-    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 2 * STAGES * 8;
+    // Staged epilogue (3M tiles): the consumers park a finished tile in shared memory (row stride BN + 1 complex:
+    // conflict-free both along rows and along columns) and three otherwise idle warps of the producer warpgroup write it
+    // to global memory while the consumers are already in the next tile's main loop.
+    static constexpr int STG_LD = BN + 1;
+    static constexpr int STG_BYTES_WANTED = BM * STG_LD * 16;
+    static constexpr int SMEM_BUDGET = 224 * 1024;
+    static constexpr bool STG = M3 && BM == 64 && (4 * STAGE_BYTES + STG_BYTES_WANTED + 2048 <= SMEM_BUDGET);
+    static constexpr int STG_BYTES = STG ? STG_BYTES_WANTED : 0;
+    static constexpr int STAGES_FIT = STG ? (SMEM_BUDGET - STG_BYTES - 2048) / STAGE_BYTES : 200 * 1024 / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int STG_WARPS = 3;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + (2 * STAGES + 2) * 8;
 };
 
 template <int WM, int WN, int FA, int FB, bool M3>
@@ -98,7 +108,9 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     using T = ZTile<WM, WN, FA, FB, M3>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + T::STAGES * T::STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
+    const uint32_t stg_base = smem_base + T::STAGES * T::STAGE_BYTES;   // staging tile of the epilogue (if any)
+    const uint32_t bar_base = stg_base + T::STG_BYTES;                  // full[s] at +8s, empty[s] at +8(STAGES+s)
+    const uint32_t stg_full = bar_base + 8 * (2 * T::STAGES), stg_empty = stg_full + 8;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -108,6 +120,8 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_init(bar_base + 8 * s, 1);
             mbar_init(bar_base + 8 * (T::STAGES + s), T::NCONS);
         }
+        mbar_init(stg_full, T::NCONS);
+        mbar_init(stg_empty, T::STG_WARPS);
         mbar_fence_init();
     }
     __syncthreads();
@@ -151,6 +165,70 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
         }
+        if constexpr (T::STG) {
+            if (warp > T::NCONS) {
+                // ===================== epilogue store warps =====================
+                // tile by tile: wait until the consumers have parked the tile, write it out (read-modify-write in
+                // accumulate mode) with the lanes along the contiguous direction of the output, hand the buffer back
+                const int sw = warp - T::NCONS - 1;
+                const double2* stg = reinterpret_cast<const double2*>(smem_raw + (stg_base - smem_u32(smem_raw)));
+                uint32_t sphase = 0;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    int b, tm, tn;
+                    tile_coords(args, tile, tiles_per_batch, b, tm, tn);
+                    double2* Cb = args.C + (args.c_off ? args.c_off[b] : 0ll);
+                    const int rows = min(T::BM, args.M - tm * T::BM);
+                    const int cols = min(T::BN, args.N - tn * T::BN);
+                    const long long sc = args.s_col;
+                    mbar_wait(stg_full, sphase);
+                    if (sc == 1) {
+                        // columns are contiguous in the output: a warp per row, lanes along the columns
+                        for (int r = sw; r < rows; r += T::STG_WARPS) {
+                            const int rg = tm * T::BM + r;
+                            double2* dst = Cb + (long long)(rg / args.rdiv) * args.s_outer +
+                                           (long long)(rg % args.rdiv) * args.s_inner + (long long)tn * T::BN;
+                            const double2* src = stg + r * T::STG_LD;
+                            for (int c = lane; c < cols; c += 32) {
+                                double2 v = src[c];
+                                if (args.accumulate) {
+                                    const double2 o = dst[c];
+                                    v.x += o.x;
+                                    v.y += o.y;
+                                }
+                                dst[c] = v;
+                            }
+                        }
+                    } else {
+                        // rows are (piecewise) contiguous: a warp per column, lanes along the 64 rows
+                        long long roff[2];
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int rg = tm * T::BM + lane + 32 * h2;
+                            roff[h2] = (long long)(rg / args.rdiv) * args.s_outer + (long long)(rg % args.rdiv) * args.s_inner;
+                        }
+                        for (int c = sw; c < cols; c += T::STG_WARPS) {
+                            double2* dst = Cb + (long long)(tn * T::BN + c) * sc;
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                const int r = lane + 32 * h2;
+                                if (r < rows) {
+                                    double2 v = stg[r * T::STG_LD + c];
+                                    if (args.accumulate) {
+                                        const double2 o = dst[roff[h2]];
+                                        v.x += o.x;
+                                        v.y += o.y;
+                                    }
+                                    dst[roff[h2]] = v;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(stg_empty);
+                    sphase ^= 1;
+                }
+            }
+        }
         return;
     }
 
@@ -179,7 +257,7 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // stage has returned its data (the MMAs that consume them have issued) before TMA may overwrite the buffer.
     // Releasing directly after the last fragment loads is not safe: the arrive does not wait for LDS in flight.
     int stage = 0, prev_stage = -1;
-    uint32_t phase = 0;
+    uint32_t phase = 0, cphase = 0;
     // One tile, with FBE <= FB column fragments per warp (a compile-time count: the short last n-tile is a second
     // instance of the same code, chosen once per tile -- a run-time test per fragment costs more than the skipped
     // MMAs save, measured).
@@ -290,7 +368,31 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
 
-        // ---------------- epilogue: registers -> global ----------------
+        // ---------------- epilogue ----------------
+        if constexpr (T::STG) {
+            // park the tile (alpha and the 3M combination applied) in the staging buffer and go on; the store
+            // warps write it out.  The buffer of the previous tile must have been drained.
+            double2* stg = reinterpret_cast<double2*>(smem_raw + (stg_base - smem_u32(smem_raw)));
+            mbar_wait(stg_empty, cphase ^ 1);
+            const double alpha = args.alpha;
+#pragma unroll
+            for (int i = 0; i < FA; ++i) {
+                double2* row = stg + (wm * FA * 8 + i * 8 + pg) * T::STG_LD + wn * FB * 8;
+#pragma unroll
+                for (int j = 0; j < FBE; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int q = 2 * t + e;
+                        const int c = j * 8 + ((q & 1) | ((q & 2) << 1) | ((q & 4) >> 1));
+                        row[c] = make_double2(alpha * (cr[i][j][e] - cs[i][j][e]), alpha * (cr[i][j][e] + ci[i][j][e]));
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stg_full);
+            cphase ^= 1;
+            return;
+        }
+        // ---------------- registers -> global ----------------
         // accumulate mode reads the old values of a whole chunk first (independent loads in flight together) and
         // only then stores: a load/store chain per element would expose one DRAM round trip per element.
         double2* Cb = args.C + (args.c_off ? args.c_off[b] : 0ll);
