@@ -120,8 +120,8 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_init(bar_base + 8 * s, 1);
             mbar_init(bar_base + 8 * (T::STAGES + s), T::NCONS);
         }
-        mbar_init(stg_full, T::NCONS);
-        mbar_init(stg_empty, T::STG_WARPS);
+        mbar_init(stg_full, T::NCONS * 32);          // every thread that writes the staging tile arrives itself
+        mbar_init(stg_empty, T::STG_WARPS * 32);     // ... and so does every thread that reads it
         mbar_fence_init();
     }
     __syncthreads();
@@ -223,8 +223,7 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(stg_empty);
+                    mbar_arrive(stg_empty);              // release: this thread's reads of the buffer are done
                     sphase ^= 1;
                 }
             }
@@ -387,8 +386,7 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         row[c] = make_double2(alpha * (cr[i][j][e] - cs[i][j][e]), alpha * (cr[i][j][e] + ci[i][j][e]));
                     }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(stg_full);
+            mbar_arrive(stg_full);                   // release: this thread's part of the tile is in place
             cphase ^= 1;
             return;
         }
