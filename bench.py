@@ -702,7 +702,9 @@ def run_ours(args):
     if world == 1 and not args.no_dmet and nspin == 1:
         from libdmet_preview_b200 import lattice as lat, slater
         torch.cuda.empty_cache()
-        base = gdf.inner
+        # the GDF tensor of the timed legs (pool of distinct blocks), kept resident in HBM across iterations the way a
+        # DMET loop keeps it (eri_transform.ResidentGDF: a pool block shared by several pairs is held once)
+        base = et.ResidentGDF(gdf)
         nval = neo - nao // 2 if neo > nao // 2 else max(1, neo // 3)       # impurity = nao/2 orbitals + nval bath
         nimp = neo - nval
         Lat = lat.Lattice(base.cell, kmesh)
@@ -715,15 +717,16 @@ def run_ours(args):
         Lat.set_Ham(None, base, C_ao_lo_h, eri_symmetry=4, ovlp=ovlp, hcore=hcore, rdm1=rdm1, vhf=vhf)
         torch.cuda.synchronize()
         t_set = time.perf_counter() - t0
-        # two iterations: the first pays one-off costs (page-locking the 1 GB result buffer, pipeline workspaces),
-        # the second is what every further DMET iteration costs
+        # three iterations: the first fills the resident store and pays the one-off costs (page-locking the 1 GB
+        # result buffer, pipeline workspaces), the last is what every further DMET iteration costs
         first = None
-        for it in range(2):
+        for it in range(3):
             t0 = time.perf_counter()
             bas = slater.get_emb_basis(Lat, Lat.rdm1_lo_R * 0.5)
             t_basis = time.perf_counter() - t0
             t0 = time.perf_counter()
-            Ham, _ = slater.embHam(Lat, bas, None, group=args.group, kl_group=args.kl_group)
+            stt = {}
+            Ham, _ = slater.embHam(Lat, bas, None, group=args.group, kl_group=args.kl_group, stats=stt)
             torch.cuda.synchronize()
             t_ham = time.perf_counter() - t0
             if first is None:
@@ -731,9 +734,12 @@ def run_ours(args):
             del Ham
         dmet_iter = {"seconds": t_basis + t_ham, "get_emb_basis_s": t_basis, "embHam_s": t_ham,
                      "first_iteration_s": first, "set_Ham_once_s": t_set, "neo": int(bas.shape[-1]),
+                     "resident_bytes": int(base.bytes_cached), "h2d_bytes": int(stt.get("h2d_bytes", 0)),
                      "note": "ConstructImpHam of this path (libdmet/dmet/HubPhSymm.py:74-100): bath SVD on the host, "
-                             "ERI build with the GDF blocks generated on the device, one-body part and J/K on the "
-                             "device, results returned as numpy"}
+                             "ERI build over the GDF tensor resident in HBM (ResidentGDF; the first iteration fills "
+                             "the store), one-body part and J/K on the device, results returned as numpy"}
+        base.release()
+        del base, Lat
 
     if rank != 0:
         if world > 1:

@@ -77,18 +77,21 @@ struct ZConfig {
     int BM, BN, threads, smem;
     void (*kernel)(const CUtensorMap, const CUtensorMap, const ZGemmArgs);
     bool m3;
+    int jp;                      // 3M: column fragments per group of the main loop (zgemm_tn.cuh)
+    bool wide;                   // 64 x (8 FB) tile, one 8-row fragment per warp
 };
 
-template <int WM, int WN, int FA, int FB, bool M3 = false>
+template <int WM, int WN, int FA, int FB, bool M3 = false, int JP = 1>
 static ZConfig make_zconfig() {
     using T = ZTile<WM, WN, FA, FB, M3>;
-    return ZConfig{T::BM, T::BN, T::THREADS, T::SMEM, zgemm_tn_kernel<WM, WN, FA, FB, M3>, M3};
+    return ZConfig{T::BM, T::BN, T::THREADS, T::SMEM, zgemm_tn_kernel<WM, WN, FA, FB, M3, JP>, M3, JP,
+                   WM == 8 && WN == 1 && FA == 1};
 }
 
-template <int FB, bool M3 = false>
+template <int FB, bool M3 = false, int JP = 1>
 static void add_wide(std::vector<ZConfig>& v) {
-    v.push_back(make_zconfig<8, 1, 1, FB, M3>());
-    if constexpr (FB > 1) add_wide<FB - 1, M3>(v);
+    v.push_back(make_zconfig<8, 1, 1, FB, M3, JP>());
+    if constexpr (FB > 1) add_wide<FB - 1, M3, JP>(v);
 }
 
 // Tile family.  First the register-blocked 32x(8*FB) warp tiles (least shared-memory traffic), then the "wide"
@@ -108,6 +111,11 @@ static const std::vector<ZConfig>& zconfigs() {
         c.push_back(make_zconfig<4, 2, 2, 5, true>());
         c.push_back(make_zconfig<4, 2, 2, 6, true>());
         c.push_back(make_zconfig<4, 2, 2, 4, true>());
+        // the wide 3M family again with the column fragments of the main loop taken two at a time (k-step loop outside
+        // the pair: DMMAs on the same accumulator are 6 instead of 3 instructions apart; a lone warp issues
+        // back-to-back dependent DMMAs 26 clocks apart instead of 16, tools/dmma_probe.cu).  LDM_Z3M_JP=1 selects the
+        // single-fragment order.
+        add_wide<13, true, 2>(c);
         return c;
     }();
     return v;
@@ -122,10 +130,12 @@ static const ZConfig& pick_zconfig(int N, bool m3) {
     // cost of a configuration: padded N, inflated by a per-tile overhead that shrinks with the tile width (a 64x8
     // tile pads N = 150 to 152 but spends its time in fragment loads and epilogues); ties: the earlier (more
     // register-blocked) entry wins
+    static const int want_jp = getenv("LDM_Z3M_JP") ? atoi(getenv("LDM_Z3M_JP")) : 2;
     int best = -1;
     double best_cost = 0.0;
     for (size_t i = 0; i < v.size(); ++i) {
         if (v[i].m3 != m3) continue;
+        if (m3 && v[i].wide && v[i].jp != want_jp) continue;   // wide family: one order
         const int tiles = (N + v[i].BN - 1) / v[i].BN;
         double pad = (double)tiles * v[i].BN;
         // 3M tiles run their last n-tile with one column fragment less when that fragment would be all padding

@@ -101,7 +101,7 @@ struct ZTile {
     static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + (2 * STAGES + 2) * 8;
 };
 
-template <int WM, int WN, int FA, int FB, bool M3>
+template <int WM, int WN, int FA, int FB, bool M3, int JP = 1>
 __global__ void __launch_bounds__((WM * WN + 4) * 32, 1)
 zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ZGemmArgs args) {
@@ -303,31 +303,47 @@ zgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                     const uint32_t b_addr = sbase + b_off;
-                    double f0[2], f1[2], f2[2], g0[2] = {0.0, 0.0}, g1[2] = {0.0, 0.0}, g2[2] = {0.0, 0.0};
-                    lds128(b_addr, f0[0], f0[1]);
-                    lds128(b_addr + T::B_SLAB, f1[0], f1[1]);
-                    lds128(b_addr + 2 * T::B_SLAB, f2[0], f2[1]);
+                    // column fragments are processed in groups of JP: within a group the k-step loop is outside the
+                    // fragment loop, so two DMMAs on the same accumulator are 3 * JP instructions apart
+                    constexpr int NG = (FBE + JP - 1) / JP;
+                    double f[JP][3][2], gn[JP][3][2];
 #pragma unroll
-                    for (int j = 0; j < FBE; ++j) {
-                        if (j + 1 < FBE) {
-                            lds128(b_addr + (j + 1) * 512, g0[0], g0[1]);
-                            lds128(b_addr + (j + 1) * 512 + T::B_SLAB, g1[0], g1[1]);
-                            lds128(b_addr + (j + 1) * 512 + 2 * T::B_SLAB, g2[0], g2[1]);
+                    for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+                        for (int pl = 0; pl < 3; ++pl) {
+                            gn[jj][pl][0] = gn[jj][pl][1] = 0.0;
+                            if (jj < FBE) lds128(b_addr + jj * 512 + pl * T::B_SLAB, f[jj][pl][0], f[jj][pl][1]);
                         }
+#pragma unroll
+                    for (int jg = 0; jg < NG; ++jg) {
+#pragma unroll
+                        for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+                            for (int pl = 0; pl < 3; ++pl)
+                                if ((jg + 1) * JP + jj < FBE)
+                                    lds128(b_addr + ((jg + 1) * JP + jj) * 512 + pl * T::B_SLAB, gn[jj][pl][0],
+                                           gn[jj][pl][1]);
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-                            for (int i = 0; i < FA; ++i) {
-                                dmma884(cr[i][j][0], cr[i][j][1], ain[kk][i], f0[kk]);     // k1 = (Ar + Ai) Br
-                                dmma884(ci[i][j][0], ci[i][j][1], ar[kk][i], f1[kk]);      // k2 = Ar (Bi - Br)
-                                dmma884(cs[i][j][0], cs[i][j][1], aip[kk][i], f2[kk]);     // k3 = Ai (Br + Bi)
+                            for (int jj = 0; jj < JP; ++jj) {
+                                const int j = jg * JP + jj;
+                                if (j < FBE) {
+#pragma unroll
+                                    for (int i = 0; i < FA; ++i) {
+                                        dmma884(cr[i][j][0], cr[i][j][1], ain[kk][i], f[jj][0][kk]);   // k1 = (Ar + Ai) Br
+                                        dmma884(ci[i][j][0], ci[i][j][1], ar[kk][i], f[jj][1][kk]);    // k2 = Ar (Bi - Br)
+                                        dmma884(cs[i][j][0], cs[i][j][1], aip[kk][i], f[jj][2][kk]);   // k3 = Ai (Br + Bi)
+                                    }
+                                }
                             }
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            f0[kk] = g0[kk];
-                            f1[kk] = g1[kk];
-                            f2[kk] = g2[kk];
-                        }
+                        for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+                            for (int pl = 0; pl < 3; ++pl) {
+                                f[jj][pl][0] = gn[jj][pl][0];
+                                f[jj][pl][1] = gn[jj][pl][1];
+                            }
                     }
                 } else {
 #pragma unroll

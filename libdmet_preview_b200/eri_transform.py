@@ -97,11 +97,17 @@ class ResidentGDF(object):
             if hasattr(provider, a):
                 setattr(self, a, getattr(provider, a))
         self.max_bytes = max_bytes
-        self._stores = {}        # (l0, l1) -> [tensor (nslots, l1-l0, nao, nao), {(ki, kj): slot}]
+        self._stores = {}        # (l0, l1) -> [tensor (nslots, l1-l0, nao, nao), {block key: slot}]
         self.bytes_cached = 0
 
     def load(self, ki, kj):
         return self.inner.load(ki, kj)
+
+    def block_key(self, ki, kj):
+        """identity of the block a pair is served from: providers whose pairs share blocks (synthetic.PooledGDF)
+        say so through `block_key`, and a shared block is kept once"""
+        f = getattr(self.inner, "block_key", None)
+        return (ki, kj) if f is None else f(ki, kj)
 
     def _budget(self):
         if self.max_bytes is not None:
@@ -128,8 +134,9 @@ class ResidentGDF(object):
         t, slots = self._stores[(l0, l1)]
         if t is None:
             return None
-        if (ki, kj) in slots:
-            return slots[(ki, kj)]
+        key = self.block_key(ki, kj)
+        if key in slots:
+            return slots[key]
         if len(slots) >= t.shape[0]:
             return None
         slot = len(slots)
@@ -147,7 +154,7 @@ class ResidentGDF(object):
             L = inner.load(ki, kj)
             L = L if isinstance(L, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(L, dtype=np.complex128))
             t[slot].copy_(L[l0:l1].reshape(t[slot].shape))
-        slots[(ki, kj)] = slot
+        slots[key] = slot
         return slot
 
     def release(self):
@@ -572,7 +579,7 @@ def emb_eri_device(provider, CT, t_reversal_symm=True, kconserv_tol=KPT_DIFF_TOL
             if stores is not None:
                 b.set_store(stores[(l0, l1)])
             elif isinstance(provider, ResidentGDF) and source in ("auto", "resident"):
-                nwant = sum(len(schedule.units[u][2]) for (u, _, _) in sub)
+                nwant = len({provider.block_key(ki, kj) for (u, _, _) in sub for (ki, kj, _) in schedule.units[u][2]})
                 t, _ = provider.store_for(l0, l1, nwant)
                 if t is not None:
                     b.set_store(t)

@@ -164,6 +164,10 @@ class PooledGDF(object):
     def pool_pair(self, s):
         return s % self.nkpts, (s // self.nkpts) % self.nkpts
 
+    def block_key(self, ki, kj):
+        """pairs that share a pool block share its resident copy (eri_transform.ResidentGDF)"""
+        return self.pool_index(ki, kj)
+
     def keys(self, ki, kj):
         return self.inner.keys(*self.pool_pair(self.pool_index(ki, kj)))
 

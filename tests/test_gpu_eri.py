@@ -192,6 +192,14 @@ def test_resident_gdf_cache(dev):
         res.release()
     syn = et.ResidentGDF(gdf)
     assert np.abs(et.get_emb_eri(gdf.cell, syn, C_ao_lo=C, basis=basis) - ref).max() < TOL
+    # pairs that share a block (PooledGDF.block_key) share its resident copy: 3 slots serve the whole schedule
+    from libdmet_preview_b200 import synthetic
+    pooled = synthetic.PooledGDF(gdf, 3)
+    refp = oe.get_emb_eri(gdf.cell, pooled, C_ao_lo=C, basis=basis)
+    rp = et.ResidentGDF(pooled)
+    for _ in range(2):
+        assert np.abs(et.get_emb_eri(gdf.cell, rp, C_ao_lo=C, basis=basis) - refp).max() < TOL
+    assert rp.bytes_cached == 3 * 22 * 8 * 8 * 16
 
 
 def test_imaginary_part_diagnostic(dev):
