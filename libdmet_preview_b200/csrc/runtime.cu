@@ -108,14 +108,14 @@ static const std::vector<ZConfig>& zconfigs() {
         // 3-multiplication family (three accumulator sets): 64 x (8*FB) wide tiles up to FB = 13 (measured 2 % faster
         // than the register-blocked tiles of equal shape), then 64x80 / 64x96 / 64x64 with two row fragments per warp
         add_wide<13, true>(c);
-        c.push_back(make_zconfig<4, 2, 2, 5, true>());
-        c.push_back(make_zconfig<4, 2, 2, 6, true>());
-        c.push_back(make_zconfig<4, 2, 2, 4, true>());
         // the wide 3M family again with the column fragments of the main loop taken two at a time (k-step loop outside
         // the pair: DMMAs on the same accumulator are 6 instead of 3 instructions apart; a lone warp issues
         // back-to-back dependent DMMAs 26 clocks apart instead of 16, tools/dmma_probe.cu).  LDM_Z3M_JP=1 selects the
         // single-fragment order.
         add_wide<13, true, 2>(c);
+        c.push_back(make_zconfig<4, 2, 2, 5, true>());
+        c.push_back(make_zconfig<4, 2, 2, 6, true>());
+        c.push_back(make_zconfig<4, 2, 2, 4, true>());
         return c;
     }();
     return v;
@@ -139,7 +139,8 @@ static const ZConfig& pick_zconfig(int N, bool m3) {
         const int tiles = (N + v[i].BN - 1) / v[i].BN;
         double pad = (double)tiles * v[i].BN;
         // 3M tiles run their last n-tile with one column fragment less when that fragment would be all padding
-        if (v[i].m3 && tiles > 1 && v[i].BN > 8 && (N - (tiles - 1) * v[i].BN + 7) / 8 == v[i].BN / 8 - 1) pad -= 8.0;
+        if (v[i].m3 && v[i].wide && tiles > 1 && v[i].BN > 8 && (N - (tiles - 1) * v[i].BN + 7) / 8 == v[i].BN / 8 - 1)
+            pad -= 8.0;
         const double cost = pad * (1.0 + 24.0 / v[i].BN);
         if (best < 0 || cost < best_cost) {
             best = (int)i;
@@ -384,7 +385,7 @@ static int launch_zgemm(ldm_handle h, cudaStream_t st, const ZConfig& cfg, const
     // the last n-tile needs one column fragment less than the others: run it with FB - 1 fragments (zgemm_tn.cuh)
     const int fb_full = cfg.BN / 8, fb_last = (N - (a.tiles_n - 1) * cfg.BN + 7) / 8;
     static const bool allow_short = getenv("LDM_ZGEMM_SHORT_LAST") ? atoi(getenv("LDM_ZGEMM_SHORT_LAST")) != 0 : true;
-    a.short_last = (allow_short && cfg.m3 && fb_full > 1 && fb_last == fb_full - 1 && a.tiles_n > 1 &&
+    a.short_last = (allow_short && cfg.m3 && cfg.wide && fb_full > 1 && fb_last == fb_full - 1 && a.tiles_n > 1 &&
                     grid % a.tiles_n == 0) ? 1 : 0;
     cfg.kernel<<<grid, cfg.threads, cfg.smem, st>>>(tmA, tmB, a);
     LDM_CUDA_OK(cudaGetLastError());
