@@ -61,7 +61,9 @@ int ldm_zgemm_tn(ldm_handle h, void* stream, const void* A_d, int za_count, cons
 
 /* ---- real TN GEMM / SYRK on the FP64 tensor cores -------------------------------------------------------
  * C(r, c) (+)= alpha * sum_{k<K} A(r, k) * B(c, k);  A: (M, lda), B: (N, ldb) row-major doubles; lower_only=1
- * computes only the tiles on or below the diagonal (A == B, syrk).  Replaces PySCF lib.dot in `_Lij_s4_to_eri`
+ * computes only the tiles on or below the diagonal (A == B, syrk): the lower triangle is valid afterwards, elements
+ * above it are either computed too (inside a diagonal tile) or left as they were.  Tiles are 128 x 128, or 64 x 64
+ * when the product has fewer 128 x 128 tiles than the device has SMs.  Replaces PySCF lib.dot in `_Lij_s4_to_eri`
  * (eri_transform.py:450-485).                                                                               */
 int ldm_dgemm_tn(ldm_handle h, void* stream, const double* A_d, int64_t lda, const double* B_d, int64_t ldb, int M,
                  int N, int K, double* C_d, int64_t ldc, double alpha, int accumulate, int lower_only);

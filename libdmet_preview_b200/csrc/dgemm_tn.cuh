@@ -29,10 +29,14 @@ struct DGemmArgs {
     int tiles_m, tiles_n;
 };
 
-struct DTile {
-    static constexpr int WM = 4, WN = 2, FA = 4, FB = 8;
-    static constexpr int BM = WM * FA * 8;   // 128
-    static constexpr int BN = WN * FB * 8;   // 128
+// Tile shapes: 128 x 128 (warp tile 32 x 64) for the large Gram products, 64 x 64 (warp tile 16 x 32) when the
+// product has too few 128 x 128 tiles to occupy the SMs (npair of a few hundred to ~2000: BASELINE configs 1 - 3 and
+// the lower end of the sweep).
+template <int FA_, int FB_>
+struct DTileT {
+    static constexpr int WM = 4, WN = 2, FA = FA_, FB = FB_;
+    static constexpr int BM = WM * FA * 8;
+    static constexpr int BN = WN * FB * 8;
     static constexpr int A_BYTES = BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -41,6 +45,8 @@ struct DTile {
     static constexpr int STAGES = 6;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8;
 };
+using DTile = DTileT<4, 8>;       // 128 x 128
+using DTileS = DTileT<2, 4>;      // 64 x 64
 
 __device__ __forceinline__ void dsyrk_tile_coords(int lin, int lower_only, int tiles_n, int& tm, int& tn) {
     if (!lower_only) {
@@ -55,10 +61,10 @@ __device__ __forceinline__ void dsyrk_tile_coords(int lin, int lower_only, int t
     }
 }
 
-__global__ void __launch_bounds__(DTile::THREADS, 1)
+template <class T>
+__global__ void __launch_bounds__(T::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const DGemmArgs args) {
-    using T = DTile;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + T::STAGES * T::STAGE_BYTES;

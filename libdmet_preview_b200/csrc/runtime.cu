@@ -213,7 +213,9 @@ static int ensure_attrs(ldm_handle h) {
     if (h->attrs_set) return 0;
     for (const auto& c : zconfigs())
         LDM_CUDA_OK(cudaFuncSetAttribute((const void*)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem));
-    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)dgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)dgemm_tn_kernel<DTileS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     DTileS::SMEM));
+    LDM_CUDA_OK(cudaFuncSetAttribute((const void*)dgemm_tn_kernel<DTile>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      DTile::SMEM));
     LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      200 * 1024));
@@ -410,26 +412,38 @@ static int make_bforms(ldm_handle h, cudaStream_t st, int slot, const void* B_d,
                               8ull * Kp * N, 8, BN, 2);
 }
 
-static int launch_dgemm(ldm_handle h, cudaStream_t st, const double* A, long long lda, const double* B, long long ldb,
-                        int M, int N, int K, double* C, long long ldc, double alpha, int accumulate, int lower_only) {
-    if (M <= 0 || N <= 0) return 0;
-    LDM_REQUIRE(!lower_only || M == N, "lower_only needs a square product");
+template <class T>
+static int launch_dgemm_t(ldm_handle h, cudaStream_t st, const double* A, long long lda, const double* B, long long ldb,
+                          int M, int N, int K, double* C, long long ldc, double alpha, int accumulate, int lower_only) {
     CUtensorMap tmA, tmB;
-    int rc = encode_tmap_f64_3d(&tmA, A, (uint64_t)K, (uint64_t)M, 1, (uint64_t)lda * 8, 0, 16, DTile::BM, true);
+    int rc = encode_tmap_f64_3d(&tmA, A, (uint64_t)K, (uint64_t)M, 1, (uint64_t)lda * 8, 0, 16, T::BM, true);
     if (rc) return rc;
-    rc = encode_tmap_f64_3d(&tmB, B, (uint64_t)K, (uint64_t)N, 1, (uint64_t)ldb * 8, 0, 16, DTile::BN, true);
+    rc = encode_tmap_f64_3d(&tmB, B, (uint64_t)K, (uint64_t)N, 1, (uint64_t)ldb * 8, 0, 16, T::BN, true);
     if (rc) return rc;
     DGemmArgs a;
     a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.alpha = alpha; a.accumulate = accumulate;
     a.lower_only = lower_only;
-    a.tiles_m = (M + DTile::BM - 1) / DTile::BM;
-    a.tiles_n = (N + DTile::BN - 1) / DTile::BN;
+    a.tiles_m = (M + T::BM - 1) / T::BM;
+    a.tiles_n = (N + T::BN - 1) / T::BN;
     long long ntiles = lower_only ? (long long)a.tiles_m * (a.tiles_m + 1) / 2 : (long long)a.tiles_m * a.tiles_n;
     int grid = (int)std::min<long long>(ntiles, h->num_sms);
-    dgemm_tn_kernel<<<grid, DTile::THREADS, DTile::SMEM, st>>>(tmA, tmB, a);
+    dgemm_tn_kernel<T><<<grid, T::THREADS, T::SMEM, st>>>(tmA, tmB, a);
     LDM_CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
+}
+
+static int launch_dgemm(ldm_handle h, cudaStream_t st, const double* A, long long lda, const double* B, long long ldb,
+                        int M, int N, int K, double* C, long long ldc, double alpha, int accumulate, int lower_only) {
+    if (M <= 0 || N <= 0) return 0;
+    LDM_REQUIRE(!lower_only || M == N, "lower_only needs a square product");
+    // fewer 128 x 128 tiles than SMs: 64 x 64 tiles occupy the machine (four times as many, each a quarter of the work)
+    const long long tm = (M + DTile::BM - 1) / DTile::BM, tn = (N + DTile::BN - 1) / DTile::BN;
+    const long long big = lower_only ? tm * (tm + 1) / 2 : tm * tn;
+    static const int force = getenv("LDM_DGEMM_TILE") ? atoi(getenv("LDM_DGEMM_TILE")) : 0;   // development aid: 64 / 128
+    const bool small = force ? force == 64 : big < h->num_sms;
+    if (small) return launch_dgemm_t<DTileS>(h, st, A, lda, B, ldb, M, N, K, C, ldc, alpha, accumulate, lower_only);
+    return launch_dgemm_t<DTile>(h, st, A, lda, B, ldb, M, N, K, C, ldc, alpha, accumulate, lower_only);
 }
 
 extern "C" {

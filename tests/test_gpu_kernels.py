@@ -103,6 +103,8 @@ def test_zgemm_strided_output(dev):
 @pytest.mark.parametrize("M,N,K,lower,acc,pad", [
     (128, 128, 16, False, False, 0), (300, 200, 100, False, True, 0), (1000, 1000, 333, True, True, 1),
     (515, 515, 48, True, False, 0), (130, 77, 5, False, False, 3), (1, 1, 1, True, False, 1),
+    # enough 128 x 128 tiles to fill the SMs: the large tile shape (smaller products run with 64 x 64 tiles)
+    (2200, 2200, 40, True, True, 0), (1700, 1500, 24, False, True, 1),
 ])
 def test_dgemm_tn_and_mirror(dev, M, N, K, lower, acc, pad):
     rng = np.random.default_rng(M + K)
@@ -116,9 +118,11 @@ def test_dgemm_tn_and_mirror(dev, M, N, K, lower, acc, pad):
     dev.dgemm_tn(Ad, Bd, Cd, K=K, alpha=2.0, accumulate=acc, lower_only=lower)
     got = Cd.cpu().numpy()
     if lower:
+        # the lower triangle is the contract; what lies above the diagonal tiles (64 or 128 wide) is untouched
+        low = np.tril(np.ones((M, M), dtype=bool))
+        assert np.abs((got - ref) * low).max() < 1e-11 * max(1.0, np.abs(ref).max())
         tm = np.arange(M) // 128
         mask = tm[:, None] >= tm[None, :]
-        assert np.abs((got - ref) * mask).max() < 1e-11 * max(1.0, np.abs(ref).max())
         assert np.array_equal(got[~mask], C0[~mask])                   # tiles above the diagonal untouched
         dev.mirror_lower(Cd)
         full = np.tril(ref) + np.tril(ref, -1).T
