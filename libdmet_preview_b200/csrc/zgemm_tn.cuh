@@ -32,6 +32,10 @@
 // fragment -- DADDs share the FP64 pipe with the DMMAs and each one costs tensor issue slots.
 // 3M stage: A tile as above; B = 3 planes of BN rows x 64 B (8 real k in the order 0,4,1,5,2,6,3,7), 64-byte
 // swizzled by TMA; one LDS.128 per plane and column fragment delivers the words of both k-steps of the stage.
+// JP = column fragments per group of the 3M main loop: within a group the k-step loop runs outside the fragment loop,
+// so with JP = 2 (the default of the wide tiles) two DMMAs on the same accumulator are six instructions apart in the
+// source instead of three.  The pipe takes one DMMA per 16 clocks and sub-partition, but a lone warp that issues two
+// DMMAs on one accumulator back to back waits 26 (tools/dmma_probe.cu) -- the order ptxas otherwise derives.
 #pragma once
 #include <type_traits>
 
