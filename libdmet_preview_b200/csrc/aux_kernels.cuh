@@ -1035,6 +1035,164 @@ jk_tri_kernel(const double* __restrict__ eri4, const double* __restrict__ D, con
     }
 }
 
+// The same kernel with the packed density dd held in REGISTERS: thread t owns the words q = t + c T of every row, so
+// dd[q] is loaded once per CTA instead of once per row from L2 (the J pass of jk_tri_kernel is bound by the latency of
+// those loads: 8 in flight per thread, 4.5 round trips per long row).  T threads (>= 2 NP; only the first 2 NP walk
+// the K matrix) are chosen so that the column accumulators and dd -- 2 NCMAX doubles per thread -- leave room for the
+// rest: NP = 152, T = 384 gives 2 x 31 doubles.  The K walk is unrolled four-fold (four independent load / FMA chains).
+template <int NP, int T>
+__global__ void __launch_bounds__(T, 1)
+jk_tri2_kernel(const double* __restrict__ eri4, const double* __restrict__ D, const double* __restrict__ dd,
+               double* __restrict__ vj_row, double* __restrict__ jpart, double* __restrict__ kpart, int n,
+               long long npair, int with_k, int arena_words) {
+    static_assert(T >= 2 * NP, "the K walk needs at least two groups of NP threads");
+    constexpr int NG = T / NP;                                 // thread groups of the K walk
+    constexpr int NCMAX = (NP * (NP + 1) / 2 + T - 1) / T;
+    extern __shared__ __align__(16) double jkt_rows[];         // arena_words doubles: a ring of row slots
+    __shared__ double2 sD[NP];                                 // (D[i][l], D[j][l])
+    __shared__ double sY[NG][2][NP];
+    __shared__ double sJ[T / 32];
+    __shared__ __align__(8) unsigned long long bars[JKT_MAXBUF];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const long long nblk = (npair + JKT_ROWS - 1) / JKT_ROWS;
+    const long long B = nblk - 1 - blockIdx.x;                  // heaviest blocks first
+    const long long Phi = min(npair, (B + 1) * JKT_ROWS) - 1, Plo = B * JKT_ROWS;
+    const int nrows = (int)(Phi - Plo + 1);
+    const long long total = npair * npair;
+    const int slot_words = (int)((Phi + 2 * NP + 6) & ~1LL);
+    const int nbuf = max(2, min(JKT_MAXBUF, arena_words / slot_words));
+    if (t == 0) {
+        for (int x = 0; x < JKT_MAXBUF; ++x) mbar_init(smem_u32(&bars[x]), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](long long P, int b) {
+        const long long off = P * npair, a0 = off & ~1LL;
+        const int head = (int)(off - a0);
+        long long cnt = ((long long)head + P + 2) & ~1LL;
+        if (a0 + cnt > total) cnt -= 2;
+        double* buf = jkt_rows + (size_t)b * slot_words;
+        if (t == 0) {
+            fence_proxy_async_smem();
+            const uint32_t bar = smem_u32(&bars[b]);
+            mbar_expect_tx(bar, (uint32_t)(cnt * 8));
+            const uint32_t dst = smem_u32(buf);
+            for (long long c = 0; c < cnt; c += 4096)
+                bulk_load_1d(dst + (uint32_t)(c * 8), eri4 + a0 + c, (uint32_t)(min(4096LL, cnt - c) * 8), bar);
+        }
+        for (long long q = cnt - head + t; q <= P; q += T) buf[head + q] = eri4[off + q];
+    };
+
+    for (int r = 0; r < min(nbuf - 1, nrows); ++r) issue(Phi - r, r);
+    double colacc[NCMAX], ddreg[NCMAX];
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c) {
+        const long long q = t + (long long)c * T;
+        colacc[c] = 0.0;
+        ddreg[c] = q <= Phi ? dd[q] : 0.0;                           // the rows of this block end at Phi
+    }
+    __syncthreads();                                                // plain-load tail of the very last row
+    for (int r = 0; r < nrows; ++r) {
+        const long long P = Phi - r;
+        const int b = r % nbuf;
+        if (r + nbuf - 1 < nrows) issue(P - (nbuf - 1), (r + nbuf - 1) % nbuf);   // the slot row r - 1 has just left
+        int i = (int)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+        while ((long long)(i + 1) * (i + 2) / 2 <= P) ++i;
+        while ((long long)i * (i + 1) / 2 > P) --i;
+        const int j = (int)(P - (long long)i * (i + 1) / 2);
+        for (int l = t; l < NP; l += T)
+            sD[l] = l < n ? make_double2(D[(size_t)i * n + l], D[(size_t)j * n + l]) : make_double2(0.0, 0.0);
+        double* srow = jkt_rows + (size_t)b * slot_words + (int)((P * npair) & 1LL);
+        const double ddP = dd[P];
+        mbar_wait(smem_u32(&bars[b]), (uint32_t)((r / nbuf) & 1));
+        // ---- J: row dot product and column updates, no global loads ----
+        double racc = 0.0, racc2 = 0.0;
+        const int Pi = (int)P;
+#pragma unroll
+        for (int c = 0; c < NCMAX; c += 2) {
+            if (c * T > Pi) break;                                  // warp-uniform: the row ends before this chunk
+            const int q0 = t + c * T, q1 = q0 + T;
+            const double e0 = q0 <= Pi ? srow[q0] : 0.0;
+            const double e1 = (c + 1 < NCMAX && q1 <= Pi) ? srow[q1] : 0.0;
+            racc = fma(e0, ddreg[c], racc);
+            colacc[c] = fma(q0 < Pi ? e0 : 0.0, ddP, colacc[c]);
+            if (c + 1 < NCMAX) {
+                racc2 = fma(e1, ddreg[c + 1], racc2);
+                colacc[c + 1] = fma(q1 < Pi ? e1 : 0.0, ddP, colacc[c + 1]);
+            }
+        }
+        racc += racc2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+        if (lane == 0) sJ[w] = racc;
+        __syncthreads();
+        if (t == 0) {
+            double sj = 0.0;
+            for (int x = 0; x < T / 32; ++x) sj += sJ[x];
+            vj_row[P] = sj;
+        }
+        if (with_k) {
+            // the rest of packed row i is not part of the truncated matrix; the word Q = P counts half
+            const int rowend = (i + 1) * (i + 2) / 2;
+            for (int q = Pi + 1 + t; q < rowend; q += T) srow[q] = 0.0;
+            if (t == T - 1) srow[P] *= 0.5;
+            __syncthreads();
+            // K walk: NG = T / NP groups of NP threads share the l range; thread (g, k) walks row k of the symmetric
+            // matrix over its part of the l range -- M[k][l] sits at k (k + 1) / 2 + l for l <= k and at
+            // l (l + 1) / 2 + k beyond the diagonal, both conflict free across consecutive k; every lane of a warp does
+            // useful work in every trip (uniform l), (D[i][l], D[j][l]) is one broadcast 16-byte load
+            const int ne = i + 1;
+            const int g = t / NP, k = t - g * NP;
+            const int part = (ne + NG - 1) / NG;
+            const int l0 = g * part, l1 = min(ne, l0 + part);
+            double y1 = 0.0, y2 = 0.0, z1 = 0.0, z2 = 0.0;
+            if (g < NG && k < ne) {
+                int offA = k * (k + 1) / 2 + l0;                    // M[k][l], l <= k
+                int offB = l0 * (l0 + 1) / 2 + k;                   // M[l][k], l > k
+                int l = l0;
+                for (; l + 1 < l1; l += 2) {
+                    const double m0 = srow[l <= k ? offA : offB];
+                    const double m1 = srow[l + 1 <= k ? offA + 1 : offB + l + 1];
+                    const double2 d0 = sD[l], d1 = sD[l + 1];
+                    y1 = fma(m0, d0.x, y1);
+                    y2 = fma(m0, d0.y, y2);
+                    z1 = fma(m1, d1.x, z1);
+                    z2 = fma(m1, d1.y, z2);
+                    offA += 2;
+                    offB += 2 * l + 3;
+                }
+                if (l < l1) {
+                    const double m0 = srow[l <= k ? offA : offB];
+                    const double2 d0 = sD[l];
+                    y1 = fma(m0, d0.x, y1);
+                    y2 = fma(m0, d0.y, y2);
+                }
+            }
+            if (g < NG) {
+                sY[g][0][k] = y1 + z1;
+                sY[g][1][k] = y2 + z2;
+            }
+            __syncthreads();
+            for (int x = t; x < 2 * n; x += T) {
+                const int v = x >= n, kk = x - v * n;
+                double sum = sY[0][v][kk];
+#pragma unroll
+                for (int gg = 1; gg < NG; ++gg) sum += sY[gg][v][kk];
+                kpart[(P * 2 + v) * n + kk] = sum;
+            }
+        }
+        fence_proxy_async_smem();        // generic writes to this slot (zero fill, halving) before the next bulk copy
+        __syncthreads();                                            // slot, sD, sY, sJ free for the next row
+    }
+    double* jp = jpart + (size_t)B * npair;
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c) {
+        const long long q = t + (long long)c * T;
+        if (q < Phi) jp[q] = colacc[c];
+    }
+}
+
 // vj_packed[q] = vj_row[q] + sum over the row blocks B >= q / JKT_ROWS of their column partials (fixed order)
 __global__ void __launch_bounds__(256)
 jk_tri_jsum_kernel(const double* __restrict__ vj_row, const double* __restrict__ jpart,

@@ -809,6 +809,7 @@ int ldm_jk_s4_symm(ldm_handle h, void* stream, const double* eri4_d, const doubl
     jk_pack_dm_kernel<<<(unsigned)std::min<long long>((npair + 255) / 256, 1024), 256, 0, st>>>(dm_d, dd, n);
     LDM_CUDA_OK(cudaGetLastError());
     const int wk = vk_d != nullptr;
+    static const bool use_tri2 = getenv("LDM_JK_TRI2") ? atoi(getenv("LDM_JK_TRI2")) != 0 : true;
     static bool attr = false;
     if (!attr) {
         LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_tri_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -817,6 +818,8 @@ int ldm_jk_s4_symm(ldm_handle h, void* stream, const double* eri4_d, const doubl
                                          214 * 1024));
         LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_tri_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          214 * 1024));
+        LDM_CUDA_OK(cudaFuncSetAttribute((const void*)jk_tri2_kernel<152, 384>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024));
         attr = true;
     }
     if (n <= 64)
@@ -825,6 +828,9 @@ int ldm_jk_s4_symm(ldm_handle h, void* stream, const double* eri4_d, const doubl
     else if (n <= 128)
         jk_tri_kernel<128><<<(unsigned)nblk, 256, smem, st>>>(eri4_d, dm_d, dd, vj_row, jpart, kpart, n, npair, wk,
                                                              rowbuf_words);
+    else if (n <= 152 && use_tri2)      // dd in registers (LDM_JK_TRI2=0: the kernel that fetches it from L2 per row)
+        jk_tri2_kernel<152, 384><<<(unsigned)nblk, 384, smem, st>>>(eri4_d, dm_d, dd, vj_row, jpart, kpart, n, npair,
+                                                                     wk, rowbuf_words);
     else
         jk_tri_kernel<160><<<(unsigned)nblk, 320, smem, st>>>(eri4_d, dm_d, dd, vj_row, jpart, kpart, n, npair, wk,
                                                              rowbuf_words);
