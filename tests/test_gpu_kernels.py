@@ -53,6 +53,27 @@ def _zgemm_case(dev, za, zb, M, N, K, nseg, nbatch, cA, cB, acc):
     assert np.abs(Cd.cpu().numpy() - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("m3", [1, 0])
+def test_zgemm_every_width(dev, m3):
+    """the tile chooser over the whole range of N (every fragment count of both tile families, the short last n-tile,
+    two and three n-tiles), with more tiles than CTAs so that the wave-rotated tile order is exercised -- a wrong
+    pairing of tile shape and short-last shortcut would drop whole column fragments"""
+    old = dev.set_option("zgemm_3m", m3)
+    try:
+        rng = np.random.default_rng(77)
+        M, K = 9500, 11
+        A = _z(rng, 1, M, K)
+        Ad = dev.to_device(A, torch.complex128)
+        for N in sorted(set(range(1, 210, 9)) | {56, 64, 72, 80, 104, 120, 128, 150, 152, 160, 200}):
+            B = _z(rng, 1, N, K)
+            Cd = dev.empty((1, M, N), torch.complex128)
+            dev.zgemm_tn(Ad, dev.to_device(B, torch.complex128), [[0, 0, 0, 1]], Cd)
+            ref = A[0] @ B[0].conj().T
+            assert np.abs(Cd.cpu().numpy()[0] - ref).max() < 1e-11 * np.abs(ref).max(), N
+    finally:
+        dev.set_option("zgemm_3m", old)
+
+
 def test_zgemm_3m_rounding_only(dev):
     """the 3-multiplication form differs from the 4-multiplication form by rounding: both within a few ulp of
     |A||B| of an exact (integer-valued) product, and the imaginary part has no systematic cancellation error even
